@@ -1,0 +1,806 @@
+// hare_abi.cu -- implementation of include/hare_b200.h: handles, device buffers, streams,
+// kernel launches.  No CPU fallback: every compute entry point needs a usable CUDA device.
+#include "../../include/hare_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_build.hpp"
+#include "kernels.cuh"
+
+using namespace hare;
+
+// ---------------------------------------------------------------------------------------
+// errors / globals
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{ 0 };
+static std::mutex g_mu;
+static std::vector<int> g_devices;   // empty = not initialised
+static bool g_host_only = false;     // hare_init(NULL, -1): build-time tooling without a device
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(HARE_ERR_CUDA, b_);                                                        \
+        }                                                                                          \
+    } while (0)
+
+static int ensure_init() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_host_only || !g_devices.empty()) return HARE_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(HARE_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (hare_b200 has no CPU fallback)");
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    g_devices.push_back(cur);
+    return HARE_OK;
+}
+
+struct DevInfo { int sms = 0; };
+static DevInfo dev_info(int dev) {
+    DevInfo d; cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev); return d;
+}
+
+template <class T>
+static cudaError_t dmalloc(T** p, size_t n) { *p = nullptr; return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+// ---------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------
+struct hare_topo_s {
+    HostTopo host;
+    std::vector<int> devs;
+    std::vector<PolyRec*> d_polys;   // one replica per device
+};
+
+struct PartDev {
+    int dev = 0, sms = 0;
+    cudaStream_t stream[2] = { nullptr, nullptr };
+    const PolyRec* polys = nullptr;
+    // voxel grid
+    uint2* cells = nullptr; uint32_t* cell_poly = nullptr; uint32_t* occ = nullptr; uint32_t* cell_offset = nullptr;
+    // trees
+    void* nodes = nullptr; uint32_t* lists = nullptr;
+    // staging (per stream), sized for `cap` rays
+    int64_t cap = 0;
+    double *s_o[2] = {}, *s_d[2] = {}, *s_t[2] = {}, *s_xyz[2] = {}, *s_uv[2] = {}, *s_om[2] = {};
+    int32_t *s_o1[2] = {}, *s_o2[2] = {}, *s_rid[2] = {}, *s_pid[2] = {};
+    // chain staging
+    int64_t ccap = 0, celems = 0;
+    int32_t* c_evpid[2] = {}; double* c_evt[2] = {}; int32_t* c_ns[2] = {};
+    unsigned long long* counters = nullptr;   // 4 counters + total_shots
+    size_t bytes = 0;
+};
+
+struct hare_part_s {
+    int kind = 0;
+    hare_topo_s* topo = nullptr;
+    std::vector<PartDev> dev;
+    std::mutex mu;
+    // voxel grid
+    double obox[6] = {}, vd[3] = {}; int ct[3] = {}; int64_t npairs = 0;
+    // trees (host copies, for *_download and *_info)
+    OctTree oct; KdTree kd;
+};
+
+static void free_partdev(PartDev& d) {
+    cudaSetDevice(d.dev);
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(d.s_o[s]); cudaFree(d.s_d[s]); cudaFree(d.s_t[s]); cudaFree(d.s_xyz[s]); cudaFree(d.s_uv[s]); cudaFree(d.s_om[s]);
+        cudaFree(d.s_o1[s]); cudaFree(d.s_o2[s]); cudaFree(d.s_rid[s]); cudaFree(d.s_pid[s]);
+        cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
+        if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
+    }
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.counters);
+}
+
+static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
+    d.dev = dev; d.polys = polys; d.sms = dev_info(dev).sms;
+    CK(cudaSetDevice(dev));
+    for (int s = 0; s < 2; ++s) CK(cudaStreamCreateWithFlags(&d.stream[s], cudaStreamNonBlocking));
+    CK(dmalloc(&d.counters, 8));
+    CK(cudaMemset(d.counters, 0, 8 * sizeof(unsigned long long)));
+    return HARE_OK;
+}
+
+static int ensure_staging(PartDev& d, int64_t n) {
+    if (n <= d.cap) return HARE_OK;
+    CK(cudaSetDevice(d.dev));
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(d.s_o[s]); cudaFree(d.s_d[s]); cudaFree(d.s_t[s]); cudaFree(d.s_xyz[s]); cudaFree(d.s_uv[s]); cudaFree(d.s_om[s]);
+        cudaFree(d.s_o1[s]); cudaFree(d.s_o2[s]); cudaFree(d.s_rid[s]); cudaFree(d.s_pid[s]);
+        CK(dmalloc(&d.s_o[s], 3 * n)); CK(dmalloc(&d.s_d[s], 3 * n)); CK(dmalloc(&d.s_t[s], n)); CK(dmalloc(&d.s_xyz[s], 3 * n));
+        CK(dmalloc(&d.s_uv[s], 2 * n)); CK(dmalloc(&d.s_om[s], 3 * n));
+        CK(dmalloc(&d.s_o1[s], n)); CK(dmalloc(&d.s_o2[s], n)); CK(dmalloc(&d.s_rid[s], n)); CK(dmalloc(&d.s_pid[s], n));
+    }
+    d.cap = n;
+    return HARE_OK;
+}
+
+static int ensure_chain_staging(PartDev& d, int64_t n, int order) {
+    if (n * order <= d.celems && n <= d.ccap) return HARE_OK;
+    CK(cudaSetDevice(d.dev));
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
+        CK(dmalloc(&d.c_evpid[s], (size_t)n * order)); CK(dmalloc(&d.c_evt[s], (size_t)n * order)); CK(dmalloc(&d.c_ns[s], n));
+    }
+    d.ccap = n; d.celems = n * order;
+    return HARE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------
+extern "C" const char* hare_version(void) { return "hare_b200 0.1 (sm_100a)"; }
+extern "C" const char* hare_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t hare_launch_count(void) { return g_launches.load(); }
+
+extern "C" int hare_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int hare_init(const int* device_ids, int n_devices) {
+    if (n_devices == -1) {   // host-only handles: builders, info and download work; every compute call fails
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_devices.clear(); g_host_only = true;
+        return HARE_OK;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(HARE_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (hare_b200 has no CPU fallback)");
+    std::vector<int> devs;
+    if (n_devices <= 0) {
+        int cur = 0; CK(cudaGetDevice(&cur)); devs.push_back(cur);
+    } else {
+        for (int i = 0; i < n_devices; ++i) {
+            int id = device_ids ? device_ids[i] : i;
+            if (id < 0 || id >= n) return fail(HARE_ERR_INVALID, "hare_init: device id out of range");
+            devs.push_back(id);
+        }
+    }
+    for (int id : devs) {
+        cudaDeviceProp p;
+        CK(cudaGetDeviceProperties(&p, id));
+        if (p.major < 10) return fail(HARE_ERR_CUDA, "hare_init: device is not sm_100 or newer; this library ships sm_100a code only");
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_devices = devs; g_host_only = false;
+    return HARE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Topology
+// ---------------------------------------------------------------------------------------
+extern "C" int hare_topology_ingest(const double* raw_verts, const int32_t* vcount, int64_t P, const double minpt[3], const double maxpt[3],
+                                    double* verts_out, double* normals_out, double minmax_out[6], int64_t* vertex_count_out) {
+    if (!raw_verts || !vcount || P < 0 || !minpt || !maxpt || !verts_out || !normals_out || !minmax_out)
+        return fail(HARE_ERR_INVALID, "hare_topology_ingest: null argument");
+    int r = topology_ingest(raw_verts, vcount, P, minpt, maxpt, verts_out, normals_out, minmax_out, vertex_count_out);
+    if (r == -3) return fail(HARE_ERR_UNSUPPORTED, "Hare Does not yet support polygons of more than 4 sides.");
+    return r;
+}
+
+extern "C" int hare_topology_create(const double* verts, const double* normals, const int32_t* vcount, int64_t P,
+                                    const double minmax[6], hare_topo_t* out) {
+    if (!verts || !normals || !vcount || P <= 0 || !minmax || !out) return fail(HARE_ERR_INVALID, "hare_topology_create: bad argument");
+    if (P > 0x7fffffffLL) return fail(HARE_ERR_INVALID, "hare_topology_create: more than 2^31-1 polygons");
+    int rc = ensure_init();
+    if (rc) return rc;
+    for (int64_t i = 0; i < P; ++i)
+        if (vcount[i] != 3 && vcount[i] != 4) return fail(HARE_ERR_UNSUPPORTED, "Hare Does not yet support polygons of more than 4 sides.");
+    hare_topo_s* t = new hare_topo_s();
+    t->host.P = P;
+    t->host.verts.assign(verts, verts + 12 * P);
+    t->host.normals.assign(normals, normals + 3 * P);
+    t->host.vcount.assign(vcount, vcount + P);
+    std::memcpy(t->host.minmax, minmax, 6 * sizeof(double));
+    for (int a = 0; a < 3; ++a) { t->host.vmin[a] = INFINITY; t->host.vmax[a] = -INFINITY; }
+    std::vector<PolyRec> recs((size_t)P);
+    for (int64_t i = 0; i < P; ++i) {
+        for (int k = 0; k < 12; ++k) recs[i].v[k] = verts[12 * i + k];
+        if (vcount[i] == 3) for (int a = 0; a < 3; ++a) recs[i].v[9 + a] = verts[12 * i + 6 + a];
+        for (int a = 0; a < 3; ++a) recs[i].v[12 + a] = normals[3 * i + a];
+        recs[i].v[15] = (double)vcount[i];
+        for (int k = 0; k < vcount[i]; ++k)
+            for (int a = 0; a < 3; ++a) {
+                double c = verts[12 * i + 3 * k + a];
+                if (c < t->host.vmin[a]) t->host.vmin[a] = c;
+                if (c > t->host.vmax[a]) t->host.vmax[a] = c;
+            }
+    }
+    { std::lock_guard<std::mutex> lk(g_mu); t->devs = g_devices; }
+    for (int dev : t->devs) {
+        PolyRec* d = nullptr;
+        cudaError_t e = cudaSetDevice(dev);
+        if (e == cudaSuccess) e = dmalloc(&d, (size_t)P);
+        if (e == cudaSuccess) e = cudaMemcpy(d, recs.data(), (size_t)P * sizeof(PolyRec), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            for (size_t k = 0; k < t->d_polys.size(); ++k) { cudaSetDevice(t->devs[k]); cudaFree(t->d_polys[k]); }
+            cudaFree(d); delete t;
+            return fail(HARE_ERR_CUDA, std::string("hare_topology_create: ") + cudaGetErrorString(e));
+        }
+        t->d_polys.push_back(d);
+    }
+    *out = t;
+    return HARE_OK;
+}
+
+extern "C" int64_t hare_topology_polygon_count(hare_topo_t t) { return t ? t->host.P : -1; }
+
+extern "C" int hare_topology_destroy(hare_topo_t t) {
+    if (!t) return HARE_OK;
+    for (size_t k = 0; k < t->d_polys.size(); ++k) { cudaSetDevice(t->devs[k]); cudaFree(t->d_polys[k]); }
+    delete t;
+    return HARE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Voxel_Grid
+// ---------------------------------------------------------------------------------------
+static void vg_bounds(const HostTopo& M, double obox[6]) {
+    // Voxel_Grid.cs:50-75 for a single topology: MinPT/MaxPT = Model.Min/Max -/+ Epsilon, OBox = that -/+ 0.1
+    const double Epsilon = 0.001;
+    for (int a = 0; a < 3; ++a) {
+        double MaxPT = -INFINITY, MinPT = INFINITY;
+        if ((M.minmax[3 + a] + 0.01) > MaxPT) MaxPT = (M.minmax[3 + a] + Epsilon);
+        if ((M.minmax[a] - 0.01) < MinPT) MinPT = (M.minmax[a] - Epsilon);
+        obox[a] = MinPT - .1;
+        obox[3 + a] = MaxPT + .1;
+    }
+}
+
+static VGrid make_vgrid(const hare_part_s* p, const PartDev& d) {
+    VGrid g;
+    g.ominx = p->obox[0]; g.ominy = p->obox[1]; g.ominz = p->obox[2]; g.omaxx = p->obox[3]; g.omaxy = p->obox[4]; g.omaxz = p->obox[5];
+    g.vdx = p->vd[0]; g.vdy = p->vd[1]; g.vdz = p->vd[2];
+    g.nx = p->ct[0]; g.ny = p->ct[1]; g.nz = p->ct[2];
+    g.cells = d.cells; g.cell_poly = d.cell_poly; g.occ = d.occ;
+    return g;
+}
+
+static int new_part(hare_topo_t topo, int kind, hare_part_s** out) {
+    hare_part_s* p = new hare_part_s();
+    p->kind = kind; p->topo = topo;
+    p->dev.resize(topo->devs.size());
+    for (size_t k = 0; k < topo->devs.size(); ++k) {
+        int rc = init_partdev(p->dev[k], topo->devs[k], topo->d_polys[k]);
+        if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    }
+    *out = p;
+    return HARE_OK;
+}
+
+static int vg_set_dims(hare_part_s* p, const double obox[6], const int32_t ct[3]) {
+    std::memcpy(p->obox, obox, 6 * sizeof(double));
+    for (int a = 0; a < 3; ++a) {
+        p->ct[a] = ct[a];
+        p->vd[a] = (obox[3 + a] - obox[a]) / ct[a];   // VoxelDims = BoxDims / VoxelCt  Voxel_Grid.cs:85-86
+    }
+    return HARE_OK;
+}
+
+static int scan_u32(const uint32_t* in, int64_t n, uint32_t* out /* n + 1 */, uint32_t* tile_tmp, cudaStream_t st) {
+    const int64_t tiles = (n + HARE_SCAN_TILE - 1) / HARE_SCAN_TILE;
+    scan_tile_sums<<<(unsigned)tiles, 1024, 0, st>>>(in, n, tile_tmp);
+    scan_tile_offsets<<<1, 1024, 0, st>>>(tile_tmp, tiles, out + n);
+    scan_tiles<<<(unsigned)tiles, 1024, 0, st>>>(in, n, tile_tmp, out);
+    g_launches += 3;
+    CK(cudaGetLastError());
+    return HARE_OK;
+}
+
+extern "C" int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* out) {
+    if (!topo || !out || domain < 1 || domain > 1290) return fail(HARE_ERR_INVALID, "hare_voxelgrid_build: bad argument (1 <= Domain <= 1290)");
+    if (topo->devs.empty()) return fail(HARE_ERR_CUDA, "hare_voxelgrid_build: host-only handle, no CUDA device (hare_b200 has no CPU fallback)");
+    hare_part_s* p = nullptr;
+    int rc = new_part(topo, HARE_VOXEL_GRID, &p);
+    if (rc) return rc;
+    double obox[6]; vg_bounds(topo->host, obox);
+    const int32_t ct[3] = { domain, domain, domain };
+    vg_set_dims(p, obox, ct);
+    const int64_t ncells = (int64_t)domain * domain * domain;
+    const int64_t P = topo->host.P;
+    for (PartDev& d : p->dev) {
+        auto body = [&]() -> int {
+            CK(cudaSetDevice(d.dev));
+            cudaStream_t st = d.stream[0];
+            uint32_t *count = nullptr, *cursor = nullptr, *tiles = nullptr;
+            CK(dmalloc(&count, ncells)); CK(dmalloc(&cursor, ncells));
+            CK(dmalloc(&tiles, (ncells + HARE_SCAN_TILE - 1) / HARE_SCAN_TILE + 1));
+            CK(dmalloc(&d.cell_offset, ncells + 1)); CK(dmalloc(&d.cells, ncells)); CK(dmalloc(&d.occ, (ncells + 31) / 32 + 1));
+            CK(cudaMemsetAsync(count, 0, ncells * 4, st)); CK(cudaMemsetAsync(cursor, 0, ncells * 4, st));
+            VGBuild g = { obox[0], obox[1], obox[2], p->vd[0], p->vd[1], p->vd[2], domain, domain, domain };
+            const int blocks = d.sms * 8;
+            vg_bin_kernel<0><<<blocks, 256, 0, st>>>(g, d.polys, P, count, nullptr, nullptr, nullptr);
+            ++g_launches;
+            CK(cudaGetLastError());
+            int r = scan_u32(count, ncells, d.cell_offset, tiles, st);
+            if (r) return r;
+            uint32_t total = 0;
+            CK(cudaMemcpyAsync(&total, d.cell_offset + ncells, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            p->npairs = total;
+            CK(dmalloc(&d.cell_poly, (size_t)total));
+            vg_bin_kernel<1><<<blocks, 256, 0, st>>>(g, d.polys, P, nullptr, d.cell_offset, cursor, d.cell_poly);
+            vg_finish_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(d.cell_offset, count, ncells, d.cell_poly, d.cells, d.occ);
+            g_launches += 2;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+            cudaFree(count); cudaFree(cursor); cudaFree(tiles);
+            d.bytes = (size_t)ncells * 12 + (size_t)total * 4 + (size_t)ncells / 8;
+            return HARE_OK;
+        };
+        rc = body();
+        if (rc) { for (auto& dd : p->dev) free_partdev(dd); delete p; return rc; }
+    }
+    *out = p;
+    return HARE_OK;
+}
+
+extern "C" int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], const int32_t ct[3],
+                                     const uint32_t* cell_offset, const uint32_t* cell_poly, hare_part_t* out) {
+    if (!topo || !obox || !ct || !cell_offset || !out || ct[0] < 1 || ct[1] < 1 || ct[2] < 1)
+        return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: bad argument");
+    const int64_t ncells = (int64_t)ct[0] * ct[1] * ct[2];
+    if (ncells > 0x7fffffffLL) return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: more than 2^31-1 cells");
+    const uint32_t total = cell_offset[ncells];
+    if (total && !cell_poly) return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: cell_poly is null");
+    for (uint32_t k = 0; k < total; ++k)
+        if ((int64_t)cell_poly[k] >= topo->host.P) return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: polygon index out of range");
+    hare_part_s* p = nullptr;
+    int rc = new_part(topo, HARE_VOXEL_GRID, &p);
+    if (rc) return rc;
+    vg_set_dims(p, obox, ct);
+    p->npairs = total;
+    for (PartDev& d : p->dev) {
+        auto body = [&]() -> int {
+            CK(cudaSetDevice(d.dev));
+            cudaStream_t st = d.stream[0];
+            CK(dmalloc(&d.cell_offset, ncells + 1)); CK(dmalloc(&d.cells, ncells)); CK(dmalloc(&d.occ, (ncells + 31) / 32 + 1));
+            CK(dmalloc(&d.cell_poly, (size_t)total));
+            CK(cudaMemcpyAsync(d.cell_offset, cell_offset, (ncells + 1) * 4, cudaMemcpyHostToDevice, st));
+            if (total) CK(cudaMemcpyAsync(d.cell_poly, cell_poly, (size_t)total * 4, cudaMemcpyHostToDevice, st));
+            vg_pack_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(d.cell_offset, ncells, d.cells, d.occ);
+            ++g_launches;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+            d.bytes = (size_t)ncells * 12 + (size_t)total * 4 + (size_t)ncells / 8;
+            return HARE_OK;
+        };
+        rc = body();
+        if (rc) { for (auto& dd : p->dev) free_partdev(dd); delete p; return rc; }
+    }
+    *out = p;
+    return HARE_OK;
+}
+
+extern "C" int hare_voxelgrid_info(hare_part_t p, double obox[6], double voxeldims[3], int32_t ct[3], int64_t* npairs) {
+    if (!p || p->kind != HARE_VOXEL_GRID) return fail(HARE_ERR_INVALID, "hare_voxelgrid_info: not a Voxel_Grid");
+    if (obox) std::memcpy(obox, p->obox, 6 * sizeof(double));
+    if (voxeldims) std::memcpy(voxeldims, p->vd, 3 * sizeof(double));
+    if (ct) std::memcpy(ct, p->ct, 3 * sizeof(int32_t));
+    if (npairs) *npairs = p->npairs;
+    return HARE_OK;
+}
+
+extern "C" int hare_voxelgrid_download(hare_part_t p, uint32_t* cell_offset, uint32_t* cell_poly) {
+    if (!p || p->kind != HARE_VOXEL_GRID) return fail(HARE_ERR_INVALID, "hare_voxelgrid_download: not a Voxel_Grid");
+    if (p->dev.empty()) return fail(HARE_ERR_CUDA, "hare_voxelgrid_download: host-only handle");
+    PartDev& d = p->dev[0];
+    const int64_t ncells = (int64_t)p->ct[0] * p->ct[1] * p->ct[2];
+    CK(cudaSetDevice(d.dev));
+    if (cell_offset) CK(cudaMemcpy(cell_offset, d.cell_offset, (ncells + 1) * 4, cudaMemcpyDeviceToHost));
+    if (cell_poly && p->npairs) CK(cudaMemcpy(cell_poly, d.cell_poly, (size_t)p->npairs * 4, cudaMemcpyDeviceToHost));
+    return HARE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Octree
+// ---------------------------------------------------------------------------------------
+static int oct_depth(const OctTree& t) {
+    int best = 0;
+    std::vector<std::pair<int, int>> st; st.push_back({ 0, 0 });
+    while (!st.empty()) {
+        auto [n, dpt] = st.back(); st.pop_back();
+        best = std::max(best, dpt);
+        if (t.first_child[n] >= 0) for (int i = 0; i < 8; ++i) st.push_back({ t.first_child[n] + i, dpt + 1 });
+    }
+    return best;
+}
+
+static int oct_to_device(hare_part_s* p) {
+    const OctTree& t = p->oct;
+    const size_t N = t.first_child.size();
+    if (oct_depth(t) >= HARE_OCT_MAXLVL) return fail(HARE_ERR_UNSUPPORTED, "octree deeper than HARE_OCT_MAXLVL levels");
+    std::vector<OctNode> nodes(N);
+    for (size_t i = 0; i < N; ++i) {
+        OctNode& n = nodes[i];
+        n.mnx = t.box[6 * i]; n.mny = t.box[6 * i + 1]; n.mnz = t.box[6 * i + 2]; n.mxx = t.box[6 * i + 3]; n.mxy = t.box[6 * i + 4]; n.mxz = t.box[6 * i + 5];
+        n.first_child = t.first_child[i]; n.list_off = t.list_off[i]; n.list_cnt = t.list_cnt[i]; n.pad = 0;
+    }
+    for (PartDev& d : p->dev) {
+        CK(cudaSetDevice(d.dev));
+        OctNode* dn = nullptr;
+        CK(dmalloc(&dn, N)); d.nodes = dn;
+        CK(dmalloc(&d.lists, t.polys.size()));
+        CK(cudaMemcpy(dn, nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
+        if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
+        d.bytes = N * sizeof(OctNode) + t.polys.size() * 4;
+    }
+    return HARE_OK;
+}
+
+extern "C" int hare_octree_build(hare_topo_t topo, int maxDepth, int maxPolys, hare_part_t* out) {
+    if (!topo || !out || maxDepth < 0 || maxDepth >= HARE_OCT_MAXLVL) return fail(HARE_ERR_INVALID, "hare_octree_build: bad argument");
+    hare_part_s* p = nullptr;
+    int rc = new_part(topo, HARE_OCTREE, &p);
+    if (rc) return rc;
+    build_octree(topo->host, maxDepth, maxPolys, p->oct);
+    rc = oct_to_device(p);
+    if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    *out = p;
+    return HARE_OK;
+}
+
+extern "C" int hare_octree_upload(hare_topo_t topo, const double* node_box, const int32_t* first_child,
+                                  const uint32_t* list_off, const uint32_t* list_cnt, const uint32_t* polys,
+                                  int64_t n_nodes, int64_t n_list, hare_part_t* out) {
+    if (!topo || !node_box || !first_child || !list_off || !list_cnt || n_nodes < 1 || n_list < 0 || !out || (n_list && !polys))
+        return fail(HARE_ERR_INVALID, "hare_octree_upload: bad argument");
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        if (first_child[i] >= 0 && (int64_t)first_child[i] + 8 > n_nodes) return fail(HARE_ERR_INVALID, "hare_octree_upload: child index out of range");
+        if (first_child[i] < 0 && (int64_t)list_off[i] + list_cnt[i] > n_list) return fail(HARE_ERR_INVALID, "hare_octree_upload: list range out of bounds");
+    }
+    for (int64_t k = 0; k < n_list; ++k) if ((int64_t)polys[k] >= topo->host.P) return fail(HARE_ERR_INVALID, "hare_octree_upload: polygon index out of range");
+    hare_part_s* p = nullptr;
+    int rc = new_part(topo, HARE_OCTREE, &p);
+    if (rc) return rc;
+    p->oct.box.assign(node_box, node_box + 6 * n_nodes);
+    p->oct.first_child.assign(first_child, first_child + n_nodes);
+    p->oct.list_off.assign(list_off, list_off + n_nodes);
+    p->oct.list_cnt.assign(list_cnt, list_cnt + n_nodes);
+    if (n_list) p->oct.polys.assign(polys, polys + n_list);
+    p->oct.depth = oct_depth(p->oct);
+    rc = oct_to_device(p);
+    if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    *out = p;
+    return HARE_OK;
+}
+
+extern "C" int hare_octree_info(hare_part_t p, int64_t* n_nodes, int64_t* n_list, int64_t* lost, int32_t* depth) {
+    if (!p || p->kind != HARE_OCTREE) return fail(HARE_ERR_INVALID, "hare_octree_info: not an Octree");
+    if (n_nodes) *n_nodes = (int64_t)p->oct.first_child.size();
+    if (n_list) *n_list = (int64_t)p->oct.polys.size();
+    if (lost) *lost = p->oct.lost;
+    if (depth) *depth = p->oct.depth;
+    return HARE_OK;
+}
+
+extern "C" int hare_octree_download(hare_part_t p, double* node_box, int32_t* first_child, uint32_t* list_off, uint32_t* list_cnt, uint32_t* polys) {
+    if (!p || p->kind != HARE_OCTREE) return fail(HARE_ERR_INVALID, "hare_octree_download: not an Octree");
+    const OctTree& t = p->oct;
+    if (node_box) std::memcpy(node_box, t.box.data(), t.box.size() * 8);
+    if (first_child) std::memcpy(first_child, t.first_child.data(), t.first_child.size() * 4);
+    if (list_off) std::memcpy(list_off, t.list_off.data(), t.list_off.size() * 4);
+    if (list_cnt) std::memcpy(list_cnt, t.list_cnt.data(), t.list_cnt.size() * 4);
+    if (polys && !t.polys.empty()) std::memcpy(polys, t.polys.data(), t.polys.size() * 4);
+    return HARE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// KDTree
+// ---------------------------------------------------------------------------------------
+static int kd_depth(const KdTree& t) {
+    int best = 0;
+    std::vector<std::pair<int, int>> st; st.push_back({ 0, 0 });
+    while (!st.empty()) {
+        auto [n, dpt] = st.back(); st.pop_back();
+        best = std::max(best, dpt);
+        if (t.left[n] >= 0) { st.push_back({ t.left[n], dpt + 1 }); st.push_back({ t.left[n] + 1, dpt + 1 }); }
+    }
+    return best;
+}
+
+static int kd_to_device(hare_part_s* p) {
+    const KdTree& t = p->kd;
+    const size_t N = t.axis.size();
+    if (kd_depth(t) + 2 > HARE_KD_MAXSTACK) return fail(HARE_ERR_UNSUPPORTED, "kd-tree deeper than HARE_KD_MAXSTACK allows");
+    std::vector<KdNode> nodes(N);
+    for (size_t i = 0; i < N; ++i) {
+        KdNode& n = nodes[i];
+        n.mnx = t.box[6 * i]; n.mny = t.box[6 * i + 1]; n.mnz = t.box[6 * i + 2]; n.mxx = t.box[6 * i + 3]; n.mxy = t.box[6 * i + 4]; n.mxz = t.box[6 * i + 5];
+        n.left = t.left[i]; n.axis = t.left[i] >= 0 ? t.axis[i] : 0;
+        if (t.left[i] >= 0) n.split = t.split[i];
+        else { uint64_t bits = (uint64_t)t.list_off[i] | ((uint64_t)t.list_cnt[i] << 32); std::memcpy(&n.split, &bits, 8); }
+    }
+    for (PartDev& d : p->dev) {
+        CK(cudaSetDevice(d.dev));
+        KdNode* dn = nullptr;
+        CK(dmalloc(&dn, N)); d.nodes = dn;
+        CK(dmalloc(&d.lists, t.polys.size()));
+        CK(cudaMemcpy(dn, nodes.data(), N * sizeof(KdNode), cudaMemcpyHostToDevice));
+        if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
+        d.bytes = N * sizeof(KdNode) + t.polys.size() * 4;
+    }
+    return HARE_OK;
+}
+
+extern "C" int hare_kdtree_build(hare_topo_t topo, int maxDepth, int maxPolys, hare_part_t* out) {
+    if (!topo || !out || maxDepth < 0 || maxDepth + 2 > HARE_KD_MAXSTACK) return fail(HARE_ERR_INVALID, "hare_kdtree_build: bad argument");
+    hare_part_s* p = nullptr;
+    int rc = new_part(topo, HARE_KDTREE, &p);
+    if (rc) return rc;
+    build_kdtree(topo->host, maxDepth, maxPolys, p->kd);
+    rc = kd_to_device(p);
+    if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    *out = p;
+    return HARE_OK;
+}
+
+extern "C" int hare_kdtree_upload(hare_topo_t topo, const double* node_box, const double* split, const int32_t* axis, const int32_t* left,
+                                  const uint32_t* list_off, const uint32_t* list_cnt, const uint32_t* polys,
+                                  int64_t n_nodes, int64_t n_list, hare_part_t* out) {
+    if (!topo || !node_box || !split || !axis || !left || !list_off || !list_cnt || n_nodes < 1 || n_list < 0 || !out || (n_list && !polys))
+        return fail(HARE_ERR_INVALID, "hare_kdtree_upload: bad argument");
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        if (left[i] >= 0 && ((int64_t)left[i] + 2 > n_nodes || axis[i] < 0 || axis[i] > 2)) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: bad internal node");
+        if (left[i] < 0 && (int64_t)list_off[i] + list_cnt[i] > n_list) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: list range out of bounds");
+    }
+    for (int64_t k = 0; k < n_list; ++k) if ((int64_t)polys[k] >= topo->host.P) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: polygon index out of range");
+    hare_part_s* p = nullptr;
+    int rc = new_part(topo, HARE_KDTREE, &p);
+    if (rc) return rc;
+    p->kd.box.assign(node_box, node_box + 6 * n_nodes);
+    p->kd.split.assign(split, split + n_nodes);
+    p->kd.axis.assign(axis, axis + n_nodes);
+    p->kd.left.assign(left, left + n_nodes);
+    p->kd.list_off.assign(list_off, list_off + n_nodes);
+    p->kd.list_cnt.assign(list_cnt, list_cnt + n_nodes);
+    if (n_list) p->kd.polys.assign(polys, polys + n_list);
+    p->kd.depth = kd_depth(p->kd);
+    rc = kd_to_device(p);
+    if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    *out = p;
+    return HARE_OK;
+}
+
+extern "C" int hare_kdtree_info(hare_part_t p, int64_t* n_nodes, int64_t* n_list, int32_t* depth) {
+    if (!p || p->kind != HARE_KDTREE) return fail(HARE_ERR_INVALID, "hare_kdtree_info: not a KDTree");
+    if (n_nodes) *n_nodes = (int64_t)p->kd.axis.size();
+    if (n_list) *n_list = (int64_t)p->kd.polys.size();
+    if (depth) *depth = p->kd.depth;
+    return HARE_OK;
+}
+
+extern "C" int hare_kdtree_download(hare_part_t p, double* node_box, double* split, int32_t* axis, int32_t* left,
+                                    uint32_t* list_off, uint32_t* list_cnt, uint32_t* polys) {
+    if (!p || p->kind != HARE_KDTREE) return fail(HARE_ERR_INVALID, "hare_kdtree_download: not a KDTree");
+    const KdTree& t = p->kd;
+    if (node_box) std::memcpy(node_box, t.box.data(), t.box.size() * 8);
+    if (split) std::memcpy(split, t.split.data(), t.split.size() * 8);
+    if (axis) std::memcpy(axis, t.axis.data(), t.axis.size() * 4);
+    if (left) std::memcpy(left, t.left.data(), t.left.size() * 4);
+    if (list_off) std::memcpy(list_off, t.list_off.data(), t.list_off.size() * 4);
+    if (list_cnt) std::memcpy(list_cnt, t.list_cnt.data(), t.list_cnt.size() * 4);
+    if (polys && !t.polys.empty()) std::memcpy(polys, t.polys.data(), t.polys.size() * 4);
+    return HARE_OK;
+}
+
+extern "C" int hare_part_kind(hare_part_t p) { return p ? p->kind : HARE_ERR_INVALID; }
+extern "C" int64_t hare_part_device_bytes(hare_part_t p) { return (p && !p->dev.empty()) ? (int64_t)p->dev[0].bytes : -1; }
+
+extern "C" int hare_part_destroy(hare_part_t p) {
+    if (!p) return HARE_OK;
+    for (auto& d : p->dev) free_partdev(d);
+    delete p;
+    return HARE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Shoot
+// ---------------------------------------------------------------------------------------
+struct ShootArgs {
+    const double *o, *d; const int32_t *o1, *o2, *rid; int64_t N;
+    double *t, *xyz; int32_t* pid; double *uv, *om; unsigned long long* counters;
+};
+
+template <class PART>
+static int launch_shoot_t(const PART& part, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
+    if (a.N <= 0) return HARE_OK;
+    const int threads = 128;
+    int64_t blocks = std::min<int64_t>((a.N + threads - 1) / threads, (int64_t)d.sms * 16);
+    if (a.counters)
+        shoot_kernel<PART, true><<<(unsigned)blocks, threads, 0, st>>>(part, d.polys, a.o, a.d, a.o1, a.o2, a.rid, a.N, a.t, a.xyz, a.pid, a.uv, a.om, a.counters);
+    else
+        shoot_kernel<PART, false><<<(unsigned)blocks, threads, 0, st>>>(part, d.polys, a.o, a.d, a.o1, a.o2, a.rid, a.N, a.t, a.xyz, a.pid, a.uv, a.om, nullptr);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return HARE_OK;
+}
+
+static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
+    switch (p->kind) {
+        case HARE_VOXEL_GRID: return launch_shoot_t(make_vgrid(p, d), d, a, st);
+        case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, p->oct.depth }; return launch_shoot_t(t, d, a, st); }
+        case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, p->kd.depth }; return launch_shoot_t(t, d, a, st); }
+    }
+    return fail(HARE_ERR_INVALID, "unknown partition kind");
+}
+
+struct ChainArgs {
+    const double *o, *d; int64_t N; int order;
+    int32_t* ev_pid; double* ev_t; double *fin_o, *fin_d; int32_t* nshots;
+    unsigned long long *total, *counters;
+};
+
+template <class PART>
+static int launch_chain_t(const PART& part, const PartDev& d, const ChainArgs& a, cudaStream_t st) {
+    if (a.N <= 0) return HARE_OK;
+    const int threads = 128;
+    int64_t blocks = std::min<int64_t>((a.N + threads - 1) / threads, (int64_t)d.sms * 16);
+    if (a.counters)
+        chain_kernel<PART, true><<<(unsigned)blocks, threads, 0, st>>>(part, d.polys, a.o, a.d, a.N, a.order, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters);
+    else
+        chain_kernel<PART, false><<<(unsigned)blocks, threads, 0, st>>>(part, d.polys, a.o, a.d, a.N, a.order, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, nullptr);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return HARE_OK;
+}
+
+static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cudaStream_t st) {
+    switch (p->kind) {
+        case HARE_VOXEL_GRID: return launch_chain_t(make_vgrid(p, d), d, a, st);
+        case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, p->oct.depth }; return launch_chain_t(t, d, a, st); }
+        case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, p->kd.depth }; return launch_chain_t(t, d, a, st); }
+    }
+    return fail(HARE_ERR_INVALID, "unknown partition kind");
+}
+
+static const int64_t kChunk = 1 << 20;   // rays per pipelined chunk of the host-buffer entry points
+
+extern "C" int hare_shoot_batch(hare_part_t p, const double* o, const double* d,
+                                const int32_t* origin1, const int32_t* origin2, const int32_t* ray_id, int64_t N,
+                                double* t, double* xyz, int32_t* poly_id, double* uv, double* o_moved, uint64_t* counters) {
+    if (!p || N < 0 || (N && (!o || !d || !poly_id))) return fail(HARE_ERR_INVALID, "hare_shoot_batch: bad argument");
+    std::lock_guard<std::mutex> lk(p->mu);
+    const int G = (int)p->dev.size();
+    if (G == 0) return fail(HARE_ERR_CUDA, "hare_shoot_batch: host-only handle, no CUDA device (hare_b200 has no CPU fallback)");
+    if (counters) std::memset(counters, 0, HARE_CNT_N * sizeof(uint64_t));
+    // block-shard the batch over the devices; per device, pipeline chunks over two streams
+    for (int g = 0; g < G; ++g) {
+        PartDev& dv = p->dev[g];
+        const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
+        if (r1 <= r0) continue;
+        int rc = ensure_staging(dv, std::min<int64_t>(kChunk, r1 - r0));
+        if (rc) return rc;
+        CK(cudaSetDevice(dv.dev));
+        if (counters) CK(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
+        if (counters) CK(cudaStreamSynchronize(dv.stream[0]));
+        int s = 0;
+        for (int64_t c0 = r0; c0 < r1; c0 += kChunk, s ^= 1) {
+            const int64_t n = std::min<int64_t>(kChunk, r1 - c0);
+            cudaStream_t st = dv.stream[s];
+            CK(cudaMemcpyAsync(dv.s_o[s], o + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(dv.s_d[s], d + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
+            if (origin1) CK(cudaMemcpyAsync(dv.s_o1[s], origin1 + c0, n * 4, cudaMemcpyHostToDevice, st));
+            if (origin2) CK(cudaMemcpyAsync(dv.s_o2[s], origin2 + c0, n * 4, cudaMemcpyHostToDevice, st));
+            if (ray_id) CK(cudaMemcpyAsync(dv.s_rid[s], ray_id + c0, n * 4, cudaMemcpyHostToDevice, st));
+            ShootArgs a = { dv.s_o[s], dv.s_d[s], origin1 ? dv.s_o1[s] : nullptr, origin2 ? dv.s_o2[s] : nullptr, ray_id ? dv.s_rid[s] : nullptr, n,
+                            t ? dv.s_t[s] : nullptr, xyz ? dv.s_xyz[s] : nullptr, dv.s_pid[s], uv ? dv.s_uv[s] : nullptr,
+                            o_moved ? dv.s_om[s] : nullptr, counters ? dv.counters : nullptr };
+            int rc2 = launch_shoot(p, dv, a, st);
+            if (rc2) return rc2;
+            CK(cudaMemcpyAsync(poly_id + c0, dv.s_pid[s], n * 4, cudaMemcpyDeviceToHost, st));
+            if (t) CK(cudaMemcpyAsync(t + c0, dv.s_t[s], n * 8, cudaMemcpyDeviceToHost, st));
+            if (xyz) CK(cudaMemcpyAsync(xyz + 3 * c0, dv.s_xyz[s], n * 24, cudaMemcpyDeviceToHost, st));
+            if (uv) CK(cudaMemcpyAsync(uv + 2 * c0, dv.s_uv[s], n * 16, cudaMemcpyDeviceToHost, st));
+            if (o_moved) CK(cudaMemcpyAsync(o_moved + 3 * c0, dv.s_om[s], n * 24, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int g = 0; g < G; ++g) {
+        PartDev& dv = p->dev[g];
+        CK(cudaSetDevice(dv.dev));
+        CK(cudaStreamSynchronize(dv.stream[0]));
+        CK(cudaStreamSynchronize(dv.stream[1]));
+        if (counters) {
+            unsigned long long h[4];
+            CK(cudaMemcpy(h, dv.counters, sizeof h, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < 4; ++k) counters[k] += h[k];
+        }
+    }
+    return HARE_OK;
+}
+
+extern "C" int hare_shoot_batch_device(hare_part_t p, const double* o, const double* d,
+                                       const int32_t* origin1, const int32_t* origin2, const int32_t* ray_id, int64_t N,
+                                       double* t, double* xyz, int32_t* poly_id, double* uv, double* o_moved,
+                                       uint64_t* counters_device, void* cuda_stream) {
+    if (!p || N < 0 || (N && (!o || !d || !poly_id))) return fail(HARE_ERR_INVALID, "hare_shoot_batch_device: bad argument");
+    if (p->dev.size() != 1) return fail(p->dev.empty() ? HARE_ERR_CUDA : HARE_ERR_INVALID, "hare_shoot_batch_device: needs a single-device partition handle");
+    PartDev& dv = p->dev[0];
+    CK(cudaSetDevice(dv.dev));
+    ShootArgs a = { o, d, origin1, origin2, ray_id, N, t, xyz, poly_id, uv, o_moved, (unsigned long long*)counters_device };
+    return launch_shoot(p, dv, a, cuda_stream ? (cudaStream_t)cuda_stream : dv.stream[0]);
+}
+
+extern "C" int hare_reflect_chain(hare_part_t p, const double* o, const double* d, int64_t N, int order,
+                                  int32_t* ev_poly_id, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots,
+                                  uint64_t* total_shots, uint64_t* counters) {
+    if (!p || N < 0 || order < 1 || (N && (!o || !d))) return fail(HARE_ERR_INVALID, "hare_reflect_chain: bad argument");
+    std::lock_guard<std::mutex> lk(p->mu);
+    const int G = (int)p->dev.size();
+    if (G == 0) return fail(HARE_ERR_CUDA, "hare_reflect_chain: host-only handle, no CUDA device (hare_b200 has no CPU fallback)");
+    const bool events = ev_poly_id || ev_t;
+    const int64_t chunk = events ? std::max<int64_t>(1024, kChunk / order) : kChunk;
+    if (counters) std::memset(counters, 0, HARE_CNT_N * sizeof(uint64_t));
+    if (total_shots) *total_shots = 0;
+    for (int g = 0; g < G; ++g) {
+        PartDev& dv = p->dev[g];
+        const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
+        if (r1 <= r0) continue;
+        int rc = ensure_staging(dv, std::min<int64_t>(chunk, r1 - r0));
+        if (rc) return rc;
+        if (events) { rc = ensure_chain_staging(dv, std::min<int64_t>(chunk, r1 - r0), order); if (rc) return rc; }
+        else if (nshots) { rc = ensure_chain_staging(dv, std::min<int64_t>(chunk, r1 - r0), 1); if (rc) return rc; }
+        CK(cudaSetDevice(dv.dev));
+        CK(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
+        CK(cudaStreamSynchronize(dv.stream[0]));
+        int s = 0;
+        for (int64_t c0 = r0; c0 < r1; c0 += chunk, s ^= 1) {
+            const int64_t n = std::min<int64_t>(chunk, r1 - c0);
+            cudaStream_t st = dv.stream[s];
+            CK(cudaMemcpyAsync(dv.s_o[s], o + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(dv.s_d[s], d + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
+            ChainArgs a = { dv.s_o[s], dv.s_d[s], n, order, ev_poly_id ? dv.c_evpid[s] : nullptr, ev_t ? dv.c_evt[s] : nullptr,
+                            fin_o ? dv.s_xyz[s] : nullptr, fin_d ? dv.s_om[s] : nullptr, nshots ? dv.c_ns[s] : nullptr,
+                            dv.counters + 4, counters ? dv.counters : nullptr };
+            int rc2 = launch_chain(p, dv, a, st);
+            if (rc2) return rc2;
+            if (ev_poly_id) CK(cudaMemcpyAsync(ev_poly_id + c0 * order, dv.c_evpid[s], (size_t)n * order * 4, cudaMemcpyDeviceToHost, st));
+            if (ev_t) CK(cudaMemcpyAsync(ev_t + c0 * order, dv.c_evt[s], (size_t)n * order * 8, cudaMemcpyDeviceToHost, st));
+            if (fin_o) CK(cudaMemcpyAsync(fin_o + 3 * c0, dv.s_xyz[s], n * 24, cudaMemcpyDeviceToHost, st));
+            if (fin_d) CK(cudaMemcpyAsync(fin_d + 3 * c0, dv.s_om[s], n * 24, cudaMemcpyDeviceToHost, st));
+            if (nshots) CK(cudaMemcpyAsync(nshots + c0, dv.c_ns[s], n * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int g = 0; g < G; ++g) {
+        PartDev& dv = p->dev[g];
+        CK(cudaSetDevice(dv.dev));
+        CK(cudaStreamSynchronize(dv.stream[0]));
+        CK(cudaStreamSynchronize(dv.stream[1]));
+        unsigned long long h[5];
+        CK(cudaMemcpy(h, dv.counters, sizeof h, cudaMemcpyDeviceToHost));
+        if (counters) for (int k = 0; k < 4; ++k) counters[k] += h[k];
+        if (total_shots) *total_shots += h[4];
+    }
+    return HARE_OK;
+}
+
+extern "C" int hare_reflect_chain_device(hare_part_t p, const double* o, const double* d, int64_t N, int order,
+                                         int32_t* ev_poly_id, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots,
+                                         uint64_t* total_shots_device, uint64_t* counters_device, void* cuda_stream) {
+    if (!p || N < 0 || order < 1 || (N && (!o || !d)) || !total_shots_device) return fail(HARE_ERR_INVALID, "hare_reflect_chain_device: bad argument");
+    if (p->dev.size() != 1) return fail(p->dev.empty() ? HARE_ERR_CUDA : HARE_ERR_INVALID, "hare_reflect_chain_device: needs a single-device partition handle");
+    PartDev& dv = p->dev[0];
+    CK(cudaSetDevice(dv.dev));
+    ChainArgs a = { o, d, N, order, ev_poly_id, ev_t, fin_o, fin_d, nshots, (unsigned long long*)total_shots_device, (unsigned long long*)counters_device };
+    return launch_chain(p, dv, a, cuda_stream ? (cudaStream_t)cuda_stream : dv.stream[0]);
+}

@@ -1,0 +1,273 @@
+// kernels.cuh -- __global__ entry points (sm_100a).
+//
+//   shoot_kernel<PART>    K1/K3/K4: batched Shoot, one ray per thread, persistent grid-stride loop
+//   chain_kernel<PART>    K5: specular reflection chains kept on the device
+//   vg_* kernels          K2: Voxel_Grid cell-list build (count -> scan -> scatter -> per-cell sort)
+#pragma once
+#include <cstdint>
+#include "hare_math.cuh"
+#include "sat.cuh"
+#include "shoot.cuh"
+
+namespace hare {
+
+template <bool COUNT>
+__device__ __forceinline__ void flush_counters(const CntT<COUNT>& c, unsigned long long* __restrict__ counters) {
+    if (!COUNT) return;
+    unsigned int v[4] = { c.cells, c.entries, c.tests, c.hits };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned int s = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(counters + k, (unsigned long long)s);
+    }
+}
+
+template <class PART, bool COUNT>
+__global__ void __launch_bounds__(128)
+shoot_kernel(const PART part, const PolyRec* __restrict__ polys,
+             const double* __restrict__ o, const double* __restrict__ d,
+             const int32_t* __restrict__ o1, const int32_t* __restrict__ o2, const int32_t* __restrict__ rid,
+             long long N, double* __restrict__ t, double* __restrict__ xyz, int32_t* __restrict__ pid,
+             double* __restrict__ uv, double* __restrict__ omoved, unsigned long long* __restrict__ counters) {
+    CntT<COUNT> c;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        Ray3 R = { o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2] };
+        Event ev;
+        const bool blind = rid ? (rid[i] == 0) : false;
+        shoot_one<COUNT>(part, polys, R, o1 ? o1[i] : -1, o2 ? o2[i] : -1, blind, ev, c);
+        pid[i] = ev.pid;
+        if (t) t[i] = ev.t;
+        if (xyz) { xyz[3 * i] = ev.x; xyz[3 * i + 1] = ev.y; xyz[3 * i + 2] = ev.z; }
+        if (uv) { uv[2 * i] = ev.u; uv[2 * i + 1] = ev.v; }
+        if (omoved) { omoved[3 * i] = R.x; omoved[3 * i + 1] = R.y; omoved[3 * i + 2] = R.z; }
+    }
+    flush_counters<COUNT>(c, counters);
+}
+
+// Reflection chain (harness-defined): after a hit on polygon p with unit normal n,
+//   k = 2*((dx*nx)+(dy*ny)+(dz*nz)); d' = (dx - k*nx, dy - k*ny, dz - k*nz); o' = X_Point; poly_origin1 = p.
+template <class PART, bool COUNT>
+__global__ void __launch_bounds__(128)
+chain_kernel(const PART part, const PolyRec* __restrict__ polys,
+             const double* __restrict__ o, const double* __restrict__ d, long long N, int order,
+             int32_t* __restrict__ ev_pid, double* __restrict__ ev_t,
+             double* __restrict__ fin_o, double* __restrict__ fin_d, int32_t* __restrict__ nshots,
+             unsigned long long* __restrict__ total_shots, unsigned long long* __restrict__ counters) {
+    CntT<COUNT> c;
+    unsigned int shots = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        Ray3 R = { o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2] };
+        int origin = -1, b = 0;
+        for (; b < order; ++b) {
+            Event ev;
+            const int st = shoot_one<COUNT>(part, polys, R, origin, -1, false, ev, c);
+            if (ev_pid) ev_pid[i * order + b] = ev.pid;
+            if (ev_t) ev_t[i * order + b] = ev.t;
+            if (st != 1) { ++b; break; }
+            const double* P = polys[ev.pid].v;
+            const double nx = __ldg(P + 12), ny = __ldg(P + 13), nz = __ldg(P + 14);
+            const double k = 2 * ((R.dx * nx) + (R.dy * ny) + (R.dz * nz));
+            R.dx = R.dx - k * nx; R.dy = R.dy - k * ny; R.dz = R.dz - k * nz;
+            R.x = ev.x; R.y = ev.y; R.z = ev.z;
+            origin = ev.pid;
+        }
+        shots += (unsigned int)b;
+        for (int q = b; q < order; ++q) {
+            if (ev_pid) ev_pid[i * order + q] = -3;
+            if (ev_t) ev_t[i * order + q] = 0;
+        }
+        if (fin_o) { fin_o[3 * i] = R.x; fin_o[3 * i + 1] = R.y; fin_o[3 * i + 2] = R.z; }
+        if (fin_d) { fin_d[3 * i] = R.dx; fin_d[3 * i + 1] = R.dy; fin_d[3 * i + 2] = R.dz; }
+        if (nshots) nshots[i] = b;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) shots += __shfl_xor_sync(0xffffffffu, shots, off);
+    if ((threadIdx.x & 31) == 0 && shots) atomicAdd(total_shots, (unsigned long long)shots);
+    flush_counters<COUNT>(c, counters);
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: Voxel_Grid build.  Voxel_Grid(Model, Domain) tests every voxel against every polygon
+// (Voxel_Grid.cs:273-304).  Here each polygon enumerates only the voxels whose inflated box
+// can touch the polygon's bounding box (a superset of the voxels the SAT's box-axis tests
+// accept) and runs the same predicate on each; lists end up ascending like the reference's.
+// ---------------------------------------------------------------------------------------
+struct VGBuild {
+    double ominx, ominy, ominz, vdx, vdy, vdz;
+    int nx, ny, nz;
+};
+
+__device__ __forceinline__ void candidate_range(double mn, double mx, double omin, double vd, int n, int& lo, int& hi) {
+    // voxel X spans [X*vd - eps + omin, (X+1)*vd + eps + omin]; 1e-9 of a voxel of slack keeps this a superset
+    double a = floor((mn - HARE_EPS - omin) / vd - 1e-9) ;
+    double b = floor((mx + HARE_EPS - omin) / vd + 1e-9);
+    a = fmax(a, 0.0); b = fmin(b, (double)(n - 1));
+    lo = (int)a; hi = (int)b;
+    if (!(a <= b)) { lo = 0; hi = -1; }
+}
+
+// MODE 0: count per cell; MODE 1: scatter into cell_poly via per-cell cursors.
+// One warp per polygon: lanes stride over the polygon's candidate voxels.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+vg_bin_kernel(const VGBuild g, const PolyRec* __restrict__ polys, long long P,
+              uint32_t* __restrict__ cell_count, const uint32_t* __restrict__ cell_offset,
+              uint32_t* __restrict__ cursor, uint32_t* __restrict__ cell_poly) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = warp; p < P; p += nwarps) {
+        double V[16];
+        load_poly(polys, (uint32_t)p, V);
+        const int n = (V[15] == 4.0) ? 4 : 3;
+        int lo[3], hi[3];
+        {
+            double mnx = fmin(fmin(V[0], V[3]), V[6]), mxx = fmax(fmax(V[0], V[3]), V[6]);
+            double mny = fmin(fmin(V[1], V[4]), V[7]), mxy = fmax(fmax(V[1], V[4]), V[7]);
+            double mnz = fmin(fmin(V[2], V[5]), V[8]), mxz = fmax(fmax(V[2], V[5]), V[8]);
+            if (n == 4) {
+                mnx = fmin(mnx, V[9]); mxx = fmax(mxx, V[9]); mny = fmin(mny, V[10]); mxy = fmax(mxy, V[10]);
+                mnz = fmin(mnz, V[11]); mxz = fmax(mxz, V[11]);
+            }
+            candidate_range(mnx, mxx, g.ominx, g.vdx, g.nx, lo[0], hi[0]);
+            candidate_range(mny, mxy, g.ominy, g.vdy, g.ny, lo[1], hi[1]);
+            candidate_range(mnz, mxz, g.ominz, g.vdz, g.nz, lo[2], hi[2]);
+        }
+        const int ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1;
+        if (ex <= 0 || ey <= 0 || ez <= 0) continue;
+        const long long total = (long long)ex * ey * ez;
+        for (long long q = lane; q < total; q += 32) {
+            const int z = lo[2] + (int)(q % ez);
+            const int y = lo[1] + (int)((q / ez) % ey);
+            const int x = lo[0] + (int)(q / ((long long)ez * ey));
+            // voxel box exactly as Fill_Voxels builds it (Voxel_Grid.cs:283-285)
+            const Box3 B = make_box(((double)x * g.vdx - HARE_EPS) + g.ominx, ((double)y * g.vdy - HARE_EPS) + g.ominy,
+                                    ((double)z * g.vdz - HARE_EPS) + g.ominz,
+                                    ((double)(x + 1) * g.vdx + HARE_EPS) + g.ominx, ((double)(y + 1) * g.vdy + HARE_EPS) + g.ominy,
+                                    ((double)(z + 1) * g.vdz + HARE_EPS) + g.ominz);
+            if (poly_box_overlap(B, V, n)) {
+                const uint32_t ci = ((uint32_t)x * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nz + (uint32_t)z;
+                if (MODE == 0) atomicAdd(cell_count + ci, 1u);
+                else cell_poly[cell_offset[ci] + atomicAdd(cursor + ci, 1u)] = (uint32_t)p;
+            }
+        }
+    }
+}
+
+// Exclusive scan of n uint32 in three passes (tile sums, scan of tile sums, tile scan + offset).
+#define HARE_SCAN_TILE 4096   /* 1024 threads x 4 items */
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* warp_sums, uint32_t& block_total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += y; }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = warp_sums[lane], si = s;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, si, off); if (lane >= off) si += y; }
+        warp_sums[lane] = si - s;          // exclusive per-warp base
+        if (lane == 31) warp_sums[32] = si;  // block total
+    }
+    __syncthreads();
+    block_total = warp_sums[32];
+    return inc - v + warp_sums[w];
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_sums(const uint32_t* __restrict__ in, long long n, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t ws[33];
+    const long long base = (long long)blockIdx.x * HARE_SCAN_TILE + threadIdx.x * 4;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (base + k < n) s += in[base + k];
+    uint32_t tot;
+    block_exclusive_scan_1024(s, ws, tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of m tile sums in place (m arbitrary, processed 1024 at a time)
+__global__ void __launch_bounds__(1024) scan_tile_offsets(uint32_t* __restrict__ tile_sums, long long m, uint32_t* __restrict__ grand_total) {
+    __shared__ uint32_t ws[33];
+    uint32_t carry = 0;
+    for (long long b = 0; b < m; b += 1024) {
+        const long long i = b + threadIdx.x;
+        const uint32_t v = (i < m) ? tile_sums[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_exclusive_scan_1024(v, ws, tot);
+        if (i < m) tile_sums[i] = ex + carry;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+// out[i] = exclusive prefix; out[n] = total is written by the host wrapper from grand_total.
+__global__ void __launch_bounds__(1024) scan_tiles(const uint32_t* __restrict__ in, long long n, const uint32_t* __restrict__ tile_offsets,
+                                                  uint32_t* __restrict__ out) {
+    __shared__ uint32_t ws[33];
+    const long long base = (long long)blockIdx.x * HARE_SCAN_TILE + threadIdx.x * 4;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = (base + k < n) ? in[base + k] : 0u; s += v[k]; }
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan_1024(s, ws, tot) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+
+// Sort each cell's list ascending (the scatter order is arbitrary), and emit the packed
+// (offset, count) header plus the occupancy bit.  One thread per cell; lists are short.
+__global__ void __launch_bounds__(256)
+vg_finish_cells(const uint32_t* __restrict__ cell_offset, const uint32_t* __restrict__ cell_count, long long ncells,
+                uint32_t* __restrict__ cell_poly, uint2* __restrict__ cells, uint32_t* __restrict__ occ) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0;
+    if (c < ncells) {
+        const uint32_t off = cell_offset[c];
+        cnt = cell_count[c];
+        uint32_t* L = cell_poly + off;
+        if (cnt <= 48) {
+            for (uint32_t i = 1; i < cnt; ++i) {
+                const uint32_t key = L[i]; uint32_t j = i;
+                while (j > 0 && L[j - 1] > key) { L[j] = L[j - 1]; --j; }
+                L[j] = key;
+            }
+        } else {   // heap sort in place
+            auto sift = [&](uint32_t start, uint32_t end) {
+                uint32_t root = start;
+                while (2 * root + 1 < end) {
+                    uint32_t ch = 2 * root + 1;
+                    if (ch + 1 < end && L[ch] < L[ch + 1]) ++ch;
+                    if (L[root] < L[ch]) { uint32_t tmp = L[root]; L[root] = L[ch]; L[ch] = tmp; root = ch; } else break;
+                }
+            };
+            for (int s = (int)(cnt / 2) - 1; s >= 0; --s) sift((uint32_t)s, cnt);
+            for (uint32_t e = cnt - 1; e > 0; --e) { uint32_t tmp = L[0]; L[0] = L[e]; L[e] = tmp; sift(0, e); }
+        }
+        cells[c] = make_uint2(off, cnt);
+    }
+    const unsigned int bits = __ballot_sync(0xffffffffu, cnt > 0);
+    if ((threadIdx.x & 31) == 0 && c < ncells) occ[c >> 5] = bits;
+}
+
+// host-uploaded CSR -> packed headers + occupancy
+__global__ void __launch_bounds__(256)
+vg_pack_cells(const uint32_t* __restrict__ cell_offset, long long ncells, uint2* __restrict__ cells, uint32_t* __restrict__ occ) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0;
+    if (c < ncells) {
+        const uint32_t off = cell_offset[c];
+        cnt = cell_offset[c + 1] - off;
+        cells[c] = make_uint2(off, cnt);
+    }
+    const unsigned int bits = __ballot_sync(0xffffffffu, cnt > 0);
+    if ((threadIdx.x & 31) == 0 && c < ncells) occ[c >> 5] = bits;
+}
+
+}  // namespace hare
