@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -636,9 +637,37 @@ static int launch_shoot_t(const PART& part, const PartDev& d, const ShootArgs& a
     return HARE_OK;
 }
 
+#ifndef HARE_VG_SBATCH
+#define HARE_VG_SBATCH 6
+#endif
+#ifndef HARE_VG_WMAX
+#define HARE_VG_WMAX 8
+#endif
+static bool use_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
+
+// Voxel_Grid: phased persistent kernel (vg_walk.cuh); one launch covers Shoot batches and chains
+template <bool CHAIN>
+static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
+                          const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+    if (N <= 0) return HARE_OK;
+    const int threads = 128;
+    int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms * 4);
+    if (w.counters)
+        vg_walk_kernel<CHAIN, true, HARE_VG_SBATCH, HARE_VG_WMAX><<<(unsigned)blocks, threads, 0, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
+    else
+        vg_walk_kernel<CHAIN, false, HARE_VG_SBATCH, HARE_VG_WMAX><<<(unsigned)blocks, threads, 0, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return HARE_OK;
+}
+
 static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
     switch (p->kind) {
-        case HARE_VOXEL_GRID: return launch_shoot_t(make_vgrid(p, d), d, a, st);
+        case HARE_VOXEL_GRID: {
+            if (use_v1()) return launch_shoot_t(make_vgrid(p, d), d, a, st);
+            WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
+            return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
+        }
         case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, p->oct.depth }; return launch_shoot_t(t, d, a, st); }
         case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, p->kd.depth }; return launch_shoot_t(t, d, a, st); }
     }
@@ -667,7 +696,11 @@ static int launch_chain_t(const PART& part, const PartDev& d, const ChainArgs& a
 
 static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cudaStream_t st) {
     switch (p->kind) {
-        case HARE_VOXEL_GRID: return launch_chain_t(make_vgrid(p, d), d, a, st);
+        case HARE_VOXEL_GRID: {
+            if (use_v1()) return launch_chain_t(make_vgrid(p, d), d, a, st);
+            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
+            return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
+        }
         case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, p->oct.depth }; return launch_chain_t(t, d, a, st); }
         case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, p->kd.depth }; return launch_chain_t(t, d, a, st); }
     }

@@ -24,6 +24,10 @@ __device__ __forceinline__ void flush_counters(const CntT<COUNT>& c, unsigned lo
     }
 }
 
+}  // namespace hare
+#include "vg_walk.cuh"
+namespace hare {
+
 template <class PART, bool COUNT>
 __global__ void __launch_bounds__(128)
 shoot_kernel(const PART part, const PolyRec* __restrict__ polys,
