@@ -12,7 +12,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)
-SO_PATH = os.path.join(_PKG, "libhare_b200.so")
+SO_PATH = os.environ.get("HARE_B200_LIB") or os.path.join(_PKG, "libhare_b200.so")   # override: tuning experiments only
 HEADER = os.path.join(ROOT, "include", "hare_b200.h")
 
 _lib = None

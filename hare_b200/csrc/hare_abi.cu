@@ -641,24 +641,37 @@ static int launch_shoot_t(const PART& part, const PartDev& d, const ShootArgs& a
 #define HARE_VG_SBATCH 6
 #endif
 #ifndef HARE_VG_WMAX
-#define HARE_VG_WMAX 8
+#define HARE_VG_WMAX 2
 #endif
 static bool use_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
 
-// Voxel_Grid: phased persistent kernel (vg_walk.cuh); one launch covers Shoot batches and chains
+// Voxel_Grid: phased persistent kernel (vg_walk.cuh); one launch covers Shoot batches and chains.
+// One 512-thread CTA per SM; the occupancy bitmap rides in shared memory when it fits (<= 200 KB,
+// i.e. up to ~117^3 voxels), otherwise it is read through L1.
+template <bool CHAIN, bool COUNT, bool OCC_SMEM>
+static int launch_vg_walk2(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
+                           const int32_t* rid, int64_t N, int order, const WalkOut& w, size_t smem, cudaStream_t st) {
+    auto k = vg_walk_kernel<CHAIN, COUNT, OCC_SMEM, HARE_VG_SBATCH, HARE_VG_WMAX>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = std::min<int64_t>((N + HARE_VG_THREADS - 1) / HARE_VG_THREADS, (int64_t)d.sms);
+    k<<<(unsigned)blocks, HARE_VG_THREADS, smem, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return HARE_OK;
+}
+
 template <bool CHAIN>
 static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
                           const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
-    const int threads = 128;
-    int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms * 4);
-    if (w.counters)
-        vg_walk_kernel<CHAIN, true, HARE_VG_SBATCH, HARE_VG_WMAX><<<(unsigned)blocks, threads, 0, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
-    else
-        vg_walk_kernel<CHAIN, false, HARE_VG_SBATCH, HARE_VG_WMAX><<<(unsigned)blocks, threads, 0, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
-    ++g_launches;
-    CK(cudaGetLastError());
-    return HARE_OK;
+    const size_t occ_bytes = (((size_t)g.nx * g.ny * g.nz + 31) / 32) * 4;
+    const bool in_smem = occ_bytes <= 200 * 1024;
+    if (w.counters) {
+        if (in_smem) return launch_vg_walk2<CHAIN, true, true>(g, d, o, dd, o1, o2, rid, N, order, w, occ_bytes, st);
+        return launch_vg_walk2<CHAIN, true, false>(g, d, o, dd, o1, o2, rid, N, order, w, 0, st);
+    }
+    if (in_smem) return launch_vg_walk2<CHAIN, false, true>(g, d, o, dd, o1, o2, rid, N, order, w, occ_bytes, st);
+    return launch_vg_walk2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, w, 0, st);
 }
 
 static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cudaStream_t st) {

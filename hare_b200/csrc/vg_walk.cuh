@@ -6,11 +6,12 @@
 //   S  (batched)  lanes that need a new ray, or a DDA set-up for the next bounce, do it --
 //                 but only once S_BATCH lanes want it (or nobody can do anything else), so the
 //                 nine divides of the set-up are paid by several lanes at once;
-//   W  (cheap)    every walking lane advances its 3D-DDA -- skipping empty voxels on the
-//                 occupancy bitmap without touching the cell table -- until it holds the index
-//                 of the next polygon to test, has accepted its carried candidate, or left the grid;
-//   T  (dense)    every lane holding a polygon index fetches the 128-byte record (8 x LDG.128)
-//                 and runs the FP64 Moller-Trumbore test.
+//   W  (cheap)    every lane whose voxel list is exhausted advances its 3D-DDA -- skipping empty
+//                 voxels on the occupancy bitmap (staged in shared memory) without touching the
+//                 cell table -- until it stands in a non-empty voxel, has accepted its carried
+//                 candidate, or left the grid (at most W_MAX voxels per trip);
+//   T  (dense)    every lane with a list entry left takes the next one, fetches the 128-byte
+//                 polygon record (8 x LDG.128) and runs the FP64 Moller-Trumbore test.
 //
 // The FP64 pipe is the busiest unit of this path (ncu, profiles/), and the polygon test is
 // ~10x the cost of a voxel step; one-ray-per-thread "while-while" code left 2.6 of 32 lanes
@@ -33,12 +34,24 @@ struct WalkOut {
 
 enum : int { ST_NEED_RAY = 0, ST_NEED_SETUP = 1, ST_WALK = 2, ST_DONE = 3 };
 
-template <bool CHAIN, bool COUNT, int S_BATCH, int W_MAX>
-__global__ void __launch_bounds__(128, 4)
+#ifndef HARE_VG_THREADS
+#define HARE_VG_THREADS 512
+#endif
+
+// OCC_SMEM: the occupancy bitmap (1 bit per voxel) is staged in shared memory once per CTA, so an
+// empty-voxel step costs a 29-cycle LDS instead of an L1/L2 round trip.  One 512-thread CTA per SM.
+template <bool CHAIN, bool COUNT, bool OCC_SMEM, int S_BATCH, int W_MAX>
+__global__ void __launch_bounds__(HARE_VG_THREADS, 1)
 vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                const double* __restrict__ o, const double* __restrict__ d,
                const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a, const int32_t* __restrict__ rid,
                long long N, int order, const WalkOut out) {
+    extern __shared__ uint32_t s_occ[];
+    if (OCC_SMEM) {
+        const uint32_t words = ((uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz + 31u) >> 5;
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) s_occ[w] = __ldg(g.occ + w);
+        __syncthreads();
+    }
     CntT<COUNT> c;
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long next = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,12 +62,24 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
     double tmin = DBL_MAX, bx = 0, by = 0, bz = 0, t_start = 0;
     int X = 0, Y = 0, Z = 0, stepX = 1, stepY = 1, stepZ = 1;
     int pid = -1, or1 = -1, or2 = -1, bounce = 0;
-    uint32_t lpos = 0, lend = 0, pend = 0, last = 0xffffffffu, ci = 0;
-    bool have = false, pending = false, blind = false;
+    uint32_t lpos = 0, lend = 0, nid = 0, last = 0xffffffffu, ci = 0;
+    bool have = false, blind = false;
     int state = ST_NEED_RAY;
     int fin = 2;              // 2 = Shoot still running; otherwise its status: 1 hit, 0 miss, -2 fault
     unsigned int shots = 0;
     const int strideX = g.ny * g.nz, strideY = g.nz;
+
+    // list range of voxel ci (empty voxels never touch the cell table) and its first polygon index
+    auto enter_cell = [&]() {
+        c.cell();
+        lpos = 0; lend = 0;
+        const uint32_t word = OCC_SMEM ? s_occ[ci >> 5] : __ldg(g.occ + (ci >> 5));
+        if (!blind && ((word >> (ci & 31)) & 1u)) {
+            const uint2 h = __ldg(g.cells + ci);
+            lpos = h.x; lend = h.x + h.y;
+            nid = __ldg(g.cell_poly + lpos);
+        }
+    };
 
     while (true) {
         // ------------------------------------------------------------------ S phase
@@ -77,7 +102,7 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
             }
             if (state == ST_NEED_SETUP) {   // Voxel_Grid.cs:357-422
                 state = ST_WALK; fin = 2;
-                have = false; pending = false; tmin = DBL_MAX; pid = -1; last = 0xffffffffu; t_start = 0;
+                have = false; tmin = DBL_MAX; pid = -1; last = 0xffffffffu; t_start = 0; lpos = 0; lend = 0;
                 X = floor_to_int((R.x - g.ominx) / g.vdx);
                 Y = floor_to_int((R.y - g.ominy) / g.vdy);
                 Z = floor_to_int((R.z - g.ominz) / g.vdz);
@@ -100,24 +125,15 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                     tDeltaY = g.vdy / R.dy * (ny_ ? -1.0 : 1.0);
                     tDeltaZ = g.vdz / R.dz * (nz_ ? -1.0 : 1.0);
                     ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
-                    c.cell();
-                    lpos = 0; lend = 0;
-                    if (!blind && ((__ldg(g.occ + (ci >> 5)) >> (ci & 31)) & 1u)) { const uint2 h = __ldg(g.cells + ci); lpos = h.x; lend = h.x + h.y; }
+                    enter_cell();
                 }
             }
         }
-        // ------------------------------------------------------------------ W phase
-        if (state == ST_WALK && !pending && fin == 2) {
+        // ------------------------------------------------------------------ W phase: lanes whose list is exhausted
+        if (state == ST_WALK && fin == 2 && lpos >= lend) {
 #pragma unroll 1
             for (int guard = 0; guard < W_MAX; ++guard) {
-                if (lpos < lend) {   // next list entry of the current voxel (ascending polygon index)
-                    const uint32_t i = __ldg(g.cell_poly + lpos); ++lpos;
-                    c.entry();
-                    if ((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) continue;   // (a re-test never changes the result)
-                    pend = i; pending = true;
-                    break;
-                }
-                // list exhausted: Voxels[X,Y,Z].IsPointInBox(candidate)?   Voxel_Grid.cs:496-500
+                // Voxels[X,Y,Z].IsPointInBox(candidate)?   Voxel_Grid.cs:496-500
                 if (have) {
                     const bool in = !(bx < vox_min(X, g.vdx, g.ominx)) & !(by < vox_min(Y, g.vdy, g.ominy)) & !(bz < vox_min(Z, g.vdz, g.ominz)) &
                                     !(bx > vox_max(X, g.vdx, g.ominx)) & !(by > vox_max(Y, g.vdy, g.ominy)) & !(bz > vox_max(Z, g.vdz, g.ominz));
@@ -132,9 +148,8 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                 X += goX ? stepX : 0; Y += goY ? stepY : 0; Z += goZ ? stepZ : 0;
                 ci += (uint32_t)(goX ? stepX * strideX : (goY ? stepY * strideY : stepZ));
                 if ((unsigned)X >= (unsigned)g.nx || (unsigned)Y >= (unsigned)g.ny || (unsigned)Z >= (unsigned)g.nz) { fin = 0; break; }
-                c.cell();
-                lpos = 0; lend = 0;
-                if (!blind && ((__ldg(g.occ + (ci >> 5)) >> (ci & 31)) & 1u)) { const uint2 h = __ldg(g.cells + ci); lpos = h.x; lend = h.x + h.y; }
+                enter_cell();
+                if (lpos < lend) break;
             }
         }
         // ------------------------------------------------------------------ F phase: the Shoot is over
@@ -174,25 +189,31 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                 if (out.uv) { out.uv[2 * ray] = 0.0; out.uv[2 * ray + 1] = 0.0; }
                 if (out.omoved) { out.omoved[3 * ray] = R.x; out.omoved[3 * ray + 1] = R.y; out.omoved[3 * ray + 2] = R.z; }
             }
-            fin = 2;
+            fin = 2; lpos = 0; lend = 0;
         }
-        // ------------------------------------------------------------------ T phase
-        if (pending) {
-            pending = false;
-            last = pend;
-            c.test();
-            double P[16], t = 0;
-            load_poly(polys, pend, P);
-            // Polygon.Ray_Side picks the winding (Hare_Geometry_Polygons.cs:601-606, 637-660, 784-823):
-            //   side ? (P0,P1,P2) then (P2,P3,P0) : (P2,P1,P0) then (P0,P3,P2)
-            const bool side = !(dot3(R.dx, R.dy, R.dz, P[12], P[13], P[14]) < 0);
-            const double ax = side ? P[0] : P[6], ay = side ? P[1] : P[7], az = side ? P[2] : P[8];
-            const double cx = side ? P[6] : P[0], cy = side ? P[7] : P[1], cz = side ? P[8] : P[2];
-            bool hit = ray_x_tri_fast1(R, ax, ay, az, P[3], P[4], P[5], cx, cy, cz, t);
-            if (!hit && P[15] == 4.0) hit = ray_x_tri_fast1(R, cx, cy, cz, P[9], P[10], P[11], ax, ay, az, t);
-            if (hit && t > 0.0000000001 && t < tmin) {
-                bx = R.x + R.dx * t; by = R.y + R.dy * t; bz = R.z + R.dz * t;
-                tmin = t; pid = (int)pend; have = true;
+        // ------------------------------------------------------------------ T phase: one list entry per lane
+        if (state == ST_WALK && lpos < lend) {
+            const uint32_t i = nid;          // list entry lpos (ascending polygon index), fetched one round ahead
+            ++lpos;
+            if (lpos < lend) nid = __ldg(g.cell_poly + lpos);
+            c.entry();
+            // poly_origin skip (Voxel_Grid.cs:477); a polygon already tested for this ray cannot change the result
+            if (!((int)i == or1 || (int)i == or2 || i == last || (int)i == pid)) {
+                last = i;
+                c.test();
+                double P[16], t = 0;
+                load_poly(polys, i, P);
+                // Polygon.Ray_Side picks the winding (Hare_Geometry_Polygons.cs:601-606, 637-660, 784-823):
+                //   side ? (P0,P1,P2) then (P2,P3,P0) : (P2,P1,P0) then (P0,P3,P2)
+                const bool side = !(dot3(R.dx, R.dy, R.dz, P[12], P[13], P[14]) < 0);
+                const double ax = side ? P[0] : P[6], ay = side ? P[1] : P[7], az = side ? P[2] : P[8];
+                const double cx = side ? P[6] : P[0], cy = side ? P[7] : P[1], cz = side ? P[8] : P[2];
+                bool hit = ray_x_tri_fast1(R, ax, ay, az, P[3], P[4], P[5], cx, cy, cz, t);
+                if (!hit && P[15] == 4.0) hit = ray_x_tri_fast1(R, cx, cy, cz, P[9], P[10], P[11], ax, ay, az, t);
+                if (hit && t > 0.0000000001 && t < tmin) {
+                    bx = R.x + R.dx * t; by = R.y + R.dy * t; bz = R.z + R.dz * t;
+                    tmin = t; pid = (int)i; have = true;
+                }
             }
         }
     }
