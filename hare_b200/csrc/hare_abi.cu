@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -227,12 +228,34 @@ extern "C" int hare_topology_create(const double* verts, const double* normals, 
                 if (c > t->host.vmax[a]) t->host.vmax[a] = c;
             }
     }
+    // padded bounding spheres in FP32 (centre of the vertex box, radius to the farthest vertex, padded by 1e-3 + 1e-5 relative,
+    // which covers the FP32 evaluation in cull_sphere()): a conservative reject used by the traversal
+    // kernels, stored right after the polygon records
+    std::vector<float> sph((size_t)P * 4);
+    for (int64_t i = 0; i < P; ++i) {
+        double lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) { lo[a] = hi[a] = verts[12 * i + a]; }
+        for (int k = 1; k < vcount[i]; ++k)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], verts[12 * i + 3 * k + a]); hi[a] = std::max(hi[a], verts[12 * i + 3 * k + a]); }
+        float cf[3]; double r2 = 0;
+        for (int a = 0; a < 3; ++a) cf[a] = (float)(0.5 * (lo[a] + hi[a]));
+        for (int k = 0; k < vcount[i]; ++k) {
+            double q = 0;
+            for (int a = 0; a < 3; ++a) { double dlt = verts[12 * i + 3 * k + a] - (double)cf[a]; q += dlt * dlt; }
+            r2 = std::max(r2, q);
+        }
+        const double r = std::sqrt(r2) * (1.0 + 1e-5) + 1e-3;
+        float rf = (float)r;
+        while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
+        sph[4 * i] = cf[0]; sph[4 * i + 1] = cf[1]; sph[4 * i + 2] = cf[2]; sph[4 * i + 3] = rf;
+    }
     { std::lock_guard<std::mutex> lk(g_mu); t->devs = g_devices; }
     for (int dev : t->devs) {
         PolyRec* d = nullptr;
         cudaError_t e = cudaSetDevice(dev);
-        if (e == cudaSuccess) e = dmalloc(&d, (size_t)P);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d, (size_t)P * (sizeof(PolyRec) + 16));
         if (e == cudaSuccess) e = cudaMemcpy(d, recs.data(), (size_t)P * sizeof(PolyRec), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d + P, sph.data(), (size_t)P * 16, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             for (size_t k = 0; k < t->d_polys.size(); ++k) { cudaSetDevice(t->devs[k]); cudaFree(t->d_polys[k]); }
             cudaFree(d); delete t;
@@ -274,6 +297,7 @@ static VGrid make_vgrid(const hare_part_s* p, const PartDev& d) {
     g.vdx = p->vd[0]; g.vdy = p->vd[1]; g.vdz = p->vd[2];
     g.nx = p->ct[0]; g.ny = p->ct[1]; g.nz = p->ct[2];
     g.cells = d.cells; g.cell_poly = d.cell_poly; g.occ = d.occ;
+    g.sph = reinterpret_cast<const float4*>(d.polys + p->topo->host.P);   // spheres follow the records
     return g;
 }
 
@@ -641,7 +665,7 @@ static int launch_shoot_t(const PART& part, const PartDev& d, const ShootArgs& a
 #define HARE_VG_SBATCH 6
 #endif
 #ifndef HARE_VG_WMAX
-#define HARE_VG_WMAX 2
+#define HARE_VG_WMAX 4
 #endif
 static bool use_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
 

@@ -22,6 +22,7 @@ template <bool COUNT> struct CntT {
     __device__ __forceinline__ void entry() { if (COUNT) ++entries; }
     __device__ __forceinline__ void test() { if (COUNT) ++tests; }
     __device__ __forceinline__ void hit() { if (COUNT) ++hits; }
+    __device__ __forceinline__ void cull() {}
 };
 
 // Fetch one 128-byte polygon record as eight 128-bit read-only loads (LDG.E.128.CONSTANT),
@@ -35,6 +36,20 @@ __device__ __forceinline__ void load_poly(const PolyRec* __restrict__ polys, uin
     }
 }
 
+// Conservative reject: true only when the ray's supporting line stays outside the polygon's padded
+// bounding sphere, i.e. when no triangle test on that polygon can succeed.  Not part of the reference;
+// it never changes a result, it only spares the 128-byte fetch and the exact FP64 test.
+// Evaluated in FP32 in a frame local to the current voxel: p = a point of the ray at the voxel (rounded
+// to FP32), v = c - p is at most a voxel diagonal plus a polygon radius long, so |v x d|^2 = |v|^2|d|^2 -
+// (v.d)^2 has no large-number cancellation; its rounding error (~1e-6 m^2 for |v| <= 4 m, plus the 3e-6 m
+// rounding of p and of the stored centre) is far inside the 1e-3 m by which the host pads the radius.
+__device__ __forceinline__ bool cull_sphere(const float4 s, float px, float py, float pz, float dx, float dy, float dz, float dd) {
+    const float vx = s.x - px, vy = s.y - py, vz = s.z - pz;
+    const float vd = fmaf(vx, dx, fmaf(vy, dy, vz * dz));
+    const float vv = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
+    return fmaf(-vd, vd, vv * dd) > (s.w * s.w) * dd;   // |v x d|^2 > r^2 |d|^2   (NaN -> keep)
+}
+
 // ---------------------------------------------------------------------------------------
 // Voxel_Grid
 // ---------------------------------------------------------------------------------------
@@ -45,6 +60,7 @@ struct VGrid {
     const uint2* __restrict__ cells;        // (offset, count) per cell, index ((x*ny+y)*nz+z)
     const uint32_t* __restrict__ cell_poly; // ascending polygon indices per cell
     const uint32_t* __restrict__ occ;       // 1 bit per cell: list non-empty
+    const float4* __restrict__ sph;         // per polygon: padded bounding sphere (cx, cy, cz, r), see cull_sphere()
 };
 
 #define HARE_EPS 0.001   /* Voxel_Grid.Epsilon, Voxel_Grid.cs:39 */

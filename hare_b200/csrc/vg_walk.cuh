@@ -59,10 +59,12 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
 
     Ray3 R = { 0, 0, 0, 0, 0, 0 };
     double tMaxX = 0, tMaxY = 0, tMaxZ = 0, tDeltaX = 0, tDeltaY = 0, tDeltaZ = 0;
-    double tmin = DBL_MAX, bx = 0, by = 0, bz = 0, t_start = 0;
+    double tmin = DBL_MAX, t_start = 0;
+    float fdx = 0, fdy = 0, fdz = 0, fdd = 0, fpx = 0, fpy = 0, fpz = 0;   // FP32 copy of d, |d|^2 and of a ray point at the current voxel (cull only)
     int X = 0, Y = 0, Z = 0, stepX = 1, stepY = 1, stepZ = 1;
     int pid = -1, or1 = -1, or2 = -1, bounce = 0;
-    uint32_t lpos = 0, lend = 0, nid = 0, last = 0xffffffffu, ci = 0;
+    uint32_t lpos = 0, lend = 0, last = 0xffffffffu, ci = 0;
+    uint32_t bid0 = 0, bid1 = 0, bid2 = 0, bid3 = 0, bmask = 0;   // batch of up to 4 list entries; bit k = entry k survived the cull
     bool have = false, blind = false;
     int state = ST_NEED_RAY;
     int fin = 2;              // 2 = Shoot still running; otherwise its status: 1 hit, 0 miss, -2 fault
@@ -70,14 +72,14 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
     const int strideX = g.ny * g.nz, strideY = g.nz;
 
     // list range of voxel ci (empty voxels never touch the cell table) and its first polygon index
-    auto enter_cell = [&]() {
+    auto enter_cell = [&](double t_in) {   // t_in: ray parameter at which this voxel was entered
         c.cell();
         lpos = 0; lend = 0;
         const uint32_t word = OCC_SMEM ? s_occ[ci >> 5] : __ldg(g.occ + (ci >> 5));
         if (!blind && ((word >> (ci & 31)) & 1u)) {
             const uint2 h = __ldg(g.cells + ci);
             lpos = h.x; lend = h.x + h.y;
-            nid = __ldg(g.cell_poly + lpos);
+            fpx = (float)fma(R.dx, t_in, R.x); fpy = (float)fma(R.dy, t_in, R.y); fpz = (float)fma(R.dz, t_in, R.z);
         }
     };
 
@@ -102,7 +104,7 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
             }
             if (state == ST_NEED_SETUP) {   // Voxel_Grid.cs:357-422
                 state = ST_WALK; fin = 2;
-                have = false; tmin = DBL_MAX; pid = -1; last = 0xffffffffu; t_start = 0; lpos = 0; lend = 0;
+                have = false; bmask = 0; tmin = DBL_MAX; pid = -1; last = 0xffffffffu; t_start = 0; lpos = 0; lend = 0;
                 X = floor_to_int((R.x - g.ominx) / g.vdx);
                 Y = floor_to_int((R.y - g.ominy) / g.vdy);
                 Z = floor_to_int((R.z - g.ominz) / g.vdz);
@@ -125,16 +127,19 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                     tDeltaY = g.vdy / R.dy * (ny_ ? -1.0 : 1.0);
                     tDeltaZ = g.vdz / R.dz * (nz_ ? -1.0 : 1.0);
                     ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
-                    enter_cell();
+                    fdx = (float)R.dx; fdy = (float)R.dy; fdz = (float)R.dz;
+                    fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
+                    enter_cell(0.0);
                 }
             }
         }
-        // ------------------------------------------------------------------ W phase: lanes whose list is exhausted
-        if (state == ST_WALK && fin == 2 && lpos >= lend) {
+        // ------------------------------------------------------------------ W phase: voxel steps
+        if (state == ST_WALK && fin == 2 && bmask == 0 && lpos >= lend) {
 #pragma unroll 1
             for (int guard = 0; guard < W_MAX; ++guard) {
-                // Voxels[X,Y,Z].IsPointInBox(candidate)?   Voxel_Grid.cs:496-500
+                // list exhausted: Voxels[X,Y,Z].IsPointInBox(candidate)?   Voxel_Grid.cs:496-500
                 if (have) {
+                    const double bx = R.x + R.dx * tmin, by = R.y + R.dy * tmin, bz = R.z + R.dz * tmin;
                     const bool in = !(bx < vox_min(X, g.vdx, g.ominx)) & !(by < vox_min(Y, g.vdy, g.ominy)) & !(bz < vox_min(Z, g.vdz, g.ominz)) &
                                     !(bx > vox_max(X, g.vdx, g.ominx)) & !(by > vox_max(Y, g.vdy, g.ominy)) & !(bz > vox_max(Z, g.vdz, g.ominz));
                     if (in) { fin = 1; break; }
@@ -143,19 +148,41 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                 const bool xy = tMaxX < tMaxY, xz = tMaxX < tMaxZ, yz = tMaxY < tMaxZ;
                 const bool goX = xy & xz, goY = (!xy) & yz;
                 const bool goZ = !(goX | goY);
+                const double t_in = goX ? tMaxX : (goY ? tMaxY : tMaxZ);
                 const double nX = tMaxX + tDeltaX, nY = tMaxY + tDeltaY, nZ = tMaxZ + tDeltaZ;
                 tMaxX = goX ? nX : tMaxX; tMaxY = goY ? nY : tMaxY; tMaxZ = goZ ? nZ : tMaxZ;
                 X += goX ? stepX : 0; Y += goY ? stepY : 0; Z += goZ ? stepZ : 0;
                 ci += (uint32_t)(goX ? stepX * strideX : (goY ? stepY * strideY : stepZ));
                 if ((unsigned)X >= (unsigned)g.nx || (unsigned)Y >= (unsigned)g.ny || (unsigned)Z >= (unsigned)g.nz) { fin = 0; break; }
-                enter_cell();
+                enter_cell(t_in);
                 if (lpos < lend) break;
             }
+        }
+        // ------------------------------------------------------------------ C phase: cull a batch of list entries
+        if (state == ST_WALK && fin == 2 && bmask == 0 && lpos < lend) {
+            // next (up to) four list entries, ascending polygon index: ids and bounding spheres are fetched as
+            // two groups of independent loads, then culled in FP32; survivors wait in bmask for the T phase
+            const uint32_t n = min(4u, lend - lpos);
+            bid0 = __ldg(g.cell_poly + lpos);
+            bid1 = (n > 1) ? __ldg(g.cell_poly + lpos + 1) : bid0;
+            bid2 = (n > 2) ? __ldg(g.cell_poly + lpos + 2) : bid0;
+            bid3 = (n > 3) ? __ldg(g.cell_poly + lpos + 3) : bid0;
+            const float4 s0 = __ldg(g.sph + bid0), s1 = __ldg(g.sph + bid1), s2 = __ldg(g.sph + bid2), s3 = __ldg(g.sph + bid3);
+            lpos += n;
+            if (COUNT) c.entries += n;
+            // poly_origin skip (Voxel_Grid.cs:477); a polygon already tested for this ray cannot change the result
+            auto keep = [&](uint32_t i, const float4& s) {
+                return !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) && !cull_sphere(s, fpx, fpy, fpz, fdx, fdy, fdz, fdd);
+            };
+            bmask = (keep(bid0, s0) ? 1u : 0u) | ((n > 1 && keep(bid1, s1)) ? 2u : 0u) |
+                    ((n > 2 && keep(bid2, s2)) ? 4u : 0u) | ((n > 3 && keep(bid3, s3)) ? 8u : 0u);
         }
         // ------------------------------------------------------------------ F phase: the Shoot is over
         if (fin != 2) {
             const double ev_t = (fin == 1) ? tmin + t_start : 0.0;
             const int ev_p = (fin == 1) ? pid : (fin == -2 ? -2 : -1);
+            // X_Point = R + d*t of the winning test (Hare_Geometry_Polygons.cs:802): same bits whenever it is formed
+            const double bx = R.x + R.dx * tmin, by = R.y + R.dy * tmin, bz = R.z + R.dz * tmin;
             if (fin == 1) c.hit();
             state = ST_NEED_RAY;
             if (CHAIN) {
@@ -189,32 +216,24 @@ vg_walk_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                 if (out.uv) { out.uv[2 * ray] = 0.0; out.uv[2 * ray + 1] = 0.0; }
                 if (out.omoved) { out.omoved[3 * ray] = R.x; out.omoved[3 * ray + 1] = R.y; out.omoved[3 * ray + 2] = R.z; }
             }
-            fin = 2; lpos = 0; lend = 0;
+            fin = 2; lpos = 0; lend = 0; bmask = 0;
         }
-        // ------------------------------------------------------------------ T phase: one list entry per lane
-        if (state == ST_WALK && lpos < lend) {
-            const uint32_t i = nid;          // list entry lpos (ascending polygon index), fetched one round ahead
-            ++lpos;
-            if (lpos < lend) nid = __ldg(g.cell_poly + lpos);
-            c.entry();
-            // poly_origin skip (Voxel_Grid.cs:477); a polygon already tested for this ray cannot change the result
-            if (!((int)i == or1 || (int)i == or2 || i == last || (int)i == pid)) {
-                last = i;
-                c.test();
-                double P[16], t = 0;
-                load_poly(polys, i, P);
-                // Polygon.Ray_Side picks the winding (Hare_Geometry_Polygons.cs:601-606, 637-660, 784-823):
-                //   side ? (P0,P1,P2) then (P2,P3,P0) : (P2,P1,P0) then (P0,P3,P2)
-                const bool side = !(dot3(R.dx, R.dy, R.dz, P[12], P[13], P[14]) < 0);
-                const double ax = side ? P[0] : P[6], ay = side ? P[1] : P[7], az = side ? P[2] : P[8];
-                const double cx = side ? P[6] : P[0], cy = side ? P[7] : P[1], cz = side ? P[8] : P[2];
-                bool hit = ray_x_tri_fast1(R, ax, ay, az, P[3], P[4], P[5], cx, cy, cz, t);
-                if (!hit && P[15] == 4.0) hit = ray_x_tri_fast1(R, cx, cy, cz, P[9], P[10], P[11], ax, ay, az, t);
-                if (hit && t > 0.0000000001 && t < tmin) {
-                    bx = R.x + R.dx * t; by = R.y + R.dy * t; bz = R.z + R.dz * t;
-                    tmin = t; pid = (int)i; have = true;
-                }
-            }
+        // ------------------------------------------------------------------ T phase: the exact FP64 test
+        if (bmask) {
+            const uint32_t pend = (bmask & 1u) ? bid0 : ((bmask & 2u) ? bid1 : ((bmask & 4u) ? bid2 : bid3));   // lowest survivor first
+            bmask &= bmask - 1u;
+            last = pend;
+            c.test();
+            double P[16], t = 0;
+            load_poly(polys, pend, P);
+            // Polygon.Ray_Side picks the winding (Hare_Geometry_Polygons.cs:601-606, 637-660, 784-823):
+            //   side ? (P0,P1,P2) then (P2,P3,P0) : (P2,P1,P0) then (P0,P3,P2)
+            const bool side = !(dot3(R.dx, R.dy, R.dz, P[12], P[13], P[14]) < 0);
+            const double ax = side ? P[0] : P[6], ay = side ? P[1] : P[7], az = side ? P[2] : P[8];
+            const double cx = side ? P[6] : P[0], cy = side ? P[7] : P[1], cz = side ? P[8] : P[2];
+            bool hit = ray_x_tri_fast1(R, ax, ay, az, P[3], P[4], P[5], cx, cy, cz, t);
+            if (!hit && P[15] == 4.0) hit = ray_x_tri_fast1(R, cx, cy, cz, P[9], P[10], P[11], ax, ay, az, t);
+            if (hit && t > 0.0000000001 && t < tmin) { tmin = t; pid = (int)pend; have = true; }
         }
     }
     if (CHAIN) {
