@@ -200,6 +200,11 @@ def run_b200(args):
         g_fin_d = torch.empty((world * N, 3), dtype=torch.float64, device=dev) if rank == 0 else None
         g_ns = torch.empty(world * N, dtype=torch.int32, device=dev) if rank == 0 else None
 
+    def gather():   # X_Event rows of every rank -> rank 0, in rank order (hare_b200/dist.py; same helper as the gloo test)
+        dist.gather(fin_o, list(g_fin_o.chunk(world)) if rank == 0 else None, dst=0)
+        dist.gather(fin_d, list(g_fin_d.chunk(world)) if rank == 0 else None, dst=0)
+        dist.gather(nshots, list(g_ns.chunk(world)) if rank == 0 else None, dst=0)
+
     def cur_stream():
         # torch's default stream is the legacy default stream (handle 0); the C ABI treats NULL as "the
         # partition's own stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1).
@@ -212,9 +217,7 @@ def run_b200(args):
                                           fin_o.data_ptr(), fin_d.data_ptr(), nshots.data_ptr(), total.data_ptr(), None, C.c_void_p(stream)),
               "hare_reflect_chain_device")
         if world > 1:   # gather of per-chain results to rank 0 over NVLink (NCCL)
-            dist.gather(fin_o, list(g_fin_o.chunk(world)) if rank == 0 else None, dst=0)
-            dist.gather(fin_d, list(g_fin_d.chunk(world)) if rank == 0 else None, dst=0)
-            dist.gather(nshots, list(g_ns.chunk(world)) if rank == 0 else None, dst=0)
+            gather()
 
     def sync_all():
         if world > 1:
@@ -243,9 +246,7 @@ def run_b200(args):
               "hare_reflect_chain_device")
         kev[k][1].record()
         if world > 1:
-            dist.gather(fin_o, list(g_fin_o.chunk(world)) if rank == 0 else None, dst=0)
-            dist.gather(fin_d, list(g_fin_d.chunk(world)) if rank == 0 else None, dst=0)
-            dist.gather(nshots, list(g_ns.chunk(world)) if rank == 0 else None, dst=0)
+            gather()
         ev[k + 1].record()
     sync_all()
     launches = hb.launch_count() - launches0

@@ -51,6 +51,31 @@ def test_shoebox_trees(gpu, kind, args):
     assert_events_equal(got, ref, what=kind)
 
 
+# ---------------------------------------------------------------- committed golden vectors (second restatement)
+@pytest.mark.parametrize("name", ["shoebox", "tiny"])
+def test_golden_vectors(gpu, name):
+    """tests/golden/hare_golden.npz was produced by the pure-Python restatement (make_golden.py);
+    the CUDA path must reproduce it bit for bit, inputs taken from the fixture itself."""
+    import os
+    from hare_b200.harness.meshes import Mesh
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hare_golden.npz"))
+    mesh = Mesh(G[f"{name}_verts"], G[f"{name}_vcount"], G[f"{name}_minpt"], G[f"{name}_maxpt"], name)
+    T = gpu.Topology.from_mesh(mesh)
+    a = [int(x) for x in G[f"{name}_args"]]
+    o, d = G[f"{name}_o"], G[f"{name}_d"]
+    g = gpu.Voxel_Grid([T], a[0])
+    off, pol = g.csr()
+    assert np.array_equal(off, G[f"{name}_vg_offset"]) and np.array_equal(pol, G[f"{name}_vg_polys"])
+    first = G[f"{name}_vg_poly_id"]
+    for kind, part, o1, o2, uv in (("vg", g, None, None, False), ("vgo", g, first, np.roll(first, 1), False),
+                                   ("oct", gpu.Octree([T], a[1], a[2]), None, None, True), ("kd", gpu.KDTree([T], a[3], a[4]), None, None, True)):
+        r = part.Shoot_Batch(o, d, o1, o2, moved=True)
+        ref = {k: G[f"{name}_{kind}_{k}"] for k in ("poly_id", "t", "xyz", "uv")}
+        assert_events_equal(r, ref, uv=uv, what=f"golden {name} {kind}")
+        assert np.array_equal(r["o"], G[f"{name}_{kind}_o_moved"])
+        assert (r["poly_id"] == -2).sum() == (ref["poly_id"] == -2).sum()
+
+
 # ---------------------------------------------------------------- procedural halls
 @pytest.mark.parametrize("level,domain,nrays", [("tiny", 8, 20_000), ("2k", 16, 50_000), ("10k", 32, 100_000), ("50k", 64, 200_000)])
 def test_hall_voxelgrid(gpu, level, domain, nrays):

@@ -1,0 +1,137 @@
+"""CPU-side checks of the product library (no GPU): the C ABI loads and exports every symbol
+include/hare_b200.h declares, the host-side construction steps (Topology ingest, Octree and
+KDTree builders) agree with the oracle, arguments are validated, and every compute entry point
+fails loudly when no device is available (there is no CPU fallback)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import hare_b200 as hb
+from hare_b200 import _lib
+from hare_b200.harness import meshes
+from hare_b200.harness.meshes import Mesh
+from oracle import hare_oracle as ho
+from tests.util import canon_kdtree, canon_octree
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hare_golden.npz"))
+NO_GPU = hb.lib().hare_device_count() == 0
+
+
+@pytest.fixture(scope="module")
+def host_only():
+    """hare_init(NULL, -1): handles without a device replica (build-time tooling mode)."""
+    hb.init(host_only=True)
+    yield hb
+    if not NO_GPU:
+        hb.init([0])
+
+
+def test_abi_exports_every_declared_symbol():
+    syms = _lib.declared_symbols()
+    assert len(syms) >= 28 and "hare_shoot_batch" in syms and "hare_voxelgrid_build" in syms
+    L = hb.lib()
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.SO_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(syms) <= exported
+    assert not [s for s in exported if s.startswith("ho_")], "the oracle must not be linked into the product"
+    assert b"sm_100a" in L.hare_version()
+
+
+def test_shared_object_contains_sm100a_code_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+@pytest.mark.parametrize("level", ["tiny", "2k", "10k"])
+def test_ingest_matches_oracle(host_only, level):
+    mesh = meshes.hall(level)
+    T = hb.Topology.from_mesh(mesh); To = ho.Topology.from_mesh(mesh)
+    v, n, c, mm = To.arrays()
+    assert np.array_equal(T.verts, v) and np.array_equal(T.normals, n) and np.array_equal(T._mm, mm)
+    assert T.Vertex_Count == To.Vertex_Count and T.Polygon_Count == mesh.P
+
+
+def test_ingest_matches_golden_python_restatement(host_only):
+    for name in ("shoebox", "tiny"):
+        mesh = Mesh(G[f"{name}_verts"], G[f"{name}_vcount"], G[f"{name}_minpt"], G[f"{name}_maxpt"], name)
+        T = hb.Topology.from_mesh(mesh)
+        assert np.array_equal(T.verts, G[f"{name}_topo_verts"]) and np.array_equal(T.normals, G[f"{name}_topo_normals"])
+        assert np.array_equal(T._mm, G[f"{name}_topo_minmax"])
+
+
+def test_ingest_rounds_and_welds(host_only):
+    """Math.Round(x, 15) and the 1 mm weld (Hare_Geometry_Topology.cs:342-377)."""
+    T = hb.Topology([0, 0, 0], [2, 2, 2])
+    a = 0.1234567890123456789
+    T.Add_Polygon([[a, 0, 0], [1, 0, 0], [1, 1, 0]])
+    T.Add_Polygon([[a + 2e-4, 1e-4, 0], [1, 1, 0], [0, 1, 1]])        # first vertex shares the 1 mm cell of polygon 0's
+    T.Finish_Topology()
+    assert T.verts[0, 0, 0] == ho.round15(a) == 0.123456789012346
+    assert np.array_equal(T.verts[1, 0], T.verts[0, 0])                # welded onto the first vertex seen
+    assert T.Vertex_Count == 4
+    with pytest.raises(NotImplementedError):
+        T.Add_Polygon(np.zeros((5, 3)))
+
+
+@pytest.mark.parametrize("level,args", [("tiny", (3, 4)), ("2k", (5, 8)), ("10k", (6, 16))])
+def test_octree_build_matches_oracle(host_only, level, args):
+    mesh = meshes.hall(level)
+    t = hb.Octree([hb.Topology.from_mesh(mesh)], *args)
+    o = ho.Octree(ho.Topology.from_mesh(mesh), *args)
+    assert canon_octree(*t.arrays()) == canon_octree(*o.arrays())
+    i = t.info()
+    assert (i["nodes"], i["list_entries"], i["lost"]) == o.info() and i["depth"] <= args[0]
+
+
+@pytest.mark.parametrize("level,args", [("tiny", (8, 4)), ("2k", (14, 8)), ("10k", (18, 16))])
+def test_kdtree_build_matches_oracle(host_only, level, args):
+    mesh = meshes.hall(level)
+    t = hb.KDTree([hb.Topology.from_mesh(mesh)], *args)
+    o = ho.KDTree(ho.Topology.from_mesh(mesh), *args)
+    box, sp, ax, le, lo, lc, pol = t.arrays()
+    assert canon_kdtree(box, sp, ax, le, le + 1, lo, lc, pol) == canon_kdtree(*o.arrays())
+
+
+def test_upload_validation(host_only):
+    T = hb.Topology.from_mesh(meshes.shoebox())
+    with pytest.raises(hb.HareError):     # polygon index out of range
+        hb.Voxel_Grid.from_lists([T], [0, 0, 0, 1, 1, 1], [1, 1, 1], [0, 1], [99])
+    with pytest.raises(hb.HareError):     # child index out of range
+        hb.Octree.from_nodes([T], np.zeros((1, 6)), [5], [0], [0], [0])
+    with pytest.raises(hb.HareError):     # bad axis
+        hb.KDTree.from_nodes([T], np.zeros((3, 6)), [0, 0, 0], [7, -1, -1], [1, -1, -1], [0, 0, 0], [0, 0, 0], [0])
+    g = hb.Voxel_Grid.from_lists([T], [0, 0, 0, 2, 2, 2], [2, 2, 2], np.arange(9), np.arange(8) % 6)
+    obox, vd, ct, n = g.info()
+    assert vd.tolist() == [1.0, 1.0, 1.0] and n == 8 and g.Char_Step == 1.0
+
+
+def test_no_cpu_fallback(host_only):
+    """Host-only handles cannot compute: Shoot, chains and the GPU grid build fail with HARE_ERR_CUDA."""
+    T = hb.Topology.from_mesh(meshes.shoebox())
+    with pytest.raises(hb.HareError, match="no CPU fallback"):
+        hb.Voxel_Grid([T], 10)
+    t = hb.Octree([T], 3, 2)
+    with pytest.raises(hb.HareError, match="no CPU fallback"):
+        t.Shoot_Batch(np.zeros((4, 3)), np.ones((4, 3)))
+    with pytest.raises(hb.HareError, match="no CPU fallback"):
+        t.Reflect_Chain(np.zeros((4, 3)), np.ones((4, 3)), 3)
+
+
+@pytest.mark.skipif(not NO_GPU, reason="only meaningful on a box without a CUDA device")
+def test_device_init_fails_loudly_without_gpu():
+    with pytest.raises(hb.HareError, match="no CUDA device"):
+        hb.init([0])
+
+
+def test_missing_extension_raises(tmp_path):
+    code = ("import os, sys; os.environ['HARE_B200_LIB'] = %r; sys.path.insert(0, %r)\n"
+            "import hare_b200\n"
+            "try:\n    hare_b200.lib()\nexcept hare_b200.HareError as e:\n    print('RAISED', e)\n") % (str(tmp_path / "nope.so"), _lib.ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout
+    assert "RAISED" in out and "no CPU fallback" in out
