@@ -705,8 +705,8 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
-        case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, p->oct.depth }; return launch_shoot_t(t, d, a, st); }
-        case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, p->kd.depth }; return launch_shoot_t(t, d, a, st); }
+        case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->oct.depth }; return launch_shoot_t(t, d, a, st); }
+        case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth }; return launch_shoot_t(t, d, a, st); }
     }
     return fail(HARE_ERR_INVALID, "unknown partition kind");
 }
@@ -738,8 +738,8 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }
-        case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, p->oct.depth }; return launch_chain_t(t, d, a, st); }
-        case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, p->kd.depth }; return launch_chain_t(t, d, a, st); }
+        case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->oct.depth }; return launch_chain_t(t, d, a, st); }
+        case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth }; return launch_chain_t(t, d, a, st); }
     }
     return fail(HARE_ERR_INVALID, "unknown partition kind");
 }

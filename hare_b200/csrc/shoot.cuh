@@ -41,13 +41,15 @@ __device__ __forceinline__ void load_poly(const PolyRec* __restrict__ polys, uin
 // it never changes a result, it only spares the 128-byte fetch and the exact FP64 test.
 // Evaluated in FP32 in a frame local to the current voxel: p = a point of the ray at the voxel (rounded
 // to FP32), v = c - p is at most a voxel diagonal plus a polygon radius long, so |v x d|^2 = |v|^2|d|^2 -
-// (v.d)^2 has no large-number cancellation; its rounding error (~1e-6 m^2 for |v| <= 4 m, plus the 3e-6 m
-// rounding of p and of the stored centre) is far inside the 1e-3 m by which the host pads the radius.
+// (v.d)^2 has no large-number cancellation.  Error budget: the FP32 evaluation is good to ~3e-7 |v|^2|d|^2,
+// covered 13x by the explicit 4e-6 |v|^2 term below (it matters only when a tree leaf lists a polygon far
+// from its own box); the 3e-6 m rounding of p and of the stored centre moves the line by < 1e-5 m, far
+// inside the 1e-3 m + 1e-5 r by which the host pads the radius.
 __device__ __forceinline__ bool cull_sphere(const float4 s, float px, float py, float pz, float dx, float dy, float dz, float dd) {
     const float vx = s.x - px, vy = s.y - py, vz = s.z - pz;
     const float vd = fmaf(vx, dx, fmaf(vy, dy, vz * dz));
     const float vv = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
-    return fmaf(-vd, vd, vv * dd) > (s.w * s.w) * dd;   // |v x d|^2 > r^2 |d|^2   (NaN -> keep)
+    return fmaf(-vd, vd, vv * dd) > fmaf(4e-6f, vv, s.w * s.w) * dd;   // |v x d|^2 > (r^2 + margin) |d|^2   (NaN -> keep)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -176,6 +178,7 @@ struct alignas(64) OctNode {
 struct OctDev {
     const OctNode* __restrict__ nodes;
     const uint32_t* __restrict__ lists;
+    const float4* __restrict__ sph;   // padded bounding spheres, see cull_sphere()
     int depth;   // deepest level (root = 0)
 };
 
@@ -213,6 +216,8 @@ __device__ __forceinline__ int shoot_one(const OctDev& T, const PolyRec* __restr
     // order, depth first.  A frame per level (first child, parent interval, next q to "pop")
     // replays that order lazily; the push-time filter depends only on the parent interval.
     int fchild[HARE_OCT_MAXLVL]; double fa[HARE_OCT_MAXLVL], fb[HARE_OCT_MAXLVL]; int fq[HARE_OCT_MAXLVL];
+    const float fdx = (float)R.dx, fdy = (float)R.dy, fdz = (float)R.dz, fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
+    uint32_t last = 0xffffffffu;
     int sp = -1;
     int cur = 0;
     bool have_cur = true, hit = false;
@@ -225,10 +230,18 @@ __device__ __forceinline__ int shoot_one(const OctDev& T, const PolyRec* __restr
                 const OctNode* n = T.nodes + cur;
                 const uint4 m = __ldg(reinterpret_cast<const uint4*>(n) + 3);   // first_child, list_off, list_cnt, pad
                 if ((int)m.x < 0) {
+                    // voxel-local FP32 frame for the conservative sphere reject (cull_sphere): ray point at the leaf entry
+                    const double te = ca > 0.0 ? ca : 0.0;
+                    const float px = (float)fma(R.dx, te, R.x), py = (float)fma(R.dy, te, R.y), pz = (float)fma(R.dz, te, R.z);
                     for (uint32_t k = 0; k < m.z; ++k) {
                         const uint32_t i = __ldg(T.lists + m.y + k);
                         c.entry();
                         if ((int)i == o1 || (int)i == o2) continue;
+                        // a polygon already tested for this ray (it sits in several leaves) cannot change anything:
+                        // its t is not below closestT any more, so neither the update nor the early return fires
+                        if (i == last || (int)i == ev.pid) continue;
+                        if (cull_sphere(__ldg(T.sph + i), px, py, pz, fdx, fdy, fdz, fdd)) continue;
+                        last = i;
                         c.test();
                         double P[16], t, u, v;
                         load_poly(polys, i, P);
@@ -273,6 +286,7 @@ struct alignas(64) KdNode {
 struct KdDev {
     const KdNode* __restrict__ nodes;
     const uint32_t* __restrict__ lists;
+    const float4* __restrict__ sph;   // padded bounding spheres, see cull_sphere()
     int depth;
 };
 
@@ -280,15 +294,16 @@ struct KdDev {
 #define HARE_KD_PAD 1e-5   /* spatial inflation of node boxes for the conservative prune */
 
 // The reference visits every leaf (both children always pushed, KDTree.cs:355-356) and keeps the
-// strict minimum of t over all polygons: its result is the global closest hit.  This walk follows
-// the same first/second child order (:249-353) but skips a subtree when the ray's parameter
-// interval inside the node's box, inflated by HARE_KD_PAD, lies wholly beyond the current closest
-// hit or behind the origin -- such a subtree cannot hold a polygon hit at t <= closest.  Results
-// are identical except that among polygons hit at exactly equal t the reference keeps the first in
-// its exhaustive DFS order (the documented exact-edge ties).
+// strict minimum of t over all polygons: its result is the global closest hit.  This walk goes
+// near child first and skips a subtree when the ray's parameter interval inside the node's box,
+// inflated by HARE_KD_PAD, lies wholly beyond the current closest hit or behind the origin -- such
+// a subtree cannot hold a polygon hit at t <= closest.  Results are identical except that among
+// polygons hit at exactly equal t the reference keeps the first in its exhaustive DFS order (the
+// documented exact-edge ties).
 __device__ __forceinline__ bool kd_box_reachable(const double2 a, const double2 b, const double2 cc, const Ray3& R,
-                                                 const double* inv, double closest) {
-    double lo = 0.0, hi = closest;
+                                                 const double* inv, double closest, double& lo) {
+    double hi = closest;
+    lo = 0.0;
     const double mn[3] = { a.x - HARE_KD_PAD, a.y - HARE_KD_PAD, b.x - HARE_KD_PAD };
     const double mx[3] = { b.y + HARE_KD_PAD, cc.x + HARE_KD_PAD, cc.y + HARE_KD_PAD };
     const double o[3] = { R.x, R.y, R.z }, d[3] = { R.dx, R.dy, R.dz };
@@ -318,21 +333,25 @@ __device__ __forceinline__ int shoot_one(const KdDev& T, const PolyRec* __restri
     uint32_t last = 0xffffffffu;
     // reciprocal used only by the conservative prune (its rounding is far inside HARE_KD_PAD)
     const double inv[3] = { 1.0 / R.dx, 1.0 / R.dy, 1.0 / R.dz };
+    const float fdx = (float)R.dx, fdy = (float)R.dy, fdz = (float)R.dz, fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
     if (blind) return 0;   // Ray_ID == 0: zero-initialised mailbox rejects every polygon (KDTree.cs:58-66, 224-229)
     while (sp > 0) {
         const int ni = stack[--sp];
         const double2* q = reinterpret_cast<const double2*>(T.nodes + ni);
         const double2 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2), dd = __ldg(q + 3);
-        if (!kd_box_reachable(a, b, cc, R, inv, closest)) continue;
+        double t_in;
+        if (!kd_box_reachable(a, b, cc, R, inv, closest, t_in)) continue;
         c.cell();
         const int left = __double2loint(dd.y), axis = __double2hiint(dd.y);
         if (left < 0) {
             const uint32_t off = (uint32_t)__double2loint(dd.x), cnt = (uint32_t)__double2hiint(dd.x);
+            const float px = (float)fma(R.dx, t_in, R.x), py = (float)fma(R.dy, t_in, R.y), pz = (float)fma(R.dz, t_in, R.z);
             for (uint32_t k = 0; k < cnt; ++k) {
                 const uint32_t i = __ldg(T.lists + off + k);
                 c.entry();
                 if ((int)i == o1 || (int)i == o2) continue;
                 if (i == last || (int)i == ev.pid) continue;   // mailbox: each polygon counts once
+                if (cull_sphere(__ldg(T.sph + i), px, py, pz, fdx, fdy, fdz, fdd)) continue;
                 last = i;
                 c.test();
                 double P[16], t, u, v;
@@ -346,19 +365,11 @@ __device__ __forceinline__ int shoot_one(const KdDev& T, const PolyRec* __restri
                 }
             }
         } else {
-            // first / second  KDTree.cs:249-353
-            const double mn[3] = { a.x, a.y, b.x }, mx[3] = { b.y, cc.x, cc.y };
-            const double o[3] = { R.x, R.y, R.z }, d[3] = { R.dx, R.dy, R.dz };
-            const int b1 = (axis == 0) ? 1 : 0, b2 = (axis == 2) ? 1 : 2;
-            const double oa = axis == 0 ? o[0] : (axis == 1 ? o[1] : o[2]);
-            const double da = axis == 0 ? d[0] : (axis == 1 ? d[1] : d[2]);
-            const double side = oa - dd.x;
-            const double tSplit = -side / da;
-            const double s1 = (b1 == 0 ? o[0] : o[1]) + tSplit * (b1 == 0 ? d[0] : d[1]);
-            const double s2 = (b2 == 1 ? o[1] : o[2]) + tSplit * (b2 == 1 ? d[1] : d[2]);
-            const bool inside = (s1 <= (b1 == 0 ? mx[0] : mx[1]) && s1 >= (b1 == 0 ? mn[0] : mn[1]) &&
-                                 s2 <= (b2 == 1 ? mx[1] : mx[2]) && s2 >= (b2 == 1 ? mn[1] : mn[2]));
-            const bool right_first = inside ? (side >= 0) : !(side >= 0);
+            // The reference's first/second rule (KDTree.cs:249-353) only fixes the order in which its exhaustive
+            // walk meets the leaves; the result is the global minimum of t either way.  Here the child on the
+            // origin's side goes first so that the prune above can cut the far side as early as possible.
+            const double oa = axis == 0 ? R.x : (axis == 1 ? R.y : R.z);
+            const bool right_first = oa > dd.x;
             const int first = right_first ? left + 1 : left, second = right_first ? left : left + 1;
             if (sp + 2 <= HARE_KD_MAXSTACK) { stack[sp++] = second; stack[sp++] = first; }
         }
