@@ -47,6 +47,20 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the traversal kernel, per launch, from the committed
+    `ncu --set full` capture of this same configuration (profiles/); None for any other configuration."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_bench_kernel.json")
+    try:
+        j = json.load(open(p))
+        c = j["config"]
+        if (c["mesh"], c["domain"], c["rays"], c["order"]) == (args.mesh, args.domain, args.rays, args.order):
+            return float(j["traffic_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -186,9 +200,15 @@ def run_b200(args):
     L = lib()
 
     mesh, o, d = make_workload(args, rank)
+    N, order = args.rays, args.order
+    cpu_res = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # the CPU leg runs first, on an otherwise idle host (before pinned buffers and GPU work exist)
+        cpu_res = cpu_leg(args, mesh, o, d, args.cpu_seconds, os.cpu_count() or 1)
+    if world > 1:
+        dist.barrier()
     T = hb.Topology.from_mesh(mesh)
     part = hb.Voxel_Grid([T], args.domain)
-    N, order = args.rays, args.order
 
     # ---------------- device-resident leg: rays already in HBM --------------------------------------
     o_d = torch.from_numpy(o).to(dev); d_d = torch.from_numpy(d).to(dev)
@@ -297,7 +317,7 @@ def run_b200(args):
         bytes_per_shoot, avg = None, None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            c = cpu_leg(args, mesh, o, d, args.cpu_seconds, cores)
+            c = cpu_res
             bytes_per_shoot, avg = algorithmic_bytes(c["counters"], c["shots"])
             cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": cores, "kind": "port",
                    "sample": f"first {c['n']} chains x {order} Shoots ({c['shots']} Shoots, {c['seconds']:.1f} s) of the {N}-chain workload"}
@@ -315,8 +335,8 @@ def run_b200(args):
             "metric": "Mrays/s closest-hit Shoot", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_kind": peak_kind, "kernel": "chain_kernel<VGrid>", "kernel_ms": kernel_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args),
+                         "peak_kind": peak_kind, "kernel": "vg_walk_kernel<CHAIN>", "kernel_ms": kernel_ms,
                          "bytes_per_shoot": bytes_per_shoot, "per_shoot": avg,
                          "formula": "56 + 36 + 8*cells + 4*entries + 128*tests (SURVEY.md 8(d)), oracle-counted"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
