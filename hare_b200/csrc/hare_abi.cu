@@ -698,6 +698,27 @@ static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, con
     return launch_vg_walk2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, w, 0, st);
 }
 
+#ifndef HARE_OCT_SBATCH
+#define HARE_OCT_SBATCH 6
+#endif
+#ifndef HARE_OCT_NMAX
+#define HARE_OCT_NMAX 6
+#endif
+static bool use_oct_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_OCT_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
+
+// Octree: phased persistent kernel (oct_walk.cuh), one 512-thread CTA per SM
+template <bool CHAIN>
+static int launch_oct_walk(const OctDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
+                           int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+    if (N <= 0) return HARE_OK;
+    int64_t blocks = std::min<int64_t>((N + HARE_OCT_THREADS - 1) / HARE_OCT_THREADS, (int64_t)d.sms);
+    if (w.counters) oct_walk_kernel<CHAIN, true, HARE_OCT_SBATCH, HARE_OCT_NMAX><<<(unsigned)blocks, HARE_OCT_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, N, order, w);
+    else oct_walk_kernel<CHAIN, false, HARE_OCT_SBATCH, HARE_OCT_NMAX><<<(unsigned)blocks, HARE_OCT_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, N, order, w);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return HARE_OK;
+}
+
 static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
     switch (p->kind) {
         case HARE_VOXEL_GRID: {
@@ -705,7 +726,12 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
-        case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->oct.depth }; return launch_shoot_t(t, d, a, st); }
+        case HARE_OCTREE: {
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->oct.depth };
+            if (use_oct_v1()) return launch_shoot_t(t, d, a, st);
+            WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
+            return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
+        }
         case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth }; return launch_shoot_t(t, d, a, st); }
     }
     return fail(HARE_ERR_INVALID, "unknown partition kind");
@@ -738,7 +764,12 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }
-        case HARE_OCTREE: { OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->oct.depth }; return launch_chain_t(t, d, a, st); }
+        case HARE_OCTREE: {
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->oct.depth };
+            if (use_oct_v1()) return launch_chain_t(t, d, a, st);
+            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
+            return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);
+        }
         case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth }; return launch_chain_t(t, d, a, st); }
     }
     return fail(HARE_ERR_INVALID, "unknown partition kind");

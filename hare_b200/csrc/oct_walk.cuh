@@ -1,0 +1,203 @@
+// oct_walk.cuh -- K3 (and K5 on an Octree): persistent, warp-synchronous phased traversal of
+// Hare's Octree ("Octree - alt.cs":159-306), built like vg_walk.cuh.
+//
+// A thread owns one ray (or one reflection chain) at a time.  Each trip round the main loop the
+// warp goes through four phases together:
+//
+//   S  (batched)  finish the Shoot that ended (event out; in a chain, reflect), fetch the next ray,
+//                 reciprocals and root interval (:165-190);
+//   N  (cheap)    replay the reference's LIFO walk until a leaf with a non-empty list is reached:
+//                 one frame per level (first child, parent interval, next octant) reproduces the
+//                 far-first pop order and the push-time filter (:245-272) lazily, the pop-time prunes
+//                 (:207-211) are applied when a node is entered;
+//   C  (cheap)    next (up to) four entries of the leaf list: poly_origin and duplicate skip, then the
+//                 conservative FP32 sphere reject (cull_sphere) in a frame local to the leaf;
+//   T  (dense)    one exact test: 128-byte record, slow-path Moller-Trumbore with u, v (:224), strict
+//                 t < closestT, early `return` when closestT <= nodeTmin (:233-237).
+//
+// Entries are taken in stored order and survivors are tested lowest first, so the sequence of
+// closestT updates -- and with it the early return and the pop-time prune -- is the reference's.
+#pragma once
+#include "shoot.cuh"
+#include "vg_walk.cuh"   // WalkOut, ST_* states
+
+namespace hare {
+
+#ifndef HARE_OCT_THREADS
+#define HARE_OCT_THREADS 512
+#endif
+
+template <bool CHAIN, bool COUNT, int S_BATCH, int N_MAX>
+__global__ void __launch_bounds__(HARE_OCT_THREADS, 1)
+oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
+                const double* __restrict__ o, const double* __restrict__ d,
+                const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a,
+                long long N, int order, const WalkOut out) {
+    CntT<COUNT> c;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long next = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long ray = -1;
+
+    Ray3 R = { 0, 0, 0, 0, 0, 0 };
+    double ix = 0, iy = 0, iz = 0;                 // guarded reciprocals :165-167
+    double closest = DBL_MAX, eu = 0, ev = 0;      // closestT and the u, v of the best event
+    double ca = 0, cb = 0;                         // interval of the node being entered / of the current leaf
+    float fdx = 0, fdy = 0, fdz = 0, fdd = 0, fpx = 0, fpy = 0, fpz = 0;
+    int fchild[HARE_OCT_MAXLVL]; double fa[HARE_OCT_MAXLVL], fb[HARE_OCT_MAXLVL]; int fq[HARE_OCT_MAXLVL];
+    int sp = -1, cur = 0, sgn = 0;
+    int pid = -1, or1 = -1, or2 = -1, bounce = 0;
+    uint32_t lpos = 0, lend = 0, last = 0xffffffffu;
+    uint32_t bid0 = 0, bid1 = 0, bid2 = 0, bid3 = 0, bmask = 0;
+    bool have_cur = false, hit = false;
+    int state = ST_NEED_RAY;
+    int fin = 2;   // 2 = running; 1 hit, 0 miss
+    unsigned int shots = 0;
+
+    while (true) {
+        // ------------------------------------------------------------------ S phase
+        const unsigned want = __ballot_sync(0xffffffffu, (state == ST_NEED_RAY || state == ST_NEED_SETUP) || (state == ST_WALK && fin != 2));
+        const unsigned busy = __ballot_sync(0xffffffffu, state == ST_WALK && fin == 2);
+        if (want == 0 && busy == 0) break;
+        if (want && (__popc(want) >= S_BATCH || busy == 0)) {
+            if (state == ST_WALK && fin != 2) {
+                // ---- the Shoot is over
+                const bool h = fin == 1;
+                const double bx = R.x + R.dx * closest, by = R.y + R.dy * closest, bz = R.z + R.dz * closest;   // X_Point, Polygons.cs:749
+                if (h) c.hit();
+                state = ST_NEED_RAY;
+                if (CHAIN) {
+                    ++shots;
+                    if (out.ev_pid) out.ev_pid[ray * order + bounce] = h ? pid : -1;
+                    if (out.ev_t) out.ev_t[ray * order + bounce] = h ? closest : 0.0;
+                    ++bounce;
+                    if (h) {
+                        const double* P = polys[pid].v;
+                        const double nx = __ldg(P + 12), ny = __ldg(P + 13), nz = __ldg(P + 14);
+                        const double k = 2 * ((R.dx * nx) + (R.dy * ny) + (R.dz * nz));
+                        R.dx = R.dx - k * nx; R.dy = R.dy - k * ny; R.dz = R.dz - k * nz;
+                        R.x = bx; R.y = by; R.z = bz;
+                        or1 = pid;
+                        if (bounce < order) state = ST_NEED_SETUP;
+                    }
+                    if (state == ST_NEED_RAY) {
+                        for (int q = bounce; q < order; ++q) {
+                            if (out.ev_pid) out.ev_pid[ray * order + q] = -3;
+                            if (out.ev_t) out.ev_t[ray * order + q] = 0;
+                        }
+                        if (out.fin_o) { out.fin_o[3 * ray] = R.x; out.fin_o[3 * ray + 1] = R.y; out.fin_o[3 * ray + 2] = R.z; }
+                        if (out.fin_d) { out.fin_d[3 * ray] = R.dx; out.fin_d[3 * ray + 1] = R.dy; out.fin_d[3 * ray + 2] = R.dz; }
+                        if (out.nshots) out.nshots[ray] = bounce;
+                    }
+                } else {
+                    out.pid[ray] = h ? pid : -1;
+                    if (out.t) out.t[ray] = h ? closest : 0.0;
+                    if (out.xyz) { out.xyz[3 * ray] = h ? bx : 0.0; out.xyz[3 * ray + 1] = h ? by : 0.0; out.xyz[3 * ray + 2] = h ? bz : 0.0; }
+                    if (out.uv) { out.uv[2 * ray] = h ? eu : 0.0; out.uv[2 * ray + 1] = h ? ev : 0.0; }
+                    if (out.omoved) { out.omoved[3 * ray] = R.x; out.omoved[3 * ray + 1] = R.y; out.omoved[3 * ray + 2] = R.z; }   // the Octree never moves a ray
+                }
+                fin = 2;
+            }
+            if (state == ST_NEED_RAY) {
+                if (next < N) {
+                    ray = next; next += stride;
+                    R.x = o[3 * ray]; R.y = o[3 * ray + 1]; R.z = o[3 * ray + 2];
+                    R.dx = d[3 * ray]; R.dy = d[3 * ray + 1]; R.dz = d[3 * ray + 2];
+                    or1 = o1a ? o1a[ray] : -1; or2 = o2a ? o2a[ray] : -1;
+                    bounce = 0;
+                    state = ST_NEED_SETUP;
+                } else {
+                    state = ST_DONE;
+                }
+            }
+            if (state == ST_NEED_SETUP) {
+                state = ST_WALK; fin = 2;
+                hit = false; closest = DBL_MAX; pid = -1; eu = 0; ev = 0; last = 0xffffffffu;
+                lpos = 0; lend = 0; bmask = 0; sp = -1;
+                ix = fabs(R.dx) > 1e-16 ? 1.0 / R.dx : 1e16;
+                iy = fabs(R.dy) > 1e-16 ? 1.0 / R.dy : 1e16;
+                iz = fabs(R.dz) > 1e-16 ? 1.0 / R.dz : 1e16;
+                oct_interval(T.nodes, R, ix, iy, iz, ca, cb);
+                if (cb < ca || cb < 0) fin = 0;                       // :185-190
+                sgn = (R.dx >= 0 ? 0 : 4) | (R.dy >= 0 ? 0 : 2) | (R.dz >= 0 ? 0 : 1);   // ComputeTraversalOrder: order[q] = q ^ sgn
+                cur = 0; have_cur = true;
+                fdx = (float)R.dx; fdy = (float)R.dy; fdz = (float)R.dz;
+                fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
+            }
+        }
+        // ------------------------------------------------------------------ N phase: walk to the next leaf
+        if (state == ST_WALK && fin == 2 && bmask == 0 && lpos >= lend) {
+#pragma unroll 1
+            for (int guard = 0; guard < N_MAX; ++guard) {
+                if (have_cur) {
+                    have_cur = false;
+                    if (!(cb < ca || cb < 0) && !(hit && closest <= ca)) {            // pop-time prunes :207-211
+                        c.cell();
+                        const uint4 m = __ldg(reinterpret_cast<const uint4*>(T.nodes + cur) + 3);   // first_child, list_off, list_cnt
+                        if ((int)m.x < 0) {
+                            lpos = m.y; lend = m.y + m.z;
+                            if (lpos < lend) {
+                                // leaf-local FP32 frame for cull_sphere: the ray point where the leaf is entered
+                                const double te = ca > 0.0 ? ca : 0.0;
+                                fpx = (float)fma(R.dx, te, R.x); fpy = (float)fma(R.dy, te, R.y); fpz = (float)fma(R.dz, te, R.z);
+                                break;
+                            }
+                        } else if (sp + 1 < HARE_OCT_MAXLVL) {
+                            ++sp; fchild[sp] = (int)m.x; fa[sp] = ca; fb[sp] = cb; fq[sp] = 7;
+                        }
+                    }
+                    continue;
+                }
+                if (sp < 0) { fin = hit ? 1 : 0; break; }                              // stack empty :276-283
+                if (fq[sp] < 0) { --sp; continue; }
+                const int q = fq[sp]--;
+                const int child = fchild[sp] + (q ^ sgn);                             // pushed near->far, popped far->near
+                double lo, hi;
+                oct_interval(T.nodes + child, R, ix, iy, iz, lo, hi);
+                const double pa = fa[sp], pb = fb[sp];
+                if (hi < lo || hi < 0 || lo > pb || hi < pa) continue;                // push-time filter :268
+                cur = child; ca = net_max(lo, pa); cb = net_min(hi, pb); have_cur = true;
+            }
+        }
+        // ------------------------------------------------------------------ C phase: cull a batch of leaf entries
+        if (state == ST_WALK && fin == 2 && bmask == 0 && lpos < lend) {
+            const uint32_t n = min(4u, lend - lpos);
+            bid0 = __ldg(T.lists + lpos);
+            bid1 = (n > 1) ? __ldg(T.lists + lpos + 1) : bid0;
+            bid2 = (n > 2) ? __ldg(T.lists + lpos + 2) : bid0;
+            bid3 = (n > 3) ? __ldg(T.lists + lpos + 3) : bid0;
+            const float4 s0 = __ldg(T.sph + bid0), s1 = __ldg(T.sph + bid1), s2 = __ldg(T.sph + bid2), s3 = __ldg(T.sph + bid3);
+            lpos += n;
+            if (COUNT) c.entries += n;
+            // poly_origin skip (:218); a polygon already tested for this ray (it sits in several leaves) cannot
+            // change anything: its t is not below closestT any more, so neither the update nor the early return fires
+            auto keep = [&](uint32_t i, const float4& s) {
+                return !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) && !cull_sphere(s, fpx, fpy, fpz, fdx, fdy, fdz, fdd);
+            };
+            bmask = (keep(bid0, s0) ? 1u : 0u) | ((n > 1 && keep(bid1, s1)) ? 2u : 0u) |
+                    ((n > 2 && keep(bid2, s2)) ? 4u : 0u) | ((n > 3 && keep(bid3, s3)) ? 8u : 0u);
+        }
+        // ------------------------------------------------------------------ T phase: the exact FP64 test (slow path: u, v)
+        if (state == ST_WALK && fin == 2 && bmask) {
+            const uint32_t pend = (bmask & 1u) ? bid0 : ((bmask & 2u) ? bid1 : ((bmask & 4u) ? bid2 : bid3));
+            bmask &= bmask - 1u;
+            last = pend;
+            c.test();
+            double P[16], t, u, v;
+            load_poly(polys, pend, P);
+            if (poly_intersect<true>(P, R, t, u, v) && t > 0.0000000001) {
+                if (t < closest) {
+                    closest = t; hit = true; pid = (int)pend; eu = u; ev = v;
+                    if (closest <= ca) fin = 1;                                         // early return :233-237 (ca = this leaf's nodeTmin)
+                }
+            }
+        }
+    }
+    if (CHAIN) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) shots += __shfl_xor_sync(0xffffffffu, shots, off);
+        if ((threadIdx.x & 31) == 0 && shots) atomicAdd(out.total_shots, (unsigned long long)shots);
+    }
+    flush_counters<COUNT>(c, out.counters);
+}
+
+}  // namespace hare
