@@ -704,6 +704,12 @@ static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, con
 #ifndef HARE_OCT_NMAX
 #define HARE_OCT_NMAX 6
 #endif
+#ifndef HARE_OCT_NBATCH
+#define HARE_OCT_NBATCH 8
+#endif
+#ifndef HARE_OCT_TBATCH
+#define HARE_OCT_TBATCH 6
+#endif
 static bool use_oct_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_OCT_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
 
 // Octree: phased persistent kernel (oct_walk.cuh), one 512-thread CTA per SM
@@ -712,8 +718,8 @@ static int launch_oct_walk(const OctDev& t, const PartDev& d, const double* o, c
                            int64_t N, int order, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
     int64_t blocks = std::min<int64_t>((N + HARE_OCT_THREADS - 1) / HARE_OCT_THREADS, (int64_t)d.sms);
-    if (w.counters) oct_walk_kernel<CHAIN, true, HARE_OCT_SBATCH, HARE_OCT_NMAX><<<(unsigned)blocks, HARE_OCT_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, N, order, w);
-    else oct_walk_kernel<CHAIN, false, HARE_OCT_SBATCH, HARE_OCT_NMAX><<<(unsigned)blocks, HARE_OCT_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, N, order, w);
+    if (w.counters) oct_walk_kernel<CHAIN, true, HARE_OCT_SBATCH, HARE_OCT_NMAX, HARE_OCT_NBATCH, HARE_OCT_TBATCH><<<(unsigned)blocks, HARE_OCT_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, N, order, w);
+    else oct_walk_kernel<CHAIN, false, HARE_OCT_SBATCH, HARE_OCT_NMAX, HARE_OCT_NBATCH, HARE_OCT_TBATCH><<<(unsigned)blocks, HARE_OCT_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, N, order, w);
     ++g_launches;
     CK(cudaGetLastError());
     return HARE_OK;

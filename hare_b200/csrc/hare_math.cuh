@@ -25,6 +25,11 @@ struct alignas(128) PolyRec { double v[16]; };
 struct Ray3 { double x, y, z, dx, dy, dz; };
 
 // .NET Math.Max / Math.Min (NaN-propagating; used at "Octree - alt.cs":182-183, AABB_Main.cs:199-200)
+#if defined(__CUDA_ARCH__)
+// device: DMNMX already orders -0 < +0 like .NET; only the NaN case needs the fix-up
+HD double net_max(double a, double b) { const double r = fmax(a, b); return (a != a) ? a : ((b != b) ? b : r); }
+HD double net_min(double a, double b) { const double r = fmin(a, b); return (a != a) ? a : ((b != b) ? b : r); }
+#else
 HD double net_max(double a, double b) {
     if (a != a) return a;
     if (b != b) return b;
@@ -37,6 +42,7 @@ HD double net_min(double a, double b) {
     if (a == b) return (copysign(1.0, a) < 0) ? a : b;
     return a < b ? a : b;
 }
+#endif
 
 // (int)Math.Floor(x) as RyuJIT x64 evaluates it: cvttsd2si gives 0x80000000 for NaN/overflow.
 HD int32_t floor_to_int(double x) {

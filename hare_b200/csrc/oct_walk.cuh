@@ -10,7 +10,7 @@
 //                 one frame per level (first child, parent interval, next octant) reproduces the
 //                 far-first pop order and the push-time filter (:245-272) lazily, the pop-time prunes
 //                 (:207-211) are applied when a node is entered;
-//   C  (cheap)    next (up to) four entries of the leaf list: poly_origin and duplicate skip, then the
+//   C  (cheap)    next (up to) eight entries of the leaf list: poly_origin and duplicate skip, then the
 //                 conservative FP32 sphere reject (cull_sphere) in a frame local to the leaf;
 //   T  (dense)    one exact test: 128-byte record, slow-path Moller-Trumbore with u, v (:224), strict
 //                 t < closestT, early `return` when closestT <= nodeTmin (:233-237).
@@ -23,11 +23,14 @@
 
 namespace hare {
 
+#ifndef HARE_OCT_CB
+#define HARE_OCT_CB 8   /* leaf entries culled per C round */
+#endif
 #ifndef HARE_OCT_THREADS
 #define HARE_OCT_THREADS 512
 #endif
 
-template <bool CHAIN, bool COUNT, int S_BATCH, int N_MAX>
+template <bool CHAIN, bool COUNT, int S_BATCH, int N_MAX, int N_BATCH, int T_BATCH>
 __global__ void __launch_bounds__(HARE_OCT_THREADS, 1)
 oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                 const double* __restrict__ o, const double* __restrict__ d,
@@ -47,7 +50,7 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
     int sp = -1, cur = 0, sgn = 0;
     int pid = -1, or1 = -1, or2 = -1, bounce = 0;
     uint32_t lpos = 0, lend = 0, last = 0xffffffffu;
-    uint32_t bid0 = 0, bid1 = 0, bid2 = 0, bid3 = 0, bmask = 0;
+    uint32_t bid[HARE_OCT_CB] = { 0 }, bmask = 0;   // batch of up to 8 leaf entries; bit k = entry k survived the cull
     bool have_cur = false, hit = false;
     int state = ST_NEED_RAY;
     int fin = 2;   // 2 = running; 1 hit, 0 miss
@@ -58,7 +61,16 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
         const unsigned want = __ballot_sync(0xffffffffu, (state == ST_NEED_RAY || state == ST_NEED_SETUP) || (state == ST_WALK && fin != 2));
         const unsigned busy = __ballot_sync(0xffffffffu, state == ST_WALK && fin == 2);
         if (want == 0 && busy == 0) break;
-        if (want && (__popc(want) >= S_BATCH || busy == 0)) {
+        // N and T are dear and usually wanted by few lanes while C (cheap, long leaf lists) is wanted by most:
+        // they run once N_BATCH / T_BATCH lanes wait for them, or when nothing cheaper is left to do
+        const bool needN = state == ST_WALK && fin == 2 && bmask == 0 && lpos >= lend;
+        const bool needC = state == ST_WALK && fin == 2 && bmask == 0 && lpos < lend;
+        const bool needT = state == ST_WALK && fin == 2 && bmask != 0;
+        const int nN = __popc(__ballot_sync(0xffffffffu, needN)), nC = __popc(__ballot_sync(0xffffffffu, needC));
+        const int nT = __popc(__ballot_sync(0xffffffffu, needT));
+        const bool doT = nT > 0 && (nT >= T_BATCH || nC == 0);
+        const bool doN = nN > 0 && (nN >= N_BATCH || (nC == 0 && !doT));
+        if (want && (__popc(want) >= S_BATCH || busy == 0 || (nC == 0 && !doT && !doN))) {
             if (state == ST_WALK && fin != 2) {
                 // ---- the Shoot is over
                 const bool h = fin == 1;
@@ -125,7 +137,7 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
             }
         }
         // ------------------------------------------------------------------ N phase: walk to the next leaf
-        if (state == ST_WALK && fin == 2 && bmask == 0 && lpos >= lend) {
+        if (doN && needN) {
 #pragma unroll 1
             for (int guard = 0; guard < N_MAX; ++guard) {
                 if (have_cur) {
@@ -160,25 +172,33 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
         }
         // ------------------------------------------------------------------ C phase: cull a batch of leaf entries
         if (state == ST_WALK && fin == 2 && bmask == 0 && lpos < lend) {
-            const uint32_t n = min(4u, lend - lpos);
-            bid0 = __ldg(T.lists + lpos);
-            bid1 = (n > 1) ? __ldg(T.lists + lpos + 1) : bid0;
-            bid2 = (n > 2) ? __ldg(T.lists + lpos + 2) : bid0;
-            bid3 = (n > 3) ? __ldg(T.lists + lpos + 3) : bid0;
-            const float4 s0 = __ldg(T.sph + bid0), s1 = __ldg(T.sph + bid1), s2 = __ldg(T.sph + bid2), s3 = __ldg(T.sph + bid3);
+            const uint32_t n = min((uint32_t)HARE_OCT_CB, lend - lpos);
+            // ids, then bounding spheres: two groups of independent loads, so one round pays two memory latencies for 8 entries
+#pragma unroll
+            for (int j = 0; j < HARE_OCT_CB; ++j) bid[j] = __ldg(T.lists + lpos + (j < (int)n ? j : 0));
+            float4 s[HARE_OCT_CB];
+#pragma unroll
+            for (int j = 0; j < HARE_OCT_CB; ++j) s[j] = __ldg(T.sph + bid[j]);
             lpos += n;
             if (COUNT) c.entries += n;
             // poly_origin skip (:218); a polygon already tested for this ray (it sits in several leaves) cannot
             // change anything: its t is not below closestT any more, so neither the update nor the early return fires
-            auto keep = [&](uint32_t i, const float4& s) {
-                return !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) && !cull_sphere(s, fpx, fpy, fpz, fdx, fdy, fdz, fdd);
-            };
-            bmask = (keep(bid0, s0) ? 1u : 0u) | ((n > 1 && keep(bid1, s1)) ? 2u : 0u) |
-                    ((n > 2 && keep(bid2, s2)) ? 4u : 0u) | ((n > 3 && keep(bid3, s3)) ? 8u : 0u);
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < HARE_OCT_CB; ++j) {
+                const uint32_t i = bid[j];
+                const bool keep = (j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
+                                  !cull_sphere(s[j], fpx, fpy, fpz, fdx, fdy, fdz, fdd);
+                m |= keep ? (1u << j) : 0u;
+            }
+            bmask = m;
         }
         // ------------------------------------------------------------------ T phase: the exact FP64 test (slow path: u, v)
-        if (state == ST_WALK && fin == 2 && bmask) {
-            const uint32_t pend = (bmask & 1u) ? bid0 : ((bmask & 2u) ? bid1 : ((bmask & 4u) ? bid2 : bid3));
+        if (doT && state == ST_WALK && fin == 2 && bmask != 0) {
+            const int kk = __ffs(bmask) - 1;            // lowest survivor first: stored list order
+            uint32_t pend = bid[0];
+#pragma unroll
+            for (int j = 1; j < HARE_OCT_CB; ++j) pend = (kk == j) ? bid[j] : pend;
             bmask &= bmask - 1u;
             last = pend;
             c.test();
