@@ -130,6 +130,10 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                 iz = fabs(R.dz) > 1e-16 ? 1.0 / R.dz : 1e16;
                 oct_interval(T.nodes, R, ix, iy, iz, ca, cb);
                 if (cb < ca || cb < 0) fin = 0;                       // :185-190
+                // A ray with a NaN/Inf component is reported as a miss (documented deviation): the
+                // walk below uses oct_interval_finite, which assumes finite operands.  (In the reference such a ray
+                // makes every comparison false and every t NaN, which also ends in a miss.)
+                if (!(isfinite(R.x) && isfinite(R.y) && isfinite(R.z) && isfinite(R.dx) && isfinite(R.dy) && isfinite(R.dz))) fin = 0;
                 sgn = (R.dx >= 0 ? 0 : 4) | (R.dy >= 0 ? 0 : 2) | (R.dz >= 0 ? 0 : 1);   // ComputeTraversalOrder: order[q] = q ^ sgn
                 cur = 0; have_cur = true;
                 fdx = (float)R.dx; fdy = (float)R.dy; fdz = (float)R.dz;
@@ -164,10 +168,10 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                 const int q = fq[sp]--;
                 const int child = fchild[sp] + (q ^ sgn);                             // pushed near->far, popped far->near
                 double lo, hi;
-                oct_interval(T.nodes + child, R, ix, iy, iz, lo, hi);
+                oct_interval_finite(T.nodes + child, R, ix, iy, iz, lo, hi);
                 const double pa = fa[sp], pb = fb[sp];
                 if (hi < lo || hi < 0 || lo > pb || hi < pa) continue;                // push-time filter :268
-                cur = child; ca = net_max(lo, pa); cb = net_min(hi, pb); have_cur = true;
+                cur = child; ca = fmax(lo, pa); cb = fmin(hi, pb); have_cur = true;
             }
         }
         // ------------------------------------------------------------------ C phase: cull a batch of leaf entries

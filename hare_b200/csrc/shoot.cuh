@@ -198,6 +198,23 @@ __device__ __forceinline__ void oct_interval(const OctNode* __restrict__ n, cons
     hi = net_min(net_min(tx1, ty1), tz1);
 }
 
+// Same arithmetic for a ray whose six components are finite: the node boxes and the guarded reciprocals
+// are finite and non-zero, so no NaN can arise and Math.Max/Min reduce to DMNMX (which orders -0 < +0 as
+// .NET does).  Rays with a NaN/Inf component take the fully guarded version above.
+__device__ __forceinline__ void oct_interval_finite(const OctNode* __restrict__ n, const Ray3& R, double ix, double iy, double iz,
+                                                    double& lo, double& hi) {
+    const double2* q = reinterpret_cast<const double2*>(n);
+    const double2 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2);
+    double tx0 = (a.x - R.x) * ix, tx1 = (b.y - R.x) * ix;
+    double ty0 = (a.y - R.y) * iy, ty1 = (cc.x - R.y) * iy;
+    double tz0 = (b.x - R.z) * iz, tz1 = (cc.y - R.z) * iz;
+    if (ix < 0) { double s = tx0; tx0 = tx1; tx1 = s; }
+    if (iy < 0) { double s = ty0; ty0 = ty1; ty1 = s; }
+    if (iz < 0) { double s = tz0; tz0 = tz1; tz1 = s; }
+    lo = fmax(fmax(tx0, ty0), tz0);
+    hi = fmin(fmin(tx1, ty1), tz1);
+}
+
 template <bool COUNT>
 __device__ __forceinline__ int shoot_one(const OctDev& T, const PolyRec* __restrict__ polys, Ray3& R,
                                          int o1, int o2, bool /*blind: the octree mailbox is commented out, :221-222*/, Event& ev, CntT<COUNT>& c) {
