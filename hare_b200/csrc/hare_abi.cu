@@ -68,6 +68,7 @@ struct hare_topo_s {
     HostTopo host;
     std::vector<int> devs;
     std::vector<PolyRec*> d_polys;   // one replica per device
+    std::vector<float> sph;          // host copy of the padded bounding spheres (P x 4)
 };
 
 struct PartDev {
@@ -77,7 +78,7 @@ struct PartDev {
     // voxel grid
     uint2* cells = nullptr; uint32_t* cell_poly = nullptr; uint32_t* occ = nullptr; uint32_t* cell_offset = nullptr;
     // trees
-    void* nodes = nullptr; uint32_t* lists = nullptr;
+    void* nodes = nullptr; uint32_t* lists = nullptr; float4* csph = nullptr;   // csph: octree chunk spheres
     // staging (per stream), sized for `cap` rays
     int64_t cap = 0;
     double *s_o[2] = {}, *s_d[2] = {}, *s_t[2] = {}, *s_xyz[2] = {}, *s_uv[2] = {}, *s_om[2] = {};
@@ -108,7 +109,7 @@ static void free_partdev(PartDev& d) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
@@ -249,6 +250,7 @@ extern "C" int hare_topology_create(const double* verts, const double* normals, 
         while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
         sph[4 * i] = cf[0]; sph[4 * i + 1] = cf[1]; sph[4 * i + 2] = cf[2]; sph[4 * i + 3] = rf;
     }
+    t->sph = sph;
     { std::lock_guard<std::mutex> lk(g_mu); t->devs = g_devices; }
     for (int dev : t->devs) {
         PolyRec* d = nullptr;
@@ -461,11 +463,53 @@ static int oct_to_device(hare_part_s* p) {
         n.mnx = t.box[6 * i]; n.mny = t.box[6 * i + 1]; n.mnz = t.box[6 * i + 2]; n.mxx = t.box[6 * i + 3]; n.mxy = t.box[6 * i + 4]; n.mxz = t.box[6 * i + 5];
         n.first_child = t.first_child[i]; n.list_off = t.list_off[i]; n.list_cnt = t.list_cnt[i]; n.pad = 0;
     }
+    // pad = bit c set when the subtree of child c holds at least one polygon: the kernel never enters the others
+    // (entering a polygon-free subtree has no effect on the result).  Children have larger indices than parents.
+    {
+        std::vector<uint8_t> has(N, 0);
+        for (size_t i = N; i-- > 0;) {
+            if (t.first_child[i] < 0) has[i] = t.list_cnt[i] > 0;
+            else {
+                uint32_t m = 0;
+                for (int c = 0; c < 8; ++c) if (has[(size_t)t.first_child[i] + c]) m |= 1u << c;
+                nodes[i].pad = m; has[i] = m != 0;
+            }
+        }
+    }
+    // Chunk spheres: every run of HARE_OCT_CHUNK consecutive entries of a leaf list gets a sphere enclosing its
+    // members' padded spheres; a ray whose line misses it misses all of them (leaf.pad = index of the leaf's first chunk).
+    std::vector<float> csph;
+    {
+        const std::vector<float>& ps = p->topo->sph;
+        for (size_t i = 0; i < N; ++i) {
+            if (t.first_child[i] >= 0) continue;
+            nodes[i].pad = (uint32_t)(csph.size() / 4);
+            for (uint32_t b = 0; b < t.list_cnt[i]; b += HARE_OCT_CHUNK) {
+                const uint32_t e = std::min<uint32_t>(b + HARE_OCT_CHUNK, t.list_cnt[i]);
+                double c[3] = { 0, 0, 0 };
+                for (uint32_t k = b; k < e; ++k) { const float* s = &ps[4 * (size_t)t.polys[t.list_off[i] + k]]; c[0] += s[0]; c[1] += s[1]; c[2] += s[2]; }
+                for (int a2 = 0; a2 < 3; ++a2) c[a2] /= (double)(e - b);
+                float cf[3] = { (float)c[0], (float)c[1], (float)c[2] };
+                double r = 0;
+                for (uint32_t k = b; k < e; ++k) {
+                    const float* s = &ps[4 * (size_t)t.polys[t.list_off[i] + k]];
+                    const double dx = (double)s[0] - cf[0], dy = (double)s[1] - cf[1], dz = (double)s[2] - cf[2];
+                    r = std::max(r, std::sqrt(dx * dx + dy * dy + dz * dz) + (double)s[3]);
+                }
+                r = r * (1.0 + 1e-6) + 1e-6;
+                float rf = (float)r;
+                while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
+                csph.push_back(cf[0]); csph.push_back(cf[1]); csph.push_back(cf[2]); csph.push_back(rf);
+            }
+        }
+    }
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         OctNode* dn = nullptr;
         CK(dmalloc(&dn, N)); d.nodes = dn;
         CK(dmalloc(&d.lists, t.polys.size()));
+        CK(dmalloc(&d.csph, csph.size() / 4));
+        if (!csph.empty()) CK(cudaMemcpy(d.csph, csph.data(), csph.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
         d.bytes = N * sizeof(OctNode) + t.polys.size() * 4;
@@ -733,7 +777,7 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, p->oct.depth };
             if (use_oct_v1()) return launch_shoot_t(t, d, a, st);
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
@@ -771,7 +815,7 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, p->oct.depth };
             if (use_oct_v1()) return launch_chain_t(t, d, a, st);
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);

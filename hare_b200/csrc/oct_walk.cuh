@@ -46,11 +46,12 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
     double closest = DBL_MAX, eu = 0, ev = 0;      // closestT and the u, v of the best event
     double ca = 0, cb = 0;                         // interval of the node being entered / of the current leaf
     float fdx = 0, fdy = 0, fdz = 0, fdd = 0, fpx = 0, fpy = 0, fpz = 0;
-    int fchild[HARE_OCT_MAXLVL]; double fa[HARE_OCT_MAXLVL], fb[HARE_OCT_MAXLVL]; int fq[HARE_OCT_MAXLVL];
+    int fchild[HARE_OCT_MAXLVL]; double fa[HARE_OCT_MAXLVL], fb[HARE_OCT_MAXLVL]; uint32_t fq[HARE_OCT_MAXLVL];
     int sp = -1, cur = 0, sgn = 0;
     int pid = -1, or1 = -1, or2 = -1, bounce = 0;
     uint32_t lpos = 0, lend = 0, last = 0xffffffffu;
-    uint32_t bid[HARE_OCT_CB] = { 0 }, bmask = 0;   // batch of up to 8 leaf entries; bit k = entry k survived the cull
+    uint32_t bid[HARE_OCT_CB] = { 0 }, bmask = 0;
+    uint32_t emask = 0, cpos = 0, cidx = 0;   // surviving chunks of the current group of 8 chunks, its list position, next chunk index   // batch of up to 8 leaf entries; bit k = entry k survived the cull
     bool have_cur = false, hit = false;
     int state = ST_NEED_RAY;
     int fin = 2;   // 2 = running; 1 hit, 0 miss
@@ -63,8 +64,8 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
         if (want == 0 && busy == 0) break;
         // N and T are dear and usually wanted by few lanes while C (cheap, long leaf lists) is wanted by most:
         // they run once N_BATCH / T_BATCH lanes wait for them, or when nothing cheaper is left to do
-        const bool needN = state == ST_WALK && fin == 2 && bmask == 0 && lpos >= lend;
-        const bool needC = state == ST_WALK && fin == 2 && bmask == 0 && lpos < lend;
+        const bool needN = state == ST_WALK && fin == 2 && bmask == 0 && emask == 0 && lpos >= lend;
+        const bool needC = state == ST_WALK && fin == 2 && bmask == 0 && (emask != 0 || lpos < lend);
         const bool needT = state == ST_WALK && fin == 2 && bmask != 0;
         const int nN = __popc(__ballot_sync(0xffffffffu, needN)), nC = __popc(__ballot_sync(0xffffffffu, needC));
         const int nT = __popc(__ballot_sync(0xffffffffu, needT));
@@ -124,7 +125,7 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
             if (state == ST_NEED_SETUP) {
                 state = ST_WALK; fin = 2;
                 hit = false; closest = DBL_MAX; pid = -1; eu = 0; ev = 0; last = 0xffffffffu;
-                lpos = 0; lend = 0; bmask = 0; sp = -1;
+                lpos = 0; lend = 0; bmask = 0; emask = 0; sp = -1;
                 ix = fabs(R.dx) > 1e-16 ? 1.0 / R.dx : 1e16;
                 iy = fabs(R.dy) > 1e-16 ? 1.0 / R.dy : 1e16;
                 iz = fabs(R.dz) > 1e-16 ? 1.0 / R.dz : 1e16;
@@ -150,7 +151,7 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                         c.cell();
                         const uint4 m = __ldg(reinterpret_cast<const uint4*>(T.nodes + cur) + 3);   // first_child, list_off, list_cnt
                         if ((int)m.x < 0) {
-                            lpos = m.y; lend = m.y + m.z;
+                            lpos = m.y; lend = m.y + m.z; cidx = m.w;
                             if (lpos < lend) {
                                 // leaf-local FP32 frame for cull_sphere: the ray point where the leaf is entered
                                 const double te = ca > 0.0 ? ca : 0.0;
@@ -158,15 +159,23 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                                 break;
                             }
                         } else if (sp + 1 < HARE_OCT_MAXLVL) {
-                            ++sp; fchild[sp] = (int)m.x; fa[sp] = ca; fb[sp] = cb; fq[sp] = 7;
+                            // frame: bit q = the q-th octant in near->far order (child q ^ sgn) still has to be popped; octants
+                            // whose subtree holds no polygon (node.pad, built at upload) are never entered: they cannot change
+                            // closestT, so neither the result nor the walk after them depends on them
+                            uint32_t pm = 0;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) pm |= ((m.w >> (q ^ sgn)) & 1u) << q;
+                            ++sp; fchild[sp] = (int)m.x; fa[sp] = ca; fb[sp] = cb; fq[sp] = pm;
                         }
                     }
                     continue;
                 }
                 if (sp < 0) { fin = hit ? 1 : 0; break; }                              // stack empty :276-283
-                if (fq[sp] < 0) { --sp; continue; }
-                const int q = fq[sp]--;
-                const int child = fchild[sp] + (q ^ sgn);                             // pushed near->far, popped far->near
+                const uint32_t pm = fq[sp];
+                if (pm == 0) { --sp; continue; }
+                const int q = 31 - __clz(pm);                                         // pushed near->far, popped far->near
+                fq[sp] = pm & ~(1u << q);
+                const int child = fchild[sp] + (q ^ sgn);
                 double lo, hi;
                 oct_interval_finite(T.nodes + child, R, ix, iy, iz, lo, hi);
                 const double pa = fa[sp], pb = fb[sp];
@@ -175,27 +184,45 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
             }
         }
         // ------------------------------------------------------------------ C phase: cull a batch of leaf entries
-        if (state == ST_WALK && fin == 2 && bmask == 0 && lpos < lend) {
-            const uint32_t n = min((uint32_t)HARE_OCT_CB, lend - lpos);
-            // ids, then bounding spheres: two groups of independent loads, so one round pays two memory latencies for 8 entries
+        if (state == ST_WALK && fin == 2 && bmask == 0 && (emask != 0 || lpos < lend)) {
+            static_assert(HARE_OCT_CB == HARE_OCT_CHUNK, "one C round culls one chunk");
+            if (emask == 0) {
+                // next group of (up to) eight chunks = 64 list entries: cull the chunk spheres first
+                const uint32_t left = lend - lpos, nch = min(8u, (left + HARE_OCT_CHUNK - 1) / HARE_OCT_CHUNK);
+                float4 cs[8];
 #pragma unroll
-            for (int j = 0; j < HARE_OCT_CB; ++j) bid[j] = __ldg(T.lists + lpos + (j < (int)n ? j : 0));
-            float4 s[HARE_OCT_CB];
+                for (int j = 0; j < 8; ++j) cs[j] = __ldg(T.csph + cidx + (j < (int)nch ? j : 0));
+                uint32_t em = 0;
 #pragma unroll
-            for (int j = 0; j < HARE_OCT_CB; ++j) s[j] = __ldg(T.sph + bid[j]);
-            lpos += n;
-            if (COUNT) c.entries += n;
-            // poly_origin skip (:218); a polygon already tested for this ray (it sits in several leaves) cannot
-            // change anything: its t is not below closestT any more, so neither the update nor the early return fires
-            uint32_t m = 0;
-#pragma unroll
-            for (int j = 0; j < HARE_OCT_CB; ++j) {
-                const uint32_t i = bid[j];
-                const bool keep = (j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
-                                  !cull_sphere(s[j], fpx, fpy, fpz, fdx, fdy, fdz, fdd);
-                m |= keep ? (1u << j) : 0u;
+                for (int j = 0; j < 8; ++j) em |= (j < (int)nch && !cull_sphere(cs[j], fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? (1u << j) : 0u;
+                emask = em; cpos = lpos; cidx += nch;
+                const uint32_t adv = min(left, 8u * HARE_OCT_CHUNK);
+                lpos += adv;
+                if (COUNT) c.entries += adv;
             }
-            bmask = m;
+            if (emask != 0) {
+                // lowest surviving chunk: its (up to) eight entries, ids then spheres as two groups of independent loads
+                const int kc = __ffs(emask) - 1;
+                emask &= emask - 1u;
+                const uint32_t base = cpos + (uint32_t)kc * HARE_OCT_CHUNK;
+                const uint32_t n = min((uint32_t)HARE_OCT_CB, lend - base);
+#pragma unroll
+                for (int j = 0; j < HARE_OCT_CB; ++j) bid[j] = __ldg(T.lists + base + (j < (int)n ? j : 0));
+                float4 s[HARE_OCT_CB];
+#pragma unroll
+                for (int j = 0; j < HARE_OCT_CB; ++j) s[j] = __ldg(T.sph + bid[j]);
+                // poly_origin skip (:218); a polygon already tested for this ray (it sits in several leaves) cannot
+                // change anything: its t is not below closestT any more, so neither the update nor the early return fires
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < HARE_OCT_CB; ++j) {
+                    const uint32_t i = bid[j];
+                    const bool keep = (j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
+                                      !cull_sphere(s[j], fpx, fpy, fpz, fdx, fdy, fdz, fdd);
+                    m |= keep ? (1u << j) : 0u;
+                }
+                bmask = m;
+            }
         }
         // ------------------------------------------------------------------ T phase: the exact FP64 test (slow path: u, v)
         if (doT && state == ST_WALK && fin == 2 && bmask != 0) {

@@ -179,10 +179,12 @@ struct OctDev {
     const OctNode* __restrict__ nodes;
     const uint32_t* __restrict__ lists;
     const float4* __restrict__ sph;   // padded bounding spheres, see cull_sphere()
+    const float4* __restrict__ csph;  // one sphere per run of HARE_OCT_CHUNK consecutive leaf-list entries (leaf.pad = first chunk)
     int depth;   // deepest level (root = 0)
 };
 
 #define HARE_OCT_MAXLVL 20
+#define HARE_OCT_CHUNK 8
 
 __device__ __forceinline__ void oct_interval(const OctNode* __restrict__ n, const Ray3& R, double ix, double iy, double iz,
                                              double& lo, double& hi) {
