@@ -769,6 +769,21 @@ static int launch_oct_walk(const OctDev& t, const PartDev& d, const double* o, c
     return HARE_OK;
 }
 
+static bool use_kd_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_KD_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
+
+// KDTree: phased persistent kernel (kd_walk.cuh)
+template <bool CHAIN>
+static int launch_kd_walk(const KdDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2, const int32_t* rid,
+                          int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+    if (N <= 0) return HARE_OK;
+    int64_t blocks = std::min<int64_t>((N + HARE_KD_THREADS - 1) / HARE_KD_THREADS, (int64_t)d.sms);
+    if (w.counters) kd_walk_kernel<CHAIN, true, HARE_OCT_SBATCH, HARE_OCT_NMAX, HARE_OCT_NBATCH, HARE_OCT_TBATCH><<<(unsigned)blocks, HARE_KD_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, rid, N, order, w);
+    else kd_walk_kernel<CHAIN, false, HARE_OCT_SBATCH, HARE_OCT_NMAX, HARE_OCT_NBATCH, HARE_OCT_TBATCH><<<(unsigned)blocks, HARE_KD_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, rid, N, order, w);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return HARE_OK;
+}
+
 static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
     switch (p->kind) {
         case HARE_VOXEL_GRID: {
@@ -782,7 +797,12 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
         }
-        case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth }; return launch_shoot_t(t, d, a, st); }
+        case HARE_KDTREE: {
+            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth };
+            if (use_kd_v1()) return launch_shoot_t(t, d, a, st);
+            WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
+            return launch_kd_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
+        }
     }
     return fail(HARE_ERR_INVALID, "unknown partition kind");
 }
@@ -820,7 +840,12 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);
         }
-        case HARE_KDTREE: { KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth }; return launch_chain_t(t, d, a, st); }
+        case HARE_KDTREE: {
+            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth };
+            if (use_kd_v1()) return launch_chain_t(t, d, a, st);
+            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
+            return launch_kd_walk<true>(t, d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
+        }
     }
     return fail(HARE_ERR_INVALID, "unknown partition kind");
 }
