@@ -19,7 +19,7 @@
 namespace hare {
 
 #ifndef HARE_KD_THREADS
-#define HARE_KD_THREADS 512
+#define HARE_KD_THREADS 640
 #endif
 #define HARE_KD_CB 8
 

@@ -27,7 +27,7 @@ namespace hare {
 #define HARE_OCT_CB 8   /* leaf entries culled per C round */
 #endif
 #ifndef HARE_OCT_THREADS
-#define HARE_OCT_THREADS 512
+#define HARE_OCT_THREADS 640
 #endif
 
 template <bool CHAIN, bool COUNT, int S_BATCH, int N_MAX, int N_BATCH, int T_BATCH>

@@ -35,7 +35,7 @@ struct WalkOut {
 enum : int { ST_NEED_RAY = 0, ST_NEED_SETUP = 1, ST_WALK = 2, ST_DONE = 3 };
 
 #ifndef HARE_VG_THREADS
-#define HARE_VG_THREADS 512
+#define HARE_VG_THREADS 640
 #endif
 
 // OCC_SMEM: the occupancy bitmap (1 bit per voxel) is staged in shared memory once per CTA, so an
