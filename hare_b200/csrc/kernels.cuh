@@ -117,15 +117,17 @@ __device__ __forceinline__ void candidate_range(double mn, double mx, double omi
 }
 
 // MODE 0: count per cell; MODE 1: scatter into cell_poly via per-cell cursors.
-// One warp per polygon: lanes stride over the polygon's candidate voxels.
+// Eight lanes per polygon (four polygons per warp): a polygon of a tessellated hall touches 2-12 voxels, so
+// a whole warp per polygon would leave three quarters of the lanes idle; the eight lanes stride over the
+// polygon's candidate voxels and read its 128-byte record as one broadcast line.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 vg_bin_kernel(const VGBuild g, const PolyRec* __restrict__ polys, long long P,
               uint32_t* __restrict__ cell_count, const uint32_t* __restrict__ cell_offset,
               uint32_t* __restrict__ cursor, uint32_t* __restrict__ cell_poly) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 7;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 3;
     for (long long p = warp; p < P; p += nwarps) {
         double V[16];
         load_poly(polys, (uint32_t)p, V);
@@ -146,7 +148,7 @@ vg_bin_kernel(const VGBuild g, const PolyRec* __restrict__ polys, long long P,
         const int ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1;
         if (ex <= 0 || ey <= 0 || ez <= 0) continue;
         const long long total = (long long)ex * ey * ez;
-        for (long long q = lane; q < total; q += 32) {
+        for (long long q = lane; q < total; q += 8) {
             const int z = lo[2] + (int)(q % ez);
             const int y = lo[1] + (int)((q / ez) % ey);
             const int x = lo[0] + (int)(q / ((long long)ez * ey));
