@@ -265,3 +265,31 @@ def test_large_batch_properties(gpu):
     lo, hi = (1 << 20) - 1000, (1 << 20) + 1000
     r2 = g.Shoot_Batch(o[lo:hi], d[lo:hi])
     assert np.array_equal(r2["poly_id"], r["poly_id"][lo:hi]) and np.array_equal(r2["t"], r["t"][lo:hi])
+
+
+# ---------------------------------------------------------------- in-process multi-device sharding (the C# drop-in's multi-GPU path)
+def test_in_process_multi_device_sharding(gpu):
+    """hare_init(ids, n): handles are replicated on n devices and hare_shoot_batch block-shards the batch over
+    them; results land in the caller's arrays in ray order.  Needs >= 2 GPUs (skipped on a 1-GPU box)."""
+    n = gpu.lib().hare_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 CUDA devices")
+    mesh = meshes.hall("10k")
+    o, d = rays_from_sources(300_001, meshes.sources(4), stream=14)
+    gpu.init([0])
+    T1 = gpu.Topology.from_mesh(mesh)
+    ref = gpu.Voxel_Grid([T1], 32).Shoot_Batch(o, d)
+    refo = gpu.Octree([T1], 6, 16).Shoot_Batch(o, d)
+    refc = gpu.Voxel_Grid([T1], 32).Reflect_Chain(o[:50_000], d[:50_000], 10)
+    try:
+        gpu.init(list(range(min(n, 8))))
+        T = gpu.Topology.from_mesh(mesh)
+        got = gpu.Voxel_Grid([T], 32).Shoot_Batch(o, d)
+        assert_events_equal(got, ref, uv=False, what="multi-device Voxel_Grid")
+        goto = gpu.Octree([T], 6, 16).Shoot_Batch(o, d)
+        assert_events_equal(goto, refo, what="multi-device Octree")
+        gotc = gpu.Voxel_Grid([T], 32).Reflect_Chain(o[:50_000], d[:50_000], 10)
+        assert np.array_equal(gotc["ev_poly_id"], refc["ev_poly_id"]) and np.array_equal(gotc["ev_t"], refc["ev_t"])
+        assert gotc["total_shots"] == refc["total_shots"]
+    finally:
+        gpu.init([0])
