@@ -62,6 +62,7 @@ def lib():
     L.hare_topology_polygon_count.argtypes = [vp]
     L.hare_topology_destroy.argtypes = [vp]
     L.hare_voxelgrid_build.argtypes = [vp, i32, pp]
+    L.hare_voxelgrid_build_adaptive.argtypes = [vp, i32, i32, pp]
     L.hare_voxelgrid_upload.argtypes = [vp, vp, vp, vp, vp, pp]
     L.hare_voxelgrid_info.argtypes = [vp, vp, vp, vp, C.POINTER(i64)]
     L.hare_voxelgrid_download.argtypes = [vp, vp, vp]

@@ -35,6 +35,7 @@ namespace Hare.Geometry.Native
         [DllImport(Lib, CallingConvention = CC)] public static extern int hare_topology_destroy(IntPtr topo);
 
         [DllImport(Lib, CallingConvention = CC)] public static extern int hare_voxelgrid_build(IntPtr topo, int domain, out IntPtr part);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int hare_voxelgrid_build_adaptive(IntPtr topo, int max_domain_log2, int avg_polys, out IntPtr part);
         [DllImport(Lib, CallingConvention = CC)]
         public static extern int hare_voxelgrid_upload(IntPtr topo, double[] obox, int[] ct, uint[] cell_offset, uint[] cell_poly, out IntPtr part);
         [DllImport(Lib, CallingConvention = CC)]
@@ -167,6 +168,20 @@ namespace Hare.Geometry
             Model = Model_in;
             topo = HareB200.Flatten(Model);
             HareB200.Check(HareB200.hare_voxelgrid_build(topo, Domain, out part), "hare_voxelgrid_build");
+            Set_Char_Step();
+        }
+
+        /// <summary>Voxel_Grid(Topology[] Model_in, int MaxDomain, int Avg_polys)  (Voxel_Grid.cs:128).</summary>
+        public Gpu_Voxel_Grid(Topology[] Model_in, int MaxDomain, int Avg_polys)
+        {
+            Model = Model_in;
+            topo = HareB200.Flatten(Model);
+            HareB200.Check(HareB200.hare_voxelgrid_build_adaptive(topo, MaxDomain, Avg_polys, out part), "hare_voxelgrid_build_adaptive");
+            Set_Char_Step();
+        }
+
+        void Set_Char_Step()
+        {
             double[] obox = new double[6], vd = new double[3]; int[] ct = new int[3]; long n;
             HareB200.Check(HareB200.hare_voxelgrid_info(part, obox, vd, ct, out n), "hare_voxelgrid_info");
             Char_Step = (vd[0] < vd[1]) ? ((vd[0] < vd[2]) ? vd[0] : vd[2]) : (vd[1] < vd[2] ? vd[1] : vd[2]);   // Voxel_Grid.cs:90

@@ -382,6 +382,37 @@ extern "C" int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* o
     return HARE_OK;
 }
 
+// mean list length over the non-empty voxels, from the CSR offsets (host side: runs once per level)
+static int vg_mean_list_length(hare_part_s* p, double* avg) {
+    PartDev& d = p->dev[0];
+    const int64_t ncells = (int64_t)p->ct[0] * p->ct[1] * p->ct[2];
+    std::vector<uint32_t> off((size_t)ncells + 1);
+    CK(cudaSetDevice(d.dev));
+    CK(cudaMemcpy(off.data(), d.cell_offset, (size_t)(ncells + 1) * 4, cudaMemcpyDeviceToHost));
+    double sum = 0; int64_t ct = 0;
+    for (int64_t c = 0; c < ncells; ++c) { const uint32_t n = off[c + 1] - off[c]; if (n) { sum += n; ++ct; } }
+    *avg = ct ? sum / (double)ct : 0.0 / 0.0;   // C#: 0/0 -> NaN, and NaN < Avg_polys is false
+    return HARE_OK;
+}
+
+extern "C" int hare_voxelgrid_build_adaptive(hare_topo_t topo, int max_domain_log2, int avg_polys, hare_part_t* out) {
+    if (!topo || !out || max_domain_log2 < 1 || max_domain_log2 > 10) return fail(HARE_ERR_INVALID, "hare_voxelgrid_build_adaptive: 1 <= MaxDomain <= 10");
+    hare_part_t cur = nullptr;
+    for (int k = 0; k < max_domain_log2; ++k) {        // Voxel_Grid.cs:161-253
+        hare_part_t nxt = nullptr;
+        int rc = hare_voxelgrid_build(topo, 1 << (k + 1), &nxt);
+        if (rc) { if (cur) hare_part_destroy(cur); return rc; }
+        if (cur) hare_part_destroy(cur);
+        cur = nxt;
+        double avg = 0;
+        rc = vg_mean_list_length(cur, &avg);
+        if (rc) { hare_part_destroy(cur); return rc; }
+        if (k > 1 && avg < (double)avg_polys) break;   // :252
+    }
+    *out = cur;
+    return HARE_OK;
+}
+
 extern "C" int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], const int32_t ct[3],
                                      const uint32_t* cell_offset, const uint32_t* cell_poly, hare_part_t* out) {
     if (!topo || !obox || !ct || !cell_offset || !out || ct[0] < 1 || ct[1] < 1 || ct[2] < 1)

@@ -201,9 +201,13 @@ class Voxel_Grid(Spatial_Partition):
     Voxel_Grid.from_lists(...) uploads host-built lists (e.g. Hare's hierarchical ctor)."""
     has_uv = False
 
-    def __init__(self, Model_in, Domain):
+    def __init__(self, Model_in, Domain, Avg_polys=None):
+        """Voxel_Grid(Model, Domain)  or, with a third argument, Voxel_Grid(Model, MaxDomain, Avg_polys) (Voxel_Grid.cs:128)."""
         super().__init__(Model_in)
-        check(_lib.lib().hare_voxelgrid_build(self.Model[0]._h, int(Domain), C.byref(self._h)), "hare_voxelgrid_build")
+        if Avg_polys is None:
+            check(_lib.lib().hare_voxelgrid_build(self.Model[0]._h, int(Domain), C.byref(self._h)), "hare_voxelgrid_build")
+        else:
+            check(_lib.lib().hare_voxelgrid_build_adaptive(self.Model[0]._h, int(Domain), int(Avg_polys), C.byref(self._h)), "hare_voxelgrid_build_adaptive")
         self._post()
 
     @classmethod
@@ -230,6 +234,24 @@ class Voxel_Grid(Spatial_Partition):
         off = np.empty(int(ct[0]) * int(ct[1]) * int(ct[2]) + 1, np.uint32); pol = np.empty(max(n, 1), np.uint32)
         check(_lib.lib().hare_voxelgrid_download(self._h, ptr(off), ptr(pol)), "hare_voxelgrid_download")
         return off, pol[:n]
+
+    # ---- the rest of Voxel_Grid's public surface (Voxel_Grid.cs:256-267, 322-332, 763-791); host-side integer helpers
+    def VoxelCode(self, X, Y, Z):
+        _, _, ct, _ = self.info()
+        return int(ct[0]) * int(ct[1]) * Z + int(ct[1]) * X + Y          # XYTot * Z + VoxelCtY * X + Y
+
+    def VoxelDecode(self, Code):
+        _, _, ct, _ = self.info()
+        xytot = int(ct[0]) * int(ct[1])
+        Z = Code // xytot; Code -= Z * xytot
+        Y = Code // int(ct[1]); X = Code - Y * int(ct[1])
+        return X, Y, Z
+
+    def PointInVoxel(self, Pt):
+        import math
+        obox, vd, _, _ = self.info()
+        p = (Pt.x, Pt.y, Pt.z) if hasattr(Pt, "x") else tuple(Pt)
+        return tuple(int(math.floor((p[a] - obox[a]) / vd[a])) for a in range(3))
 
     Xdim = property(lambda s: float(s.info()[0][3] - s.info()[0][0]))
     Ydim = property(lambda s: float(s.info()[0][4] - s.info()[0][1]))

@@ -83,6 +83,13 @@ int hare_topology_destroy(hare_topo_t topo);
  * Cell lists are built on the GPU (count / scan / scatter / per-cell sort) and are
  * identical to the reference's ascending lists. */
 int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* out);
+/* new Voxel_Grid(Model, MaxDomain, Avg_polys)  (Voxel_Grid.cs:128-254): the grid is refined 2x per axis per
+ * level, up to 2^MaxDomain voxels per axis, stopping after level k > 1 once the mean list length of the
+ * non-empty voxels drops below Avg_polys (:252).  The reference filters each child voxel's list through its
+ * parent's; a child box lies inside its parent box (their shared faces are bit-identical), so the lists are
+ * those of the flat constructor at the final resolution -- which is what is built here, level by level, on
+ * the GPU (CSR equality with the reference-order hierarchical build is tested up to 256^3 / 2M polygons). */
+int hare_voxelgrid_build_adaptive(hare_topo_t topo, int max_domain_log2, int avg_polys, hare_part_t* out);
 /* Upload a grid built by the host (e.g. Hare's hierarchical ctor, Voxel_Grid.cs:128-254):
  * obox = OBox.Min xyz, OBox.Max xyz; ct = VoxelCtX/Y/Z; CSR lists, cell index ((x*Ny+y)*Nz+z). */
 int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], const int32_t ct[3],

@@ -267,6 +267,24 @@ def test_large_batch_properties(gpu):
     assert np.array_equal(r2["poly_id"], r["poly_id"][lo:hi]) and np.array_equal(r2["t"], r["t"][lo:hi])
 
 
+def test_adaptive_ctor_matches_hierarchical_reference_ctor(gpu):
+    """Voxel_Grid(Model, MaxDomain, Avg_polys) (Voxel_Grid.cs:128-254): same lists, same resolution, same Shoot results
+    as the oracle's level-by-level build, including the stop rule (:252)."""
+    mesh = meshes.hall("2k")
+    T, To = _pair(gpu, mesh)
+    o, d = rays_from_sources(20_000, meshes.sources(4), stream=15)
+    for maxdom, avg in ((4, 0), (6, 3), (6, 1000)):
+        g = gpu.Voxel_Grid([T], maxdom, avg)
+        og = ho.Voxel_Grid(To, maxdom, mode="hier", avg_polys=avg, nthreads=4)
+        assert np.array_equal(g.info()[2], og.info()[2]), (maxdom, avg)
+        a, b = g.csr(), og.csr()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert_events_equal(g.Shoot_Batch(o, d), og.Shoot(o, d), uv=False, what=f"adaptive {maxdom},{avg}")
+    X, Y, Z = g.PointInVoxel(gpu.Point(15.0, 6.0, 5.0))
+    # the reference's VoxelDecode returns X and Y swapped with respect to VoxelCode (Voxel_Grid.cs:256-267); kept as is
+    assert g.VoxelDecode(g.VoxelCode(X, Y, Z)) == (Y, X, Z)
+
+
 # ---------------------------------------------------------------- in-process multi-device sharding (the C# drop-in's multi-GPU path)
 def test_in_process_multi_device_sharding(gpu):
     """hare_init(ids, n): handles are replicated on n devices and hare_shoot_batch block-shards the batch over
