@@ -5,8 +5,8 @@
 // minimum of t, i.e. the global closest hit.  Here the walk goes near child first and drops a subtree when
 // the ray's parameter interval inside the node's box (inflated by HARE_KD_PAD) lies wholly beyond the
 // current closest hit or behind the origin (kd_box_reachable).  t and hit/miss are the reference's; among
-// polygons hit at exactly equal t the reference keeps the first of its exhaustive DFS order (documented
-// exact-edge ties).
+// polygons hit at exactly equal t the reference keeps the first of its exhaustive DFS order, which
+// kd_dfs_before() reconstructs, so Poly_id, u and v match as well.
 //
 // Phases per trip round the main loop (all lanes of the warp together):
 //   S  finish / fetch / set-up (batched);   N  pop nodes until a reachable leaf is found;
@@ -22,6 +22,45 @@ namespace hare {
 #define HARE_KD_THREADS 640
 #endif
 #define HARE_KD_CB 8
+
+// Exact-t tie between two different polygons: the reference keeps the one its exhaustive DFS meets first
+// (strict t < closestT, mailbox = first occurrence only).  That order is reconstructed analytically: walk down
+// from the root choosing first/second by the reference's rule (KDTree.cs:249-353); a polygon belongs to the Left
+// subtree iff one of its vertices is <= split on the node's axis, to the Right iff one is > split (:123-133).
+// Where the two polygons part ways the one in `first` wins; in a common leaf the earlier list entry wins.
+// Out of line and rare (axis-aligned rays through shared edges or vertices of a structured mesh).
+__device__ __noinline__ bool kd_dfs_before(const KdDev T, const PolyRec* __restrict__ polys, const Ray3 R, uint32_t pa, uint32_t pb) {
+    const double* A = polys[pa].v; const double* B = polys[pb].v;
+    const int na = (A[15] == 4.0) ? 4 : 3, nb = (B[15] == 4.0) ? 4 : 3;
+    int ni = 0;
+    for (int depth = 0; depth < HARE_KD_MAXSTACK; ++depth) {
+        const double2* q = reinterpret_cast<const double2*>(T.nodes + ni);
+        const double2 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2), dd = __ldg(q + 3);
+        const int left = __double2loint(dd.y), axis = __double2hiint(dd.y);
+        if (left < 0) {   // common leaf: stored list order
+            const uint32_t off = (uint32_t)__double2loint(dd.x), cnt = (uint32_t)__double2hiint(dd.x);
+            for (uint32_t k = 0; k < cnt; ++k) { const uint32_t i = __ldg(T.lists + off + k); if (i == pa) return true; if (i == pb) return false; }
+            return pa < pb;
+        }
+        const double split = dd.x;
+        bool aL = false, aR = false, bL = false, bR = false;
+        for (int k = 0; k < na; ++k) { const double c = A[3 * k + axis]; aL |= (c <= split); aR |= (c > split); }
+        for (int k = 0; k < nb; ++k) { const double c = B[3 * k + axis]; bL |= (c <= split); bR |= (c > split); }
+        // first / second exactly as the reference computes them
+        const double mn[3] = { a.x, a.y, b.x }, mx[3] = { b.y, cc.x, cc.y };
+        const double o[3] = { R.x, R.y, R.z }, d[3] = { R.dx, R.dy, R.dz };
+        const int b1 = (axis == 0) ? 1 : 0, b2 = (axis == 2) ? 1 : 2;
+        const double side = o[axis] - split;
+        const double tSplit = -side / d[axis];
+        const double s1 = o[b1] + tSplit * d[b1], s2 = o[b2] + tSplit * d[b2];
+        const bool inside = (s1 <= mx[b1] && s1 >= mn[b1] && s2 <= mx[b2] && s2 >= mn[b2]);
+        const bool right_first = inside ? (side >= 0) : !(side >= 0);
+        const bool aF = right_first ? aR : aL, bF = right_first ? bR : bL;   // membership in the subtree visited first
+        if (aF != bF) return aF;
+        ni = aF ? (right_first ? left + 1 : left) : (right_first ? left : left + 1);
+    }
+    return pa < pb;
+}
 
 template <bool CHAIN, bool COUNT, int S_BATCH, int N_MAX, int N_BATCH, int T_BATCH>
 __global__ void __launch_bounds__(HARE_KD_THREADS, 1)
@@ -181,6 +220,7 @@ kd_walk_kernel(const KdDev T, const PolyRec* __restrict__ polys,
             load_poly(polys, pend, P);
             if (poly_intersect<true>(P, R, t, u, v) && t > 0.0000000001) {
                 if (t < closest) { closest = t; hit = true; pid = (int)pend; eu = u; ev = v; }
+                else if (t == closest && (int)pend != pid && kd_dfs_before(T, polys, R, pend, (uint32_t)pid)) { pid = (int)pend; eu = u; ev = v; }
             }
         }
     }
