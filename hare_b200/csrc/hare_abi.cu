@@ -548,12 +548,164 @@ static int oct_to_device(hare_part_s* p) {
     return HARE_OK;
 }
 
+// Octree build on the GPU (kernels.cuh "GPU Octree build").  Produces the same OctTree as host_build.cpp's
+// build_octree(): same breadth-first node numbering, same child boxes (computed here on the host with the same
+// expressions), same list order.
+static int build_octree_gpu(hare_topo_s* topo, const PolyRec* d_polys, int dev, cudaStream_t st, int maxDepth, int maxPolys, OctTree& out) {
+    const HostTopo& T = topo->host;
+    out = OctTree();
+    CK(cudaSetDevice(dev));
+    const double ext = net_max(T.vmax[0] - T.vmin[0], net_max(T.vmax[1] - T.vmin[1], T.vmax[2] - T.vmin[2]));
+    auto add_node = [&](const double* mn, const double* mx) {
+        for (int a2 = 0; a2 < 3; ++a2) out.box.push_back(mn[a2]);
+        for (int a2 = 0; a2 < 3; ++a2) out.box.push_back(mx[a2]);
+        out.first_child.push_back(-1); out.list_off.push_back(0); out.list_cnt.push_back(0);
+        return (int)out.first_child.size() - 1;
+    };
+    {
+        double mn[3], mx[3];
+        for (int a2 = 0; a2 < 3; ++a2) { const double c = T.vmax[a2] + T.vmin[a2] / 2; mn[a2] = c - ext - 1e-1; mx[a2] = c + ext + 1e-1; }   // :79-82
+        add_node(mn, mx);
+    }
+    struct LNode { int node; uint32_t start, cnt; };
+    std::vector<LNode> level(1);
+    level[0] = { 0, 0u, (uint32_t)T.P };
+    uint32_t* cur = nullptr;   // this level's entry array (polygon ids, node-major)
+    CK(dmalloc(&cur, (size_t)T.P));
+    {
+        std::vector<uint32_t> iota((size_t)T.P);
+        for (size_t i = 0; i < iota.size(); ++i) iota[i] = (uint32_t)i;
+        CK(cudaMemcpyAsync(cur, iota.data(), iota.size() * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    int64_t E = T.P;
+    unsigned long long* d_lost = nullptr;
+    CK(dmalloc(&d_lost, 1)); CK(cudaMemsetAsync(d_lost, 0, 8, st));
+    std::vector<uint32_t*> leaf_src;                       // device entry arrays holding leaf lists, kept until the final gather
+    struct LeafCopy { uint32_t src, dst, cnt; int arr; };
+    std::vector<LeafCopy> copies;
+    uint32_t list_total = 0;
+    int rcode = HARE_OK;
+    for (int depth = 0; !level.empty(); ++depth) {
+        out.depth = depth;
+        std::vector<LNode> split;
+        leaf_src.push_back(cur);
+        const int arr = (int)leaf_src.size() - 1;
+        for (const LNode& n : level) {
+            if (depth >= maxDepth || (int64_t)n.cnt <= (int64_t)maxPolys) {                 // :93
+                out.list_off[n.node] = list_total; out.list_cnt[n.node] = n.cnt;
+                if (n.cnt) copies.push_back({ n.start, list_total, n.cnt, arr });
+                list_total += n.cnt;
+            } else split.push_back(n);
+        }
+        if (split.empty()) break;
+        const int S = (int)split.size();
+        std::vector<double> cbox((size_t)S * 48);
+        std::vector<uint32_t> seg_start(S), seg_cnt(S);
+        for (int s = 0; s < S; ++s) {
+            const int nd = split[s].node;
+            double mn[3], mx[3], mid[3];
+            for (int a2 = 0; a2 < 3; ++a2) { mn[a2] = out.box[6 * nd + a2]; mx[a2] = out.box[6 * nd + 3 + a2]; mid[a2] = (mx[a2] + mn[a2]) / 2; }
+            out.first_child[nd] = (int)out.first_child.size();
+            for (int i = 0; i < 8; ++i) {
+                double cmn[3], cmx[3];
+                for (int a2 = 0; a2 < 3; ++a2) {
+                    const bool upper = (i & (4 >> a2)) != 0;
+                    cmn[a2] = (upper ? mid[a2] : mn[a2]) - 0.1;
+                    cmx[a2] = (upper ? mx[a2] : mid[a2]) + 0.1;
+                }
+                add_node(cmn, cmx);
+                for (int a2 = 0; a2 < 3; ++a2) { cbox[((size_t)s * 8 + i) * 6 + a2] = cmn[a2]; cbox[((size_t)s * 8 + i) * 6 + 3 + a2] = cmx[a2]; }
+            }
+            seg_start[s] = split[s].start; seg_cnt[s] = split[s].cnt;
+        }
+        auto body = [&]() -> int {
+            double* d_cbox = nullptr; uint32_t *d_ss = nullptr, *d_sc = nullptr, *d_slot = nullptr, *d_flags = nullptr, *d_scan = nullptr, *d_tiles = nullptr, *d_counts = nullptr, *d_base = nullptr;
+            CK(dmalloc(&d_cbox, cbox.size())); CK(dmalloc(&d_ss, (size_t)S)); CK(dmalloc(&d_sc, (size_t)S));
+            CK(dmalloc(&d_slot, (size_t)E)); CK(dmalloc(&d_flags, (size_t)E * 8)); CK(dmalloc(&d_scan, (size_t)E * 8 + 1));
+            CK(dmalloc(&d_tiles, ((size_t)E * 8 + HARE_SCAN_TILE - 1) / HARE_SCAN_TILE + 1)); CK(dmalloc(&d_counts, (size_t)S * 8)); CK(dmalloc(&d_base, (size_t)S * 8));
+            CK(cudaMemcpyAsync(d_cbox, cbox.data(), cbox.size() * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_ss, seg_start.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_sc, seg_cnt.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(d_slot, 0xff, (size_t)E * 4, st));
+            oct_fill_slot<<<std::min(S, 65535), 256, 0, st>>>(d_ss, d_sc, S, d_slot);
+            const unsigned eb = (unsigned)((E * 8 + 255) / 256);
+            oct_mask_kernel<<<eb, 256, 0, st>>>(d_polys, cur, d_slot, d_cbox, E, d_flags, d_lost);
+            g_launches += 2;
+            CK(cudaGetLastError());
+            int r = scan_u32(d_flags, E * 8, d_scan, d_tiles, st);
+            if (r) return r;
+            oct_child_counts<<<(S * 8 + 255) / 256, 256, 0, st>>>(d_scan, d_ss, d_sc, S, E, d_counts);
+            ++g_launches;
+            std::vector<uint32_t> counts((size_t)S * 8), base((size_t)S * 8);
+            CK(cudaMemcpyAsync(counts.data(), d_counts, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            uint64_t tot = 0;
+            for (size_t i = 0; i < counts.size(); ++i) { base[i] = (uint32_t)tot; tot += counts[i]; }
+            if (tot > 0xfffffff0ull) return fail(HARE_ERR_UNSUPPORTED, "octree level with more than 2^32 list entries");
+            uint32_t* nxt = nullptr;
+            CK(dmalloc(&nxt, (size_t)tot));
+            CK(cudaMemcpyAsync(d_base, base.data(), base.size() * 4, cudaMemcpyHostToDevice, st));
+            oct_scatter<<<eb, 256, 0, st>>>(cur, d_slot, d_flags, d_scan, d_ss, d_base, E, nxt);
+            ++g_launches;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+            std::vector<LNode> next;
+            next.reserve((size_t)S * 8);
+            for (int s = 0; s < S; ++s)
+                for (int i = 0; i < 8; ++i) next.push_back({ out.first_child[split[s].node] + i, base[(size_t)s * 8 + i], counts[(size_t)s * 8 + i] });
+            level.swap(next);
+            cur = nxt; E = (int64_t)tot;
+            cudaFree(d_cbox); cudaFree(d_ss); cudaFree(d_sc); cudaFree(d_slot); cudaFree(d_flags); cudaFree(d_scan); cudaFree(d_tiles); cudaFree(d_counts); cudaFree(d_base);
+            return HARE_OK;
+        };
+        rcode = body();
+        if (rcode) break;
+    }
+    if (rcode == HARE_OK) {
+        // gather the leaf lists into their final places, then bring them to the host copy of the tree
+        uint32_t* d_lists = nullptr;
+        cudaError_t e = dmalloc(&d_lists, (size_t)list_total);
+        for (int arr = 0; e == cudaSuccess && arr < (int)leaf_src.size(); ++arr) {
+            std::vector<uint32_t> s, dd, cc;
+            for (const LeafCopy& c2 : copies) if (c2.arr == arr) { s.push_back(c2.src); dd.push_back(c2.dst); cc.push_back(c2.cnt); }
+            if (s.empty()) continue;
+            uint32_t *ds = nullptr, *ddst = nullptr, *dc = nullptr;
+            e = dmalloc(&ds, s.size()); if (e == cudaSuccess) e = dmalloc(&ddst, s.size()); if (e == cudaSuccess) e = dmalloc(&dc, s.size());
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ds, s.data(), s.size() * 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ddst, dd.data(), s.size() * 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dc, cc.data(), s.size() * 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) { oct_copy_lists<<<(unsigned)std::min<size_t>(s.size(), 65535), 256, 0, st>>>(leaf_src[arr], ds, ddst, dc, (int)s.size(), d_lists); ++g_launches; e = cudaGetLastError(); }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(ds); cudaFree(ddst); cudaFree(dc);
+        }
+        out.polys.resize(list_total);
+        unsigned long long lost = 0;
+        if (e == cudaSuccess && list_total) e = cudaMemcpy(out.polys.data(), d_lists, (size_t)list_total * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(&lost, d_lost, 8, cudaMemcpyDeviceToHost);
+        out.lost = (int64_t)lost;
+        cudaFree(d_lists);
+        if (e != cudaSuccess) rcode = fail(HARE_ERR_CUDA, std::string("build_octree_gpu: ") + cudaGetErrorString(e));
+    }
+    for (uint32_t* p2 : leaf_src) cudaFree(p2);
+    if (rcode != HARE_OK && !leaf_src.empty() && cur != leaf_src.back()) cudaFree(cur);
+    cudaFree(d_lost);
+    return rcode;
+}
+
 extern "C" int hare_octree_build(hare_topo_t topo, int maxDepth, int maxPolys, hare_part_t* out) {
     if (!topo || !out || maxDepth < 0 || maxDepth >= HARE_OCT_MAXLVL) return fail(HARE_ERR_INVALID, "hare_octree_build: bad argument");
     hare_part_s* p = nullptr;
     int rc = new_part(topo, HARE_OCTREE, &p);
     if (rc) return rc;
-    build_octree(topo->host, maxDepth, maxPolys, p->oct);
+    {
+        const char* e = getenv("HARE_OCT_HOST_BUILD");
+        if (p->dev.empty() || (e && *e == '1')) build_octree(topo->host, maxDepth, maxPolys, p->oct);   // host-only handles, or forced
+        else {
+            rc = build_octree_gpu(topo, p->dev[0].polys, p->dev[0].dev, p->dev[0].stream[0], maxDepth, maxPolys, p->oct);
+            if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+        }
+    }
     rc = oct_to_device(p);
     if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
     *out = p;

@@ -264,6 +264,86 @@ vg_finish_cells(const uint32_t* __restrict__ cell_offset, const uint32_t* __rest
     if ((threadIdx.x & 31) == 0 && c < ncells) occ[c >> 5] = bits;
 }
 
+// ---------------------------------------------------------------------------------------
+// GPU Octree build ("Octree - alt.cs":91-138), one level at a time.  The host keeps the node table and decides
+// leaf / split (:93); the device does the O(entries x 8) SAT work and the order-preserving distribution:
+//   oct_fill_slot    every entry of a node that splits learns its slot in this level's split table
+//   oct_mask_kernel  entry x child PolyBoxOverlap against the child boxes the host computed (:99-114); flags are
+//                    stored child-major (flag[c*E + e]) so that ONE exclusive scan ranks every child's entries in
+//                    parent-list order (:118-130)
+//   oct_child_counts per (split node, child): number of entries = difference of two scan values
+//   oct_scatter      entry -> position in the next level's entry array (children laid out in (node, child) order)
+//   oct_copy_lists   leaf lists -> final list array
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+oct_fill_slot(const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_cnt, int nslots, uint32_t* __restrict__ entry_slot) {
+    for (int s = blockIdx.x; s < nslots; s += gridDim.x) {
+        const uint32_t b = seg_start[s], n = seg_cnt[s];
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) entry_slot[b + k] = (uint32_t)s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+oct_mask_kernel(const PolyRec* __restrict__ polys, const uint32_t* __restrict__ entry_poly, const uint32_t* __restrict__ entry_slot,
+                const double* __restrict__ child_box /* nslots x 8 x 6 */, long long E, uint32_t* __restrict__ flags /* 8 x E */,
+                unsigned long long* __restrict__ lost) {
+    // 8 threads per entry: thread c tests child c
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = gid >> 3; const int c = (int)(gid & 7);
+    bool ov = false;
+    if (e < E) {
+        const uint32_t s = entry_slot[e];
+        if (s != 0xffffffffu) {
+            double V[16];
+            load_poly(polys, entry_poly[e], V);
+            const double* b = child_box + ((size_t)s * 8 + c) * 6;
+            const Box3 B = make_box(b[0], b[1], b[2], b[3], b[4], b[5]);
+            ov = poly_box_overlap(B, V, (V[15] == 4.0) ? 4 : 3);
+            flags[(long long)c * E + e] = ov ? 1u : 0u;
+        } else {
+            flags[(long long)c * E + e] = 0u;
+        }
+    }
+    // polygons overlapping no child are dropped (:116,129): count them
+    const unsigned m = __ballot_sync(0xffffffffu, ov);
+    if (e < E && c == 0 && entry_slot[e] != 0xffffffffu) {
+        const int sh = (threadIdx.x & 31) & ~7;
+        if (((m >> sh) & 0xffu) == 0) atomicAdd(lost, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+oct_child_counts(const uint32_t* __restrict__ scan /* 8E + 1 */, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_cnt,
+                 int nslots, long long E, uint32_t* __restrict__ counts /* nslots x 8 */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots * 8) return;
+    const int s = i >> 3, c = i & 7;
+    const long long b = (long long)c * E + seg_start[s];
+    counts[i] = scan[b + seg_cnt[s]] - scan[b];
+}
+
+__global__ void __launch_bounds__(256)
+oct_scatter(const uint32_t* __restrict__ entry_poly, const uint32_t* __restrict__ entry_slot, const uint32_t* __restrict__ flags,
+            const uint32_t* __restrict__ scan, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ child_base /* nslots x 8 */,
+            long long E, uint32_t* __restrict__ next_poly) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = gid >> 3; const int c = (int)(gid & 7);
+    if (e >= E) return;
+    const uint32_t s = entry_slot[e];
+    if (s == 0xffffffffu) return;
+    const long long idx = (long long)c * E + e;
+    if (flags[idx]) next_poly[child_base[(size_t)s * 8 + c] + (scan[idx] - scan[(long long)c * E + seg_start[s]])] = entry_poly[e];
+}
+
+__global__ void __launch_bounds__(256)
+oct_copy_lists(const uint32_t* __restrict__ src, const uint32_t* __restrict__ src_start, const uint32_t* __restrict__ dst_start,
+               const uint32_t* __restrict__ cnt, int nleaves, uint32_t* __restrict__ dst) {
+    for (int l = blockIdx.x; l < nleaves; l += gridDim.x) {
+        const uint32_t a = src_start[l], b = dst_start[l], n = cnt[l];
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) dst[b + k] = src[a + k];
+    }
+}
+
 // host-uploaded CSR -> packed headers + occupancy
 __global__ void __launch_bounds__(256)
 vg_pack_cells(const uint32_t* __restrict__ cell_offset, long long ncells, uint2* __restrict__ cells, uint32_t* __restrict__ occ) {

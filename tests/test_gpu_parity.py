@@ -335,3 +335,25 @@ def test_degenerate_rays(gpu):
         ref = getattr(ho, kind)(To, *oargs).Shoot(o, d)
         assert_events_equal(got, ref, uv=kind != "Voxel_Grid", what=kind + " degenerate rays")
         assert np.array_equal(got["o"], ref["o"]), kind
+
+
+@pytest.mark.parametrize("level,args", [("shoebox", (3, 2)), ("tiny", (3, 4)), ("2k", (5, 8)), ("10k", (6, 16)), ("50k", (7, 32))])
+def test_gpu_octree_build_matches_host_build_and_oracle(gpu, level, args):
+    """the Octree is built on the GPU level by level; node boxes, numbering, list order and the
+    lost-polygon count equal the host builder's arrays exactly and the oracle's tree structurally."""
+    import os
+    from tests.util import canon_octree
+    mesh = meshes.shoebox() if level == "shoebox" else meshes.hall(level)
+    T, To = _pair(gpu, mesh)
+    g = gpu.Octree([T], *args)
+    os.environ["HARE_OCT_HOST_BUILD"] = "1"
+    try:
+        h = gpu.Octree([T], *args)
+    finally:
+        del os.environ["HARE_OCT_HOST_BUILD"]
+    for a, b in zip(g.arrays(), h.arrays()):
+        assert np.array_equal(a, b)
+    assert g.info() == h.info()
+    o = ho.Octree(To, *args)
+    assert canon_octree(*g.arrays()) == canon_octree(*o.arrays())
+    assert (g.info()["nodes"], g.info()["list_entries"], g.info()["lost"]) == o.info()
