@@ -911,10 +911,56 @@ static int launch_vg_walk2(const VGrid& g, const PartDev& d, const double* o, co
     return HARE_OK;
 }
 
+#ifndef HARE_WAVE_SLOTS
+#define HARE_WAVE_SLOTS 64
+#endif
+#ifndef HARE_WAVE_WMAX
+#define HARE_WAVE_WMAX 4
+#endif
+// HARE_VG_WAVE=0 selects the first-generation kernel (vg_walk.cuh) for A/B measurements
+static bool use_wave() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_WAVE"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
+
+// Voxel_Grid, second generation: per-warp wavefront scheduler over shared-memory ray pools (vg_wave.cuh).
+// One CTA of HARE_WAVE_WARPS warps per SM; dynamic shared memory = occupancy bitmap (when it fits) + the pools.
+template <bool CHAIN, bool COUNT, bool OCC_SMEM>
+static int launch_vg_wave2(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
+                           const int32_t* rid, int64_t N, int order, const WalkOut& w, size_t smem, cudaStream_t st) {
+    auto k = vg_wave_kernel<CHAIN, COUNT, OCC_SMEM, HARE_WAVE_SLOTS, HARE_WAVE_WMAX>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = HARE_WAVE_WARPS * 32;
+    int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms);
+    k<<<(unsigned)blocks, threads, smem, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return HARE_OK;
+}
+
+static const size_t kSmemMax = 227 * 1024;
+
+// the wavefront kernel packs voxel coordinates into 10 bits each, ray numbers into 32 and the bounce into 16
+static bool wave_eligible(const VGrid& g, int64_t N, int order) {
+    return use_wave() && g.nx <= 1024 && g.ny <= 1024 && g.nz <= 1024 && N < (1LL << 32) && order < 65536;
+}
+
+template <bool CHAIN>
+static int launch_vg_wave(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
+                          const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+    const size_t pools = (size_t)HARE_WAVE_WARPS * WavePool<HARE_WAVE_SLOTS>::STRIDE;
+    const size_t occ_bytes = ((((size_t)g.nx * g.ny * g.nz + 31) / 32 + 3) & ~(size_t)3) * 4;
+    const bool in_smem = occ_bytes + pools <= kSmemMax;
+    if (w.counters) {
+        if (in_smem) return launch_vg_wave2<CHAIN, true, true>(g, d, o, dd, o1, o2, rid, N, order, w, occ_bytes + pools, st);
+        return launch_vg_wave2<CHAIN, true, false>(g, d, o, dd, o1, o2, rid, N, order, w, pools, st);
+    }
+    if (in_smem) return launch_vg_wave2<CHAIN, false, true>(g, d, o, dd, o1, o2, rid, N, order, w, occ_bytes + pools, st);
+    return launch_vg_wave2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, w, pools, st);
+}
+
 template <bool CHAIN>
 static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
                           const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
+    if (wave_eligible(g, N, order)) return launch_vg_wave<CHAIN>(g, d, o, dd, o1, o2, rid, N, order, w, st);
     const size_t occ_bytes = (((size_t)g.nx * g.ny * g.nz + 31) / 32) * 4;
     const bool in_smem = occ_bytes <= 200 * 1024;
     if (w.counters) {

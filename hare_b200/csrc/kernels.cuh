@@ -26,6 +26,7 @@ __device__ __forceinline__ void flush_counters(const CntT<COUNT>& c, unsigned lo
 
 }  // namespace hare
 #include "vg_walk.cuh"
+#include "vg_wave.cuh"
 #include "oct_walk.cuh"
 #include "kd_walk.cuh"
 namespace hare {

@@ -18,20 +18,30 @@ struct Cnt { unsigned long long cells, entries, tests, hits; };
 
 template <bool COUNT> struct CntT {
     unsigned int cells = 0, entries = 0, tests = 0, hits = 0;
-    __device__ __forceinline__ void cell() { if (COUNT) ++cells; }
-    __device__ __forceinline__ void entry() { if (COUNT) ++entries; }
-    __device__ __forceinline__ void test() { if (COUNT) ++tests; }
-    __device__ __forceinline__ void hit() { if (COUNT) ++hits; }
-    __device__ __forceinline__ void cull() {}
+    HD void cell() { if (COUNT) ++cells; }
+    HD void entry() { if (COUNT) ++entries; }
+    HD void test() { if (COUNT) ++tests; }
+    HD void hit() { if (COUNT) ++hits; }
+    HD void cull() {}
 };
+
+// read-only global load: LDG.E.CONSTANT on the device; a plain load when a traversal function is compiled
+// for the host (tests/emu replays the wavefront scheduler of vg_wave.cuh on the CPU)
+template <class T> HD T hare_ldg(const T* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 // Fetch one 128-byte polygon record as eight 128-bit read-only loads (LDG.E.128.CONSTANT),
 // all independent so they are in flight together.
-__device__ __forceinline__ void load_poly(const PolyRec* __restrict__ polys, uint32_t i, double* P) {
+HD void load_poly(const PolyRec* __restrict__ polys, uint32_t i, double* P) {
     const double2* src = reinterpret_cast<const double2*>(polys + i);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        double2 q = __ldg(src + k);
+        double2 q = hare_ldg(src + k);
         P[2 * k] = q.x; P[2 * k + 1] = q.y;
     }
 }
@@ -45,7 +55,7 @@ __device__ __forceinline__ void load_poly(const PolyRec* __restrict__ polys, uin
 // covered 13x by the explicit 4e-6 |v|^2 term below (it matters only when a tree leaf lists a polygon far
 // from its own box); the 3e-6 m rounding of p and of the stored centre moves the line by < 1e-5 m, far
 // inside the 1e-3 m + 1e-5 r by which the host pads the radius.
-__device__ __forceinline__ bool cull_sphere(const float4 s, float px, float py, float pz, float dx, float dy, float dz, float dd) {
+HD bool cull_sphere(const float4 s, float px, float py, float pz, float dx, float dy, float dz, float dd) {
     const float vx = s.x - px, vy = s.y - py, vz = s.z - pz;
     const float vd = fmaf(vx, dx, fmaf(vy, dy, vz * dz));
     const float vv = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
@@ -68,11 +78,11 @@ struct VGrid {
 #define HARE_EPS 0.001   /* Voxel_Grid.Epsilon, Voxel_Grid.cs:39 */
 
 // Voxels[X,Y,Z].Min / .Max on one axis: (X*vd - eps) + omin , ((X+1)*vd + eps) + omin   Voxel_Grid.cs:283-285
-__device__ __forceinline__ double vox_min(int X, double vd, double omin) { return ((double)X * vd - HARE_EPS) + omin; }
-__device__ __forceinline__ double vox_max(int X, double vd, double omin) { return ((double)(X + 1) * vd + HARE_EPS) + omin; }
+HD double vox_min(int X, double vd, double omin) { return ((double)X * vd - HARE_EPS) + omin; }
+HD double vox_max(int X, double vd, double omin) { return ((double)(X + 1) * vd + HARE_EPS) + omin; }
 
 // AABB.Intersect(ref Ray, ref tmin)  AABB_Main.cs:173-260 on OBox; moves the origin.
-__device__ __forceinline__ bool obox_enter(const VGrid& g, Ray3& R, double& tmin) {
+HD bool obox_enter(const VGrid& g, Ray3& R, double& tmin) {
     tmin = 0;
     double tmax = DBL_MAX;
     const double o[3] = { R.x, R.y, R.z }, d[3] = { R.dx, R.dy, R.dz };

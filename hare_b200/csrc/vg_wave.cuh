@@ -1,0 +1,419 @@
+// vg_wave.cuh -- K1/K5 for Voxel_Grid, second generation: a per-warp WAVEFRONT scheduler.
+//
+// vg_walk.cuh ties one ray to one thread; every trip round its loop the warp runs the S, W, C, F and T
+// phases one after the other, each with the subset of lanes whose ray happens to be in that phase: ncu
+// shows ~10 of 32 lanes active per issued instruction (profiles/r1_ncu_bench_summary.txt).
+//
+// Here the ray state lives in SHARED MEMORY instead of registers.  Every warp owns a private pool of SLOTS
+// (> 32) ray slots, stored structure-of-arrays so that any lane can work on any slot.  Each slot carries a
+// one-byte phase tag.  Each trip the warp
+//   1. counts its slots per phase (ballots over the tags),
+//   2. picks the phase with the most ready slots,
+//   3. compacts up to 32 slot indices of that phase, one per lane (popc-ranked, via a 32-byte smem list),
+//   4. runs that ONE phase converged on (up to) 32 different rays, and writes the state and new tags back.
+// No inter-warp communication exists (only __syncwarp), so there is nothing to deadlock on.
+//
+// Phases (the arithmetic of each is the same, operation for operation, as in vg_walk.cuh / shoot_one, i.e.
+// Voxel_Grid.Shoot, Voxel_Grid.cs:351-552):
+//   SF  finish a Shoot (write the event, reflect), fetch a new ray if the slot is empty, DDA set-up
+//   W   up to W_MAX voxel steps (empty voxels skipped on the occupancy bitmap in shared memory)
+//   C   next <= 4 list entries: ids + bounding spheres, FP32 conservative sphere cull
+//   T   one exact FP64 polygon test (128-byte record, Ray_Side, Moller-Trumbore)
+//
+// Every per-slot function below is `HD`: tests/emu/ compiles the same functions for the host and replays
+// the scheduler on the CPU against the oracle (logic check without a GPU, and lane-utilisation statistics).
+#pragma once
+#include "shoot.cuh"
+#include "vg_walk.cuh"
+
+namespace hare {
+
+enum : uint32_t { PH_SF = 0, PH_W = 1, PH_C = 2, PH_T = 3, PH_DONE = 4, PH_COUNT = 4 };
+
+// slot flags
+enum : uint32_t {
+    WF_NEGX = 1u, WF_NEGY = 2u, WF_NEGZ = 4u, WF_HAVE = 8u, WF_BLIND = 16u,
+    WF_NORAY = 32u,                        // the slot holds no ray: SF fetches one
+    WF_FIN_SHIFT = 6, WF_FIN_MASK = 3u << 6,   // 0 running, 1 hit, 2 miss, 3 fault (the reference throws)
+    WF_BMASK_SHIFT = 8, WF_BMASK_MASK = 15u << 8,
+    WF_BOUNCE_SHIFT = 16
+};
+enum : uint32_t { FIN_RUN = 0, FIN_HIT = 1, FIN_MISS = 2, FIN_FAULT = 3 };
+
+// field indices of the structure-of-arrays pool
+enum { D_OX, D_OY, D_OZ, D_DX, D_DY, D_DZ, D_TMX, D_TMY, D_TMZ, D_TDX, D_TDY, D_TDZ, D_TMIN, D_TSTART, D_COUNT };
+enum { U_XYZ, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_BID0, U_BID1, U_BID2, U_BID3, U_COUNT };
+enum { F_PX, F_PY, F_PZ, F_COUNT };
+
+template <int SLOTS>
+struct WavePool {
+    double* dbl; uint32_t* u32; float* f32; uint8_t* tag; uint8_t* sel;
+    static_assert(SLOTS <= 255, "phase counts are packed into bytes");
+    static constexpr size_t BYTES = (size_t)SLOTS * (D_COUNT * 8 + U_COUNT * 4 + F_COUNT * 4 + 1) + 32;
+    static constexpr size_t STRIDE = (BYTES + 15) & ~(size_t)15;
+    HD void bind(unsigned char* base) {
+        dbl = reinterpret_cast<double*>(base);
+        u32 = reinterpret_cast<uint32_t*>(base + (size_t)SLOTS * D_COUNT * 8);
+        f32 = reinterpret_cast<float*>(base + (size_t)SLOTS * (D_COUNT * 8 + U_COUNT * 4));
+        tag = base + (size_t)SLOTS * (D_COUNT * 8 + U_COUNT * 4 + F_COUNT * 4);
+        sel = tag + SLOTS;
+    }
+    HD double& D(int f, int s) const { return dbl[f * SLOTS + s]; }
+    HD uint32_t& U(int f, int s) const { return u32[f * SLOTS + s]; }
+    HD float& F(int f, int s) const { return f32[f * SLOTS + s]; }
+};
+
+// which phase a slot waits for, from its state
+HD uint32_t wave_tag(uint32_t fl, uint32_t lpos, uint32_t lend) {
+    if (fl & WF_FIN_MASK) return PH_SF;
+    if (fl & WF_BMASK_MASK) return PH_T;
+    return lpos < lend ? PH_C : PH_W;
+}
+
+// scheduling policy: the phase with the most ready slots; ties go to the later phase (drain before refill)
+HD int wave_pick(const int n[PH_COUNT]) {
+    int best = PH_T, bn = n[PH_T];
+    if (n[PH_C] > bn) { best = PH_C; bn = n[PH_C]; }
+    if (n[PH_W] > bn) { best = PH_W; bn = n[PH_W]; }
+    if (n[PH_SF] > bn) { best = PH_SF; bn = n[PH_SF]; }
+    return bn > 0 ? best : -1;
+}
+
+// list range of voxel ci and the FP32 ray point used by the cull; empty voxels never touch the cell table
+template <bool COUNT>
+HD void wave_enter_cell(const VGrid& g, const uint32_t* occ, bool occ_smem, bool blind, uint32_t ci, const Ray3& R, double t_in,
+                        uint32_t& lpos, uint32_t& lend, float& fpx, float& fpy, float& fpz, CntT<COUNT>& c) {
+    c.cell();
+    lpos = 0; lend = 0;
+    const uint32_t word = occ_smem ? occ[ci >> 5] : hare_ldg(occ + (ci >> 5));
+    if (!blind && ((word >> (ci & 31)) & 1u)) {
+        const uint2 h = hare_ldg(g.cells + ci);
+        lpos = h.x; lend = h.x + h.y;
+        fpx = (float)fma(R.dx, t_in, R.x); fpy = (float)fma(R.dy, t_in, R.y); fpz = (float)fma(R.dz, t_in, R.z);
+    }
+}
+
+// ---- SF, part 1: the Shoot in slot s is over -> write its event; a chain reflects and goes on, or ends.
+// Afterwards the slot either holds a ray that needs a set-up, or carries WF_NORAY.
+template <bool CHAIN, bool COUNT, int SLOTS>
+HD void wave_finish(const PolyRec* __restrict__ polys, const WavePool<SLOTS>& p, int s, int order, const WalkOut& out,
+                    unsigned int& shots, CntT<COUNT>& c) {
+    uint32_t fl = p.U(U_FLAGS, s);
+    const uint32_t fin = (fl & WF_FIN_MASK) >> WF_FIN_SHIFT;
+    if (fin == FIN_RUN) return;
+    const double tmin = p.D(D_TMIN, s);
+    Ray3 R = { p.D(D_OX, s), p.D(D_OY, s), p.D(D_OZ, s), p.D(D_DX, s), p.D(D_DY, s), p.D(D_DZ, s) };
+    const int pid = (int)p.U(U_PID, s);
+    const long long ray = (long long)p.U(U_RAY, s);
+    const double ev_t = (fin == FIN_HIT) ? tmin + p.D(D_TSTART, s) : 0.0;
+    const int ev_p = (fin == FIN_HIT) ? pid : (fin == FIN_FAULT ? -2 : -1);
+    // X_Point = R + d*t of the winning test (Hare_Geometry_Polygons.cs:802)
+    const double bx = R.x + R.dx * tmin, by = R.y + R.dy * tmin, bz = R.z + R.dz * tmin;
+    if (fin == FIN_HIT) c.hit();
+    fl &= ~(WF_FIN_MASK | WF_BMASK_MASK | WF_HAVE);
+    if (CHAIN) {
+        uint32_t bounce = fl >> WF_BOUNCE_SHIFT;
+        ++shots;
+        if (out.ev_pid) out.ev_pid[ray * order + bounce] = ev_p;
+        if (out.ev_t) out.ev_t[ray * order + bounce] = ev_t;
+        ++bounce;
+        bool go_on = false;
+        if (fin == FIN_HIT) {
+            const double* P = polys[pid].v;
+            const double nx = hare_ldg(P + 12), ny = hare_ldg(P + 13), nz = hare_ldg(P + 14);
+            const double k = 2 * ((R.dx * nx) + (R.dy * ny) + (R.dz * nz));
+            R.dx = R.dx - k * nx; R.dy = R.dy - k * ny; R.dz = R.dz - k * nz;
+            R.x = bx; R.y = by; R.z = bz;
+            p.D(D_OX, s) = R.x; p.D(D_OY, s) = R.y; p.D(D_OZ, s) = R.z;
+            p.D(D_DX, s) = R.dx; p.D(D_DY, s) = R.dy; p.D(D_DZ, s) = R.dz;
+            p.U(U_OR1, s) = (uint32_t)pid;
+            go_on = (int)bounce < order;
+        }
+        fl = (fl & 0xffffu) | (bounce << WF_BOUNCE_SHIFT);
+        if (!go_on) {
+            for (int q = (int)bounce; q < order; ++q) {
+                if (out.ev_pid) out.ev_pid[ray * order + q] = -3;
+                if (out.ev_t) out.ev_t[ray * order + q] = 0;
+            }
+            if (out.fin_o) { out.fin_o[3 * ray] = R.x; out.fin_o[3 * ray + 1] = R.y; out.fin_o[3 * ray + 2] = R.z; }
+            if (out.fin_d) { out.fin_d[3 * ray] = R.dx; out.fin_d[3 * ray + 1] = R.dy; out.fin_d[3 * ray + 2] = R.dz; }
+            if (out.nshots) out.nshots[ray] = (int32_t)bounce;
+            fl |= WF_NORAY;
+        }
+    } else {
+        const bool h = fin == FIN_HIT;
+        out.pid[ray] = ev_p;
+        if (out.t) out.t[ray] = ev_t;
+        if (out.xyz) { out.xyz[3 * ray] = h ? bx : 0.0; out.xyz[3 * ray + 1] = h ? by : 0.0; out.xyz[3 * ray + 2] = h ? bz : 0.0; }
+        if (out.uv) { out.uv[2 * ray] = 0.0; out.uv[2 * ray + 1] = 0.0; }
+        if (out.omoved) { out.omoved[3 * ray] = R.x; out.omoved[3 * ray + 1] = R.y; out.omoved[3 * ray + 2] = R.z; }
+        fl |= WF_NORAY;
+    }
+    p.U(U_FLAGS, s) = fl;
+}
+
+// ---- SF, part 2: put ray number `ray` into slot s
+template <int SLOTS>
+HD void wave_fetch(const WavePool<SLOTS>& p, int s, long long ray, const double* __restrict__ o, const double* __restrict__ d,
+                   const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a, const int32_t* __restrict__ rid) {
+    p.D(D_OX, s) = o[3 * ray]; p.D(D_OY, s) = o[3 * ray + 1]; p.D(D_OZ, s) = o[3 * ray + 2];
+    p.D(D_DX, s) = d[3 * ray]; p.D(D_DY, s) = d[3 * ray + 1]; p.D(D_DZ, s) = d[3 * ray + 2];
+    p.U(U_OR1, s) = (uint32_t)(o1a ? o1a[ray] : -1);
+    p.U(U_OR2, s) = (uint32_t)(o2a ? o2a[ray] : -1);
+    p.U(U_RAY, s) = (uint32_t)ray;
+    p.U(U_FLAGS, s) = (rid && rid[ray] == 0) ? WF_BLIND : 0u;   // bounce 0, running
+}
+
+// ---- SF, part 3: DDA set-up of the ray in slot s   Voxel_Grid.cs:357-422.  Returns the slot's new tag.
+template <bool COUNT, int SLOTS>
+HD uint32_t wave_setup(const VGrid& g, const uint32_t* occ, bool occ_smem, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
+    uint32_t fl = p.U(U_FLAGS, s) & (WF_BLIND | (0xffffu << WF_BOUNCE_SHIFT));
+    Ray3 R = { p.D(D_OX, s), p.D(D_OY, s), p.D(D_OZ, s), p.D(D_DX, s), p.D(D_DY, s), p.D(D_DZ, s) };
+    double t_start = 0;
+    uint32_t fin = FIN_RUN, lpos = 0, lend = 0;
+    int X = floor_to_int((R.x - g.ominx) / g.vdx);
+    int Y = floor_to_int((R.y - g.ominy) / g.vdy);
+    int Z = floor_to_int((R.z - g.ominz) / g.vdz);
+    if (X < 0 || X >= g.nx || Y < 0 || Y >= g.ny || Z < 0 || Z >= g.nz) {
+        if (!obox_enter(g, R, t_start)) fin = FIN_MISS;
+        else {
+            p.D(D_OX, s) = R.x; p.D(D_OY, s) = R.y; p.D(D_OZ, s) = R.z;   // the caller's Ray is moved (AABB_Main.cs:255-257)
+            X = floor_to_int((R.x - g.ominx + R.dx * 1E-6) / g.vdx);
+            Y = floor_to_int((R.y - g.ominy + R.dy * 1E-6) / g.vdy);
+            Z = floor_to_int((R.z - g.ominz + R.dz * 1E-6) / g.vdz);
+            if (X < 0 || X >= g.nx || Y < 0 || Y >= g.ny || Z < 0 || Z >= g.nz) fin = FIN_FAULT;
+        }
+    }
+    p.D(D_TMIN, s) = DBL_MAX; p.D(D_TSTART, s) = t_start;
+    p.U(U_PID, s) = 0xffffffffu; p.U(U_LAST, s) = 0xffffffffu;
+    if (fin == FIN_RUN) {
+        const bool nx_ = R.dx < 0, ny_ = R.dy < 0, nz_ = R.dz < 0;
+        fl |= (nx_ ? WF_NEGX : 0u) | (ny_ ? WF_NEGY : 0u) | (nz_ ? WF_NEGZ : 0u);
+        p.D(D_TMX, s) = ((nx_ ? vox_min(X, g.vdx, g.ominx) : vox_max(X, g.vdx, g.ominx)) - R.x) / R.dx;
+        p.D(D_TMY, s) = ((ny_ ? vox_min(Y, g.vdy, g.ominy) : vox_max(Y, g.vdy, g.ominy)) - R.y) / R.dy;
+        p.D(D_TMZ, s) = ((nz_ ? vox_min(Z, g.vdz, g.ominz) : vox_max(Z, g.vdz, g.ominz)) - R.z) / R.dz;
+        p.D(D_TDX, s) = g.vdx / R.dx * (nx_ ? -1.0 : 1.0);
+        p.D(D_TDY, s) = g.vdy / R.dy * (ny_ ? -1.0 : 1.0);
+        p.D(D_TDZ, s) = g.vdz / R.dz * (nz_ ? -1.0 : 1.0);
+        p.U(U_XYZ, s) = (uint32_t)X | ((uint32_t)Y << 10) | ((uint32_t)Z << 20);
+        const uint32_t ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
+        float fpx = 0, fpy = 0, fpz = 0;
+        wave_enter_cell<COUNT>(g, occ, occ_smem, (fl & WF_BLIND) != 0, ci, R, 0.0, lpos, lend, fpx, fpy, fpz, c);
+        if (lpos < lend) { p.F(F_PX, s) = fpx; p.F(F_PY, s) = fpy; p.F(F_PZ, s) = fpz; }
+    }
+    fl |= fin << WF_FIN_SHIFT;
+    p.U(U_FLAGS, s) = fl; p.U(U_LPOS, s) = lpos; p.U(U_LEND, s) = lend;
+    return wave_tag(fl, lpos, lend);
+}
+
+// ---- W: the slot's list is exhausted -> accept the carried candidate or step the 3D-DDA (<= W_MAX voxels)
+template <bool COUNT, int SLOTS, int W_MAX>
+HD uint32_t wave_walk(const VGrid& g, const uint32_t* occ, bool occ_smem, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
+    uint32_t fl = p.U(U_FLAGS, s);
+    const Ray3 R = { p.D(D_OX, s), p.D(D_OY, s), p.D(D_OZ, s), p.D(D_DX, s), p.D(D_DY, s), p.D(D_DZ, s) };
+    double tMaxX = p.D(D_TMX, s), tMaxY = p.D(D_TMY, s), tMaxZ = p.D(D_TMZ, s);
+    const double tDeltaX = p.D(D_TDX, s), tDeltaY = p.D(D_TDY, s), tDeltaZ = p.D(D_TDZ, s);
+    const uint32_t xyz = p.U(U_XYZ, s);
+    int X = (int)(xyz & 1023u), Y = (int)((xyz >> 10) & 1023u), Z = (int)(xyz >> 20);
+    const int stepX = (fl & WF_NEGX) ? -1 : 1, stepY = (fl & WF_NEGY) ? -1 : 1, stepZ = (fl & WF_NEGZ) ? -1 : 1;
+    const int strideX = g.ny * g.nz, strideY = g.nz;
+    uint32_t ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
+    const bool have = (fl & WF_HAVE) != 0, blind = (fl & WF_BLIND) != 0;
+    double bx = 0, by = 0, bz = 0;
+    if (have) { const double tmin = p.D(D_TMIN, s); bx = R.x + R.dx * tmin; by = R.y + R.dy * tmin; bz = R.z + R.dz * tmin; }
+    uint32_t fin = FIN_RUN, lpos = 0, lend = 0;
+    float fpx = 0, fpy = 0, fpz = 0;
+#pragma unroll 1
+    for (int guard = 0; guard < W_MAX; ++guard) {
+        // list exhausted: Voxels[X,Y,Z].IsPointInBox(candidate)?   Voxel_Grid.cs:496-500
+        if (have) {
+            const bool in = !(bx < vox_min(X, g.vdx, g.ominx)) & !(by < vox_min(Y, g.vdy, g.ominy)) & !(bz < vox_min(Z, g.vdz, g.ominz)) &
+                            !(bx > vox_max(X, g.vdx, g.ominx)) & !(by > vox_max(Y, g.vdy, g.ominy)) & !(bz > vox_max(Z, g.vdz, g.ominz));
+            if (in) { fin = FIN_HIT; break; }
+        }
+        // next voxel   Voxel_Grid.cs:504-550: X only if strictly below both, Y only if below Z, else Z
+        const bool xy = tMaxX < tMaxY, xz = tMaxX < tMaxZ, yz = tMaxY < tMaxZ;
+        const bool goX = xy & xz, goY = (!xy) & yz;
+        const bool goZ = !(goX | goY);
+        const double t_in = goX ? tMaxX : (goY ? tMaxY : tMaxZ);
+        const double nX = tMaxX + tDeltaX, nY = tMaxY + tDeltaY, nZ = tMaxZ + tDeltaZ;
+        tMaxX = goX ? nX : tMaxX; tMaxY = goY ? nY : tMaxY; tMaxZ = goZ ? nZ : tMaxZ;
+        X += goX ? stepX : 0; Y += goY ? stepY : 0; Z += goZ ? stepZ : 0;
+        ci += (uint32_t)(goX ? stepX * strideX : (goY ? stepY * strideY : stepZ));
+        if ((unsigned)X >= (unsigned)g.nx || (unsigned)Y >= (unsigned)g.ny || (unsigned)Z >= (unsigned)g.nz) { fin = FIN_MISS; break; }
+        wave_enter_cell<COUNT>(g, occ, occ_smem, blind, ci, R, t_in, lpos, lend, fpx, fpy, fpz, c);
+        if (lpos < lend) break;
+    }
+    fl |= fin << WF_FIN_SHIFT;
+    if (fin == FIN_RUN) {
+        p.D(D_TMX, s) = tMaxX; p.D(D_TMY, s) = tMaxY; p.D(D_TMZ, s) = tMaxZ;
+        p.U(U_XYZ, s) = (uint32_t)X | ((uint32_t)Y << 10) | ((uint32_t)Z << 20);
+        p.U(U_LPOS, s) = lpos; p.U(U_LEND, s) = lend;
+        if (lpos < lend) { p.F(F_PX, s) = fpx; p.F(F_PY, s) = fpy; p.F(F_PZ, s) = fpz; }
+    } else {
+        p.U(U_FLAGS, s) = fl;
+    }
+    return wave_tag(fl, lpos, lend);
+}
+
+// ---- C: cull the next (up to) four list entries; the survivors wait in the slot for T
+template <bool COUNT, int SLOTS>
+HD uint32_t wave_cull(const VGrid& g, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
+    uint32_t lpos = p.U(U_LPOS, s);
+    const uint32_t lend = p.U(U_LEND, s);
+    const uint32_t n = (lend - lpos) < 4u ? (lend - lpos) : 4u;
+    const uint32_t bid0 = hare_ldg(g.cell_poly + lpos);
+    const uint32_t bid1 = (n > 1) ? hare_ldg(g.cell_poly + lpos + 1) : bid0;
+    const uint32_t bid2 = (n > 2) ? hare_ldg(g.cell_poly + lpos + 2) : bid0;
+    const uint32_t bid3 = (n > 3) ? hare_ldg(g.cell_poly + lpos + 3) : bid0;
+    const float4 s0 = hare_ldg(g.sph + bid0), s1 = hare_ldg(g.sph + bid1), s2 = hare_ldg(g.sph + bid2), s3 = hare_ldg(g.sph + bid3);
+    lpos += n;
+    if (COUNT) c.entries += n;
+    const float fdx = (float)p.D(D_DX, s), fdy = (float)p.D(D_DY, s), fdz = (float)p.D(D_DZ, s);
+    const float fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
+    const float fpx = p.F(F_PX, s), fpy = p.F(F_PY, s), fpz = p.F(F_PZ, s);
+    const int or1 = (int)p.U(U_OR1, s), or2 = (int)p.U(U_OR2, s), pid = (int)p.U(U_PID, s);
+    const uint32_t last = p.U(U_LAST, s);
+    // poly_origin skip (Voxel_Grid.cs:477); a polygon already tested for this ray cannot change the result
+    auto keep = [&](uint32_t i, const float4& sp) {
+        return !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) && !cull_sphere(sp, fpx, fpy, fpz, fdx, fdy, fdz, fdd);
+    };
+    const uint32_t bmask = (keep(bid0, s0) ? 1u : 0u) | ((n > 1 && keep(bid1, s1)) ? 2u : 0u) |
+                           ((n > 2 && keep(bid2, s2)) ? 4u : 0u) | ((n > 3 && keep(bid3, s3)) ? 8u : 0u);
+    p.U(U_LPOS, s) = lpos;
+    if (bmask) {
+        p.U(U_BID0, s) = bid0; p.U(U_BID1, s) = bid1; p.U(U_BID2, s) = bid2; p.U(U_BID3, s) = bid3;
+        p.U(U_FLAGS, s) |= bmask << WF_BMASK_SHIFT;
+        return PH_T;
+    }
+    return lpos < lend ? PH_C : PH_W;
+}
+
+// ---- T: one exact FP64 test of the lowest surviving entry
+template <bool COUNT, int SLOTS>
+HD uint32_t wave_test(const PolyRec* __restrict__ polys, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
+    uint32_t fl = p.U(U_FLAGS, s);
+    const uint32_t bmask = (fl & WF_BMASK_MASK) >> WF_BMASK_SHIFT;
+    const int k = (bmask & 1u) ? 0 : ((bmask & 2u) ? 1 : ((bmask & 4u) ? 2 : 3));   // lowest survivor first
+    const uint32_t pend = p.U(U_BID0 + k, s);
+    fl &= ~((1u << k) << WF_BMASK_SHIFT);
+    c.test();
+    const Ray3 R = { p.D(D_OX, s), p.D(D_OY, s), p.D(D_OZ, s), p.D(D_DX, s), p.D(D_DY, s), p.D(D_DZ, s) };
+    double P[16], t = 0;
+    load_poly(polys, pend, P);
+    // Polygon.Ray_Side picks the winding (Hare_Geometry_Polygons.cs:601-606, 637-660, 784-823):
+    //   side ? (P0,P1,P2) then (P2,P3,P0) : (P2,P1,P0) then (P0,P3,P2)
+    const bool side = !(dot3(R.dx, R.dy, R.dz, P[12], P[13], P[14]) < 0);
+    const double ax = side ? P[0] : P[6], ay = side ? P[1] : P[7], az = side ? P[2] : P[8];
+    const double cx = side ? P[6] : P[0], cy = side ? P[7] : P[1], cz = side ? P[8] : P[2];
+    bool hit = ray_x_tri_fast1(R, ax, ay, az, P[3], P[4], P[5], cx, cy, cz, t);
+    if (!hit && P[15] == 4.0) hit = ray_x_tri_fast1(R, cx, cy, cz, P[9], P[10], P[11], ax, ay, az, t);
+    p.U(U_LAST, s) = pend;
+    if (hit && t > 0.0000000001 && t < p.D(D_TMIN, s)) { p.D(D_TMIN, s) = t; p.U(U_PID, s) = pend; fl |= WF_HAVE; }
+    p.U(U_FLAGS, s) = fl;
+    return wave_tag(fl, p.U(U_LPOS, s), p.U(U_LEND, s));
+}
+
+// number of the c-th ray consumed by warp gw out of tw warps: warps take rays in interleaved groups of 32
+HD long long wave_ray_number(long long c, long long gw, long long tw) { return ((c >> 5) * tw + gw) * 32 + (c & 31); }
+
+#if defined(__CUDACC__)
+
+#ifndef HARE_WAVE_WARPS
+#define HARE_WAVE_WARPS 16
+#endif
+
+template <bool CHAIN, bool COUNT, bool OCC_SMEM, int SLOTS, int W_MAX>
+__global__ void __launch_bounds__(HARE_WAVE_WARPS * 32, 1)
+vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
+               const double* __restrict__ o, const double* __restrict__ d,
+               const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a, const int32_t* __restrict__ rid,
+               long long N, int order, const WalkOut out) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint32_t* s_occ = reinterpret_cast<uint32_t*>(s_raw);
+    uint32_t occ_words = 0;
+    if (OCC_SMEM) {
+        occ_words = ((uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz + 31u) >> 5;
+        for (uint32_t w = threadIdx.x; w < occ_words; w += blockDim.x) s_occ[w] = __ldg(g.occ + w);
+        occ_words = (occ_words + 3u) & ~3u;
+    }
+    const uint32_t* occ = OCC_SMEM ? s_occ : g.occ;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WavePool<SLOTS> p;
+    p.bind(s_raw + (size_t)occ_words * 4 + (size_t)warp * WavePool<SLOTS>::STRIDE);
+    constexpr int GROUPS = (SLOTS + 31) / 32;
+#pragma unroll
+    for (int k = 0; k < GROUPS; ++k) {
+        const int s = k * 32 + lane;
+        if (s < SLOTS) { p.U(U_FLAGS, s) = WF_NORAY; p.U(U_LPOS, s) = 0; p.U(U_LEND, s) = 0; p.tag[s] = (uint8_t)PH_SF; }
+    }
+    __syncthreads();
+
+    CntT<COUNT> c;
+    unsigned int shots = 0;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp, tw = (long long)gridDim.x * (blockDim.x >> 5);
+    long long cur = 0;   // rays this warp has consumed (warp-uniform)
+    const unsigned lt = (1u << lane) - 1u;
+
+    while (true) {
+        // 1. count the slots per phase: one REDUX over byte-packed per-lane counts (a byte holds <= SLOTS <= 255)
+        uint32_t tg[GROUPS], packed = 0;
+#pragma unroll
+        for (int k = 0; k < GROUPS; ++k) {
+            const int s = k * 32 + lane;
+            tg[k] = (s < SLOTS) ? p.tag[s] : (uint32_t)PH_DONE;
+            packed += (tg[k] < (uint32_t)PH_COUNT) ? (1u << (8 * tg[k])) : 0u;
+        }
+        packed = __reduce_add_sync(0xffffffffu, packed);
+        const int n[PH_COUNT] = { (int)(packed & 255u), (int)((packed >> 8) & 255u), (int)((packed >> 16) & 255u), (int)(packed >> 24) };
+        // 2. pick one
+        const int ph = wave_pick(n);
+        if (ph < 0) break;
+        // 3. compact up to 32 of its slots, one per lane
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < GROUPS; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, tg[k] == (uint32_t)ph);
+            const int r = base + __popc(m & lt);
+            if (tg[k] == (uint32_t)ph && r < 32) p.sel[r] = (uint8_t)(k * 32 + lane);
+            base += __popc(m);
+        }
+        __syncwarp();
+        const int cnt = base < 32 ? base : 32;
+        const bool act = lane < cnt;
+        const int s = act ? (int)p.sel[lane] : 0;
+        // 4. run it
+        uint32_t nt = PH_DONE;
+        if (ph == PH_T) {
+            if (act) nt = wave_test<COUNT, SLOTS>(polys, p, s, c);
+        } else if (ph == PH_C) {
+            if (act) nt = wave_cull<COUNT, SLOTS>(g, p, s, c);
+        } else if (ph == PH_W) {
+            if (act) nt = wave_walk<COUNT, SLOTS, W_MAX>(g, occ, OCC_SMEM, p, s, c);
+        } else {
+            if (act) wave_finish<CHAIN, COUNT, SLOTS>(polys, p, s, order, out, shots, c);
+            const bool noray = act && (p.U(U_FLAGS, s) & WF_NORAY);
+            const unsigned want = __ballot_sync(0xffffffffu, noray);
+            bool ready = act;
+            if (noray) {
+                const long long ray = wave_ray_number(cur + __popc(want & lt), gw, tw);
+                if (ray < N) wave_fetch<SLOTS>(p, s, ray, o, d, o1a, o2a, rid);
+                else ready = false;
+            }
+            cur += __popc(want);
+            if (ready) nt = wave_setup<COUNT, SLOTS>(g, occ, OCC_SMEM, p, s, c);
+        }
+        if (act) p.tag[s] = (uint8_t)nt;
+        __syncwarp();
+    }
+    if (CHAIN) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) shots += __shfl_xor_sync(0xffffffffu, shots, off);
+        if (lane == 0 && shots) atomicAdd(out.total_shots, (unsigned long long)shots);
+    }
+    flush_counters<COUNT>(c, out.counters);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace hare

@@ -1,0 +1,142 @@
+// wave_emu.cu -- TEST INFRASTRUCTURE: replays the wavefront scheduler of hare_b200/csrc/vg_wave.cuh on the CPU.
+//
+// The per-slot phase functions of vg_wave.cuh (wave_finish / wave_fetch / wave_setup / wave_walk / wave_cull /
+// wave_test) and its policy (wave_pick, wave_tag, wave_ray_number) are `__host__ __device__`; this file compiles
+// them for the host and drives them with a sequential copy of the kernel's trip loop (one simulated warp at a
+// time, 32 "lanes" run one after the other).  It lets the CPU test-suite check the state machine against the
+// oracle without a GPU, and reports how many lanes each phase execution would keep busy.
+// Nothing here is shipped or measured; it never launches a kernel.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "../../hare_b200/csrc/kernels.cuh"
+#include "../../hare_b200/csrc/vg_wave.cuh"
+
+using namespace hare;
+
+namespace {
+
+struct Stats { double exec[4] = { 0, 0, 0, 0 }, lanes[4] = { 0, 0, 0, 0 }, wsteps_warp = 0, wsteps_lane = 0, trips = 0, whave_exec = 0, whave_lane = 0; };
+
+template <bool CHAIN, int SLOTS, int W_MAX>
+void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d, const int32_t* o1a, const int32_t* o2a,
+         const int32_t* rid, long long N, int order, const WalkOut& out, int tw, Stats& st, unsigned long long* counters) {
+    std::vector<unsigned char> mem(WavePool<SLOTS>::STRIDE + 64);
+    CntT<true> c;
+    unsigned long long total = 0;
+    for (long long gw = 0; gw < tw; ++gw) {
+        WavePool<SLOTS> p;
+        p.bind(mem.data());
+        for (int s = 0; s < SLOTS; ++s) { p.U(U_FLAGS, s) = WF_NORAY; p.U(U_LPOS, s) = 0; p.U(U_LEND, s) = 0; p.tag[s] = (uint8_t)PH_SF; }
+        long long cur = 0;
+        unsigned int shots = 0;
+        while (true) {
+            int n[PH_COUNT] = { 0, 0, 0, 0 };
+            for (int s = 0; s < SLOTS; ++s) if (p.tag[s] < PH_COUNT) ++n[p.tag[s]];
+            const int ph = wave_pick(n);
+            if (ph < 0) break;
+            // the kernel ranks group 0 (slots 0..31) before group 1, lane order inside a group = slot order
+            int sel[32], cnt = 0;
+            for (int s = 0; s < SLOTS && cnt < 32; ++s) if (p.tag[s] == ph) sel[cnt++] = s;
+            st.exec[ph] += 1; st.lanes[ph] += cnt; st.trips += 1;
+            uint32_t nt[32];
+            if (ph == PH_T) {
+                for (int l = 0; l < cnt; ++l) nt[l] = wave_test<true, SLOTS>(polys, p, sel[l], c);
+            } else if (ph == PH_C) {
+                for (int l = 0; l < cnt; ++l) nt[l] = wave_cull<true, SLOTS>(g, p, sel[l], c);
+            } else if (ph == PH_W) {
+                unsigned mx = 0; bool anyhave = false;
+                for (int l = 0; l < cnt; ++l) {
+                    if (p.U(U_FLAGS, sel[l]) & WF_HAVE) { anyhave = true; st.whave_lane += 1; }
+                    const unsigned before = c.cells;
+                    const bool had = (p.U(U_FLAGS, sel[l]) & WF_HAVE) != 0;
+                    nt[l] = wave_walk<true, SLOTS, W_MAX>(g, g.occ, false, p, sel[l], c);
+                    unsigned steps = c.cells - before;
+                    if (steps == 0 || (had && nt[l] == PH_SF)) steps += 1;   // an accept / exit iteration enters no cell
+                    st.wsteps_lane += steps; if (steps > mx) mx = steps;
+                }
+                st.wsteps_warp += mx; if (anyhave) st.whave_exec += 1;
+            } else {
+                for (int l = 0; l < cnt; ++l) wave_finish<CHAIN, true, SLOTS>(polys, p, sel[l], order, out, shots, c);
+                int rank = 0;
+                for (int l = 0; l < cnt; ++l) {
+                    bool ready = true;
+                    if (p.U(U_FLAGS, sel[l]) & WF_NORAY) {
+                        const long long ray = wave_ray_number(cur + rank, gw, tw);
+                        ++rank;
+                        if (ray < N) wave_fetch<SLOTS>(p, sel[l], ray, o, d, o1a, o2a, rid);
+                        else ready = false;
+                    }
+                    nt[l] = ready ? wave_setup<true, SLOTS>(g, g.occ, false, p, sel[l], c) : (uint32_t)PH_DONE;
+                }
+                cur += rank;
+            }
+            for (int l = 0; l < cnt; ++l) p.tag[sel[l]] = (uint8_t)nt[l];
+        }
+        total += shots;
+    }
+    if (CHAIN && out.total_shots) *out.total_shots = total;
+    if (counters) { counters[0] = c.cells; counters[1] = c.entries; counters[2] = c.tests; counters[3] = c.hits; }
+}
+
+}  // namespace
+
+// Host arrays in, host arrays out.  slots in {40, 48, 64, 96}, wmax in {2, 4, 8}.  stats: 14 doubles
+// (exec[4], lanes[4] in phase order SF, W, C, T; warp-level W iterations; lane-level W iterations; trips; 3 spare).
+extern "C" int wave_emu(const double* verts, const double* normals, const int32_t* vcount, int64_t P,
+                        const double obox[6], const int32_t ct[3], const uint32_t* cell_offset, const uint32_t* cell_poly,
+                        const double* o, const double* d, const int32_t* o1, const int32_t* o2, const int32_t* rid, int64_t N,
+                        int chain, int order,
+                        double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
+                        int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
+                        int slots, int wmax, int n_warps, double* stats, unsigned long long* counters) {
+    std::vector<PolyRec> recs((size_t)P);
+    std::vector<float4> sph((size_t)P);
+    for (int64_t i = 0; i < P; ++i) {
+        for (int k = 0; k < 12; ++k) recs[i].v[k] = verts[12 * i + k];
+        if (vcount[i] == 3) for (int a = 0; a < 3; ++a) recs[i].v[9 + a] = verts[12 * i + 6 + a];
+        for (int a = 0; a < 3; ++a) recs[i].v[12 + a] = normals[3 * i + a];
+        recs[i].v[15] = (double)vcount[i];
+        // padded FP32 bounding sphere, as hare_topology_create makes it
+        double lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) lo[a] = hi[a] = verts[12 * i + a];
+        for (int k = 1; k < vcount[i]; ++k)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::fmin(lo[a], verts[12 * i + 3 * k + a]); hi[a] = std::fmax(hi[a], verts[12 * i + 3 * k + a]); }
+        float cf[3]; double r2 = 0;
+        for (int a = 0; a < 3; ++a) cf[a] = (float)(0.5 * (lo[a] + hi[a]));
+        for (int k = 0; k < vcount[i]; ++k) {
+            double q = 0;
+            for (int a = 0; a < 3; ++a) { double dl = verts[12 * i + 3 * k + a] - (double)cf[a]; q += dl * dl; }
+            r2 = std::fmax(r2, q);
+        }
+        const double r = std::sqrt(r2) * (1.0 + 1e-5) + 1e-3;
+        float rf = (float)r;
+        while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
+        sph[i] = make_float4(cf[0], cf[1], cf[2], rf);
+    }
+    const int64_t ncells = (int64_t)ct[0] * ct[1] * ct[2];
+    std::vector<uint2> cells((size_t)ncells);
+    std::vector<uint32_t> occ((size_t)(ncells + 31) / 32 + 1, 0u);
+    for (int64_t i = 0; i < ncells; ++i) {
+        cells[i] = make_uint2(cell_offset[i], cell_offset[i + 1] - cell_offset[i]);
+        if (cells[i].y) occ[i >> 5] |= 1u << (i & 31);
+    }
+    VGrid g;
+    g.ominx = obox[0]; g.ominy = obox[1]; g.ominz = obox[2]; g.omaxx = obox[3]; g.omaxy = obox[4]; g.omaxz = obox[5];
+    g.vdx = (obox[3] - obox[0]) / ct[0]; g.vdy = (obox[4] - obox[1]) / ct[1]; g.vdz = (obox[5] - obox[2]) / ct[2];
+    g.nx = ct[0]; g.ny = ct[1]; g.nz = ct[2];
+    g.cells = cells.data(); g.cell_poly = cell_poly; g.occ = occ.data(); g.sph = sph.data();
+    WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
+    Stats st;
+#define RUN(S, W) if (slots == S && wmax == W) { if (chain) run<true, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, st, counters); \
+                                                 else run<false, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, st, counters); ok = 1; }
+    int ok = 0;
+    RUN(40, 4) RUN(48, 4) RUN(64, 4) RUN(96, 4) RUN(64, 2) RUN(64, 8) RUN(48, 8) RUN(48, 2) RUN(32, 4)
+#undef RUN
+    if (!ok) return -1;
+    if (stats) {
+        for (int k = 0; k < 4; ++k) { stats[k] = st.exec[k]; stats[4 + k] = st.lanes[k]; }
+        stats[8] = st.wsteps_warp; stats[9] = st.wsteps_lane; stats[10] = st.trips; stats[11] = st.whave_exec; stats[12] = st.whave_lane;
+    }
+    return 0;
+}

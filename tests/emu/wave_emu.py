@@ -1,0 +1,57 @@
+"""ctypes driver of tests/emu/libwave_emu.so: the CPU replay of vg_wave.cuh's wavefront scheduler (test infrastructure)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libwave_emu.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def run(topo_arrays, grid_info, csr, o, d, origin1=None, origin2=None, ray_id=None, chain=False, order=1, slots=64, wmax=4, n_warps=4):
+    """topo_arrays = oracle Topology.arrays(); grid_info = oracle Voxel_Grid.info(); csr = Voxel_Grid.csr()."""
+    verts, normals, vcount, _ = topo_arrays
+    obox, _, ct, _ = grid_info
+    off, pol = csr
+    verts = np.ascontiguousarray(verts, np.float64); normals = np.ascontiguousarray(normals, np.float64)
+    vcount = np.ascontiguousarray(vcount, np.int32); off = np.ascontiguousarray(off, np.uint32)
+    pol = np.ascontiguousarray(pol if len(pol) else np.zeros(1), np.uint32)
+    o = np.ascontiguousarray(o, np.float64).reshape(-1, 3); d = np.ascontiguousarray(d, np.float64).reshape(-1, 3)
+    N = o.shape[0]
+    o1 = None if origin1 is None else np.ascontiguousarray(origin1, np.int32)
+    o2 = None if origin2 is None else np.ascontiguousarray(origin2, np.int32)
+    rid = None if ray_id is None else np.ascontiguousarray(ray_id, np.int32)
+    stats = np.zeros(14); counters = np.zeros(4, np.uint64)
+    res = {}
+    if chain:
+        ev_pid = np.zeros((N, order), np.int32); ev_t = np.zeros((N, order)); fo = np.zeros((N, 3)); fd = np.zeros((N, 3))
+        ns = np.zeros(N, np.int32); tot = np.zeros(1, np.uint64)
+        args = [None] * 5 + [_p(ev_pid), _p(ev_t), _p(fo), _p(fd), _p(ns), _p(tot)]
+        res = dict(ev_poly_id=ev_pid, ev_t=ev_t, o=fo, d=fd, nshots=ns, total=tot)
+    else:
+        t = np.zeros(N); xyz = np.zeros((N, 3)); pid = np.zeros(N, np.int32); uv = np.ones((N, 2)); om = np.zeros((N, 3))
+        args = [_p(t), _p(xyz), _p(pid), _p(uv), _p(om)] + [None] * 6
+        res = dict(t=t, xyz=xyz, poly_id=pid, uv=uv, o=om)
+    rc = lib().wave_emu(_p(verts), _p(normals), _p(vcount), C.c_int64(len(vcount)), _p(np.ascontiguousarray(obox, np.float64)),
+                        _p(np.ascontiguousarray(ct, np.int32)), _p(off), _p(pol), _p(o), _p(d), _p(o1), _p(o2), _p(rid), C.c_int64(N),
+                        int(chain), int(order), *args, int(slots), int(wmax), int(n_warps), _p(stats), _p(counters))
+    if rc != 0:
+        raise ValueError("wave_emu: unsupported (slots, wmax)")
+    res["stats"] = dict(exec=dict(zip("SF W C T".split(), stats[0:4])), lanes=dict(zip("SF W C T".split(), stats[4:8])),
+                        wsteps_warp=stats[8], wsteps_lane=stats[9], trips=stats[10], whave_exec=stats[11], whave_lane=stats[12])
+    res["counters"] = counters
+    return res
