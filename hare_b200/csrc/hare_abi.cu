@@ -77,6 +77,7 @@ struct PartDev {
     const PolyRec* polys = nullptr;
     // voxel grid
     uint2* cells = nullptr; uint32_t* cell_poly = nullptr; uint32_t* occ = nullptr; uint32_t* cell_offset = nullptr;
+    float4* list_box = nullptr;   // per list entry: padded FP32 bounding box + polygon id (VGrid::lbox; vg_wave.cuh's cull)
     // trees
     void* nodes = nullptr; uint32_t* lists = nullptr; float4* csph = nullptr;   // csph: octree chunk spheres
     // staging (per stream), sized for `cap` rays
@@ -109,7 +110,7 @@ static void free_partdev(PartDev& d) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
@@ -300,6 +301,7 @@ static VGrid make_vgrid(const hare_part_s* p, const PartDev& d) {
     g.nx = p->ct[0]; g.ny = p->ct[1]; g.nz = p->ct[2];
     g.cells = d.cells; g.cell_poly = d.cell_poly; g.occ = d.occ;
     g.sph = reinterpret_cast<const float4*>(d.polys + p->topo->host.P);   // spheres follow the records
+    g.lbox = d.list_box;
     return g;
 }
 
@@ -321,6 +323,18 @@ static int vg_set_dims(hare_part_s* p, const double obox[6], const int32_t ct[3]
         p->ct[a] = ct[a];
         p->vd[a] = (obox[3 + a] - obox[a]) / ct[a];   // VoxelDims = BoxDims / VoxelCt  Voxel_Grid.cs:85-86
     }
+    return HARE_OK;
+}
+
+// HARE_VG_LBOX=0 leaves the per-entry boxes out (A/B measurements; 32 bytes per list entry); the cull then uses the spheres
+static bool use_lbox() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_LBOX"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
+
+static int vg_make_list_box(PartDev& d, uint32_t total, cudaStream_t st) {
+    if (!use_lbox() || total == 0) return HARE_OK;
+    CK(dmalloc(&d.list_box, 2 * (size_t)total));
+    vg_gather_list_box<<<(unsigned)(((int64_t)total + 255) / 256), 256, 0, st>>>(d.cell_poly, d.polys, total, d.list_box);
+    ++g_launches;
+    CK(cudaGetLastError());
     return HARE_OK;
 }
 
@@ -370,9 +384,11 @@ extern "C" int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* o
             vg_finish_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(d.cell_offset, count, ncells, d.cell_poly, d.cells, d.occ);
             g_launches += 2;
             CK(cudaGetLastError());
+            r = vg_make_list_box(d, total, st);
+            if (r) return r;
             CK(cudaStreamSynchronize(st));
             cudaFree(count); cudaFree(cursor); cudaFree(tiles);
-            d.bytes = (size_t)ncells * 12 + (size_t)total * 4 + (size_t)ncells / 8;
+            d.bytes = (size_t)ncells * 12 + (size_t)total * (d.list_box ? 36 : 4) + (size_t)ncells / 8;
             return HARE_OK;
         };
         rc = body();
@@ -439,8 +455,10 @@ extern "C" int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], con
             vg_pack_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(d.cell_offset, ncells, d.cells, d.occ);
             ++g_launches;
             CK(cudaGetLastError());
+            int r = vg_make_list_box(d, total, st);
+            if (r) return r;
             CK(cudaStreamSynchronize(st));
-            d.bytes = (size_t)ncells * 12 + (size_t)total * 4 + (size_t)ncells / 8;
+            d.bytes = (size_t)ncells * 12 + (size_t)total * (d.list_box ? 36 : 4) + (size_t)ncells / 8;
             return HARE_OK;
         };
         rc = body();
@@ -915,7 +933,7 @@ static int launch_vg_walk2(const VGrid& g, const PartDev& d, const double* o, co
 #define HARE_WAVE_SLOTS 64
 #endif
 #ifndef HARE_WAVE_WMAX
-#define HARE_WAVE_WMAX 4
+#define HARE_WAVE_WMAX 8
 #endif
 // HARE_VG_WAVE=0 selects the first-generation kernel (vg_walk.cuh) for A/B measurements
 static bool use_wave() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_WAVE"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
@@ -924,10 +942,10 @@ static bool use_wave() { static int v = -1; if (v < 0) { const char* e = getenv(
 // One CTA of HARE_WAVE_WARPS warps per SM; dynamic shared memory = occupancy bitmap (when it fits) + the pools.
 template <bool CHAIN, bool COUNT, bool OCC_SMEM>
 static int launch_vg_wave2(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
-                           const int32_t* rid, int64_t N, int order, const WalkOut& w, size_t smem, cudaStream_t st) {
+                           const int32_t* rid, int64_t N, int order, const WalkOut& w, int warps, size_t smem, cudaStream_t st) {
     auto k = vg_wave_kernel<CHAIN, COUNT, OCC_SMEM, HARE_WAVE_SLOTS, HARE_WAVE_WMAX>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = HARE_WAVE_WARPS * 32;
+    const int threads = warps * 32;
     int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms);
     k<<<(unsigned)blocks, threads, smem, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
     ++g_launches;
@@ -945,15 +963,21 @@ static bool wave_eligible(const VGrid& g, int64_t N, int order) {
 template <bool CHAIN>
 static int launch_vg_wave(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
                           const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
-    const size_t pools = (size_t)HARE_WAVE_WARPS * WavePool<HARE_WAVE_SLOTS>::STRIDE;
+    const size_t pool = WavePool<HARE_WAVE_SLOTS>::STRIDE;
     const size_t occ_bytes = ((((size_t)g.nx * g.ny * g.nz + 31) / 32 + 3) & ~(size_t)3) * 4;
-    const bool in_smem = occ_bytes + pools <= kSmemMax;
+    // the occupancy bitmap rides in shared memory next to the pools; a larger grid gives up warps for it (down to half),
+    // and beyond that the bitmap is read through L1
+    int warps = HARE_WAVE_WARPS;
+    while (warps > HARE_WAVE_WARPS / 2 && occ_bytes + warps * pool > kSmemMax) --warps;
+    const bool in_smem = occ_bytes + warps * pool <= kSmemMax;
+    if (!in_smem) warps = HARE_WAVE_WARPS;
+    const size_t smem = (in_smem ? occ_bytes : 0) + warps * pool;
     if (w.counters) {
-        if (in_smem) return launch_vg_wave2<CHAIN, true, true>(g, d, o, dd, o1, o2, rid, N, order, w, occ_bytes + pools, st);
-        return launch_vg_wave2<CHAIN, true, false>(g, d, o, dd, o1, o2, rid, N, order, w, pools, st);
+        if (in_smem) return launch_vg_wave2<CHAIN, true, true>(g, d, o, dd, o1, o2, rid, N, order, w, warps, smem, st);
+        return launch_vg_wave2<CHAIN, true, false>(g, d, o, dd, o1, o2, rid, N, order, w, warps, smem, st);
     }
-    if (in_smem) return launch_vg_wave2<CHAIN, false, true>(g, d, o, dd, o1, o2, rid, N, order, w, occ_bytes + pools, st);
-    return launch_vg_wave2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, w, pools, st);
+    if (in_smem) return launch_vg_wave2<CHAIN, false, true>(g, d, o, dd, o1, o2, rid, N, order, w, warps, smem, st);
+    return launch_vg_wave2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, w, warps, smem, st);
 }
 
 template <bool CHAIN>

@@ -345,6 +345,25 @@ oct_copy_lists(const uint32_t* __restrict__ src, const uint32_t* __restrict__ sr
     }
 }
 
+// per list entry (cell_poly order): the polygon's padded FP32 bounding box with its id riding in lo.w (VGrid::lbox, cull_box)
+__global__ void __launch_bounds__(256)
+vg_gather_list_box(const uint32_t* __restrict__ cell_poly, const PolyRec* __restrict__ polys, uint32_t total, float4* __restrict__ lbox) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const uint32_t i = cell_poly[k];
+    double P[16];
+    load_poly(polys, i, P);   // a triangle repeats vertex 2 in slot 3: min/max over the four slots is its box
+    float lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double l = fmin(fmin(P[a], P[3 + a]), fmin(P[6 + a], P[9 + a])), h = fmax(fmax(P[a], P[3 + a]), fmax(P[6 + a], P[9 + a]));
+        const double pad = hare_box_pad(l, h);
+        lo[a] = __double2float_rd(l - pad); hi[a] = __double2float_ru(h + pad);
+    }
+    lbox[2 * (size_t)k] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(i));
+    lbox[2 * (size_t)k + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+}
+
 // host-uploaded CSR -> packed headers + occupancy
 __global__ void __launch_bounds__(256)
 vg_pack_cells(const uint32_t* __restrict__ cell_offset, long long ncells, uint2* __restrict__ cells, uint32_t* __restrict__ occ) {

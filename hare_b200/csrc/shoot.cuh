@@ -8,6 +8,7 @@
 // operation order and compiled with -fmad=false.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include "hare_math.cuh"
 
 namespace hare {
@@ -62,6 +63,41 @@ HD bool cull_sphere(const float4 s, float px, float py, float pz, float dx, floa
     return fmaf(-vd, vd, vv * dd) > fmaf(4e-6f, vv, s.w * s.w) * dd;   // |v x d|^2 > (r^2 + margin) |d|^2   (NaN -> keep)
 }
 
+// Second conservative reject: true only when the ray's supporting line misses the polygon's padded axis-aligned
+// bounding box (slab test).  For the wall / floor / seat rectangles of a hall the box is flat, so this is far
+// tighter than the sphere.  lo/hi are the FP32 box corners, padded by 1e-3 m + 1e-5 of the extent + 4e-7 |coordinate|
+// and rounded outwards (hare_box_pad); p, d as in cull_sphere (FP32 ray point near the voxel, FP32 direction).  A ray that hits the polygon at
+// q has q at least 1e-3 m inside the padded box on every axis, i.e. its parameter lies >= 1e-3/|d_a| inside each
+// slab interval, while the FP32 evaluation of the interval ends is good to ~2e-7 |coordinate| / |d_a|: the
+// intervals computed here all contain it, so it is never rejected.  A zero direction component is replaced by
+// 1e-30 (the slab then spans (-huge, +huge) when p is inside it and is empty when p is outside).  NaN -> keep.
+HD double hare_box_pad(double l, double h) { return 1e-3 + 1e-5 * (h - l) + 4e-7 * fmax(fabs(l), fabs(h)); }
+
+HD bool cull_box(const float4 lo, const float4 hi, float px, float py, float pz, float ix, float iy, float iz) {   // ix = 1/dx ...
+    const float ax = (lo.x - px) * ix, bx = (hi.x - px) * ix;
+    const float ay = (lo.y - py) * iy, by = (hi.y - py) * iy;
+    const float az = (lo.z - pz) * iz, bz = (hi.z - pz) * iz;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    return tn > tf;
+}
+
+// bit casts between a polygon id and the float lane it rides in (VGrid::lbox)
+HD uint32_t hare_f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+HD float hare_u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // Voxel_Grid
 // ---------------------------------------------------------------------------------------
@@ -73,6 +109,7 @@ struct VGrid {
     const uint32_t* __restrict__ cell_poly; // ascending polygon indices per cell
     const uint32_t* __restrict__ occ;       // 1 bit per cell: list non-empty
     const float4* __restrict__ sph;         // per polygon: padded bounding sphere (cx, cy, cz, r), see cull_sphere()
+    const float4* __restrict__ lbox;        // per LIST ENTRY (cell_poly order): padded FP32 bounding box (lo.xyz, polygon id in lo.w; hi.xyz), or null -- cull_box()
 };
 
 #define HARE_EPS 0.001   /* Voxel_Grid.Epsilon, Voxel_Grid.cs:39 */

@@ -42,25 +42,34 @@ enum : uint32_t { FIN_RUN = 0, FIN_HIT = 1, FIN_MISS = 2, FIN_FAULT = 3 };
 
 // field indices of the structure-of-arrays pool
 enum { D_OX, D_OY, D_OZ, D_DX, D_DY, D_DZ, D_TMX, D_TMY, D_TMZ, D_TDX, D_TDY, D_TDZ, D_TMIN, D_TSTART, D_COUNT };
+// HARE_WAVE_BIDS = 1 keeps the ids of a culled batch's survivors in the slot (16 bytes); 0 re-reads them from the
+// cell list in T (the list position stays on the batch until its survivors are consumed)
+#ifndef HARE_WAVE_BRANCHY_STEP
+#define HARE_WAVE_BRANCHY_STEP 0
+#endif
+#ifndef HARE_WAVE_BIDS
+#define HARE_WAVE_BIDS 0
+#endif
+#if HARE_WAVE_BIDS
 enum { U_XYZ, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_BID0, U_BID1, U_BID2, U_BID3, U_COUNT };
-enum { F_PX, F_PY, F_PZ, F_COUNT };
+#else
+enum { U_XYZ, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_COUNT };
+#endif
 
 template <int SLOTS>
 struct WavePool {
-    double* dbl; uint32_t* u32; float* f32; uint8_t* tag; uint8_t* sel;
+    double* dbl; uint32_t* u32; uint8_t* tag; uint8_t* sel;
     static_assert(SLOTS <= 255, "phase counts are packed into bytes");
-    static constexpr size_t BYTES = (size_t)SLOTS * (D_COUNT * 8 + U_COUNT * 4 + F_COUNT * 4 + 1) + 32;
+    static constexpr size_t BYTES = (size_t)SLOTS * (D_COUNT * 8 + U_COUNT * 4 + 1) + 32;
     static constexpr size_t STRIDE = (BYTES + 15) & ~(size_t)15;
     HD void bind(unsigned char* base) {
         dbl = reinterpret_cast<double*>(base);
         u32 = reinterpret_cast<uint32_t*>(base + (size_t)SLOTS * D_COUNT * 8);
-        f32 = reinterpret_cast<float*>(base + (size_t)SLOTS * (D_COUNT * 8 + U_COUNT * 4));
-        tag = base + (size_t)SLOTS * (D_COUNT * 8 + U_COUNT * 4 + F_COUNT * 4);
+        tag = base + (size_t)SLOTS * (D_COUNT * 8 + U_COUNT * 4);
         sel = tag + SLOTS;
     }
     HD double& D(int f, int s) const { return dbl[f * SLOTS + s]; }
     HD uint32_t& U(int f, int s) const { return u32[f * SLOTS + s]; }
-    HD float& F(int f, int s) const { return f32[f * SLOTS + s]; }
 };
 
 // which phase a slot waits for, from its state
@@ -79,18 +88,12 @@ HD int wave_pick(const int n[PH_COUNT]) {
     return bn > 0 ? best : -1;
 }
 
-// list range of voxel ci and the FP32 ray point used by the cull; empty voxels never touch the cell table
+// is voxel ci occupied (for this ray)?  One bit per voxel, staged in shared memory when it fits.
 template <bool COUNT>
-HD void wave_enter_cell(const VGrid& g, const uint32_t* occ, bool occ_smem, bool blind, uint32_t ci, const Ray3& R, double t_in,
-                        uint32_t& lpos, uint32_t& lend, float& fpx, float& fpy, float& fpz, CntT<COUNT>& c) {
+HD bool wave_occupied(const uint32_t* occ, bool occ_smem, bool blind, uint32_t ci, CntT<COUNT>& c) {
     c.cell();
-    lpos = 0; lend = 0;
     const uint32_t word = occ_smem ? occ[ci >> 5] : hare_ldg(occ + (ci >> 5));
-    if (!blind && ((word >> (ci & 31)) & 1u)) {
-        const uint2 h = hare_ldg(g.cells + ci);
-        lpos = h.x; lend = h.x + h.y;
-        fpx = (float)fma(R.dx, t_in, R.x); fpy = (float)fma(R.dy, t_in, R.y); fpz = (float)fma(R.dz, t_in, R.z);
-    }
+    return !blind && ((word >> (ci & 31)) & 1u);
 }
 
 // ---- SF, part 1: the Shoot in slot s is over -> write its event; a chain reflects and goes on, or ends.
@@ -197,9 +200,7 @@ HD uint32_t wave_setup(const VGrid& g, const uint32_t* occ, bool occ_smem, const
         p.D(D_TDZ, s) = g.vdz / R.dz * (nz_ ? -1.0 : 1.0);
         p.U(U_XYZ, s) = (uint32_t)X | ((uint32_t)Y << 10) | ((uint32_t)Z << 20);
         const uint32_t ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
-        float fpx = 0, fpy = 0, fpz = 0;
-        wave_enter_cell<COUNT>(g, occ, occ_smem, (fl & WF_BLIND) != 0, ci, R, 0.0, lpos, lend, fpx, fpy, fpz, c);
-        if (lpos < lend) { p.F(F_PX, s) = fpx; p.F(F_PY, s) = fpy; p.F(F_PZ, s) = fpz; }
+        if (wave_occupied<COUNT>(occ, occ_smem, (fl & WF_BLIND) != 0, ci, c)) { const uint2 h = hare_ldg(g.cells + ci); lpos = h.x; lend = h.x + h.y; }
     }
     fl |= fin << WF_FIN_SHIFT;
     p.U(U_FLAGS, s) = fl; p.U(U_LPOS, s) = lpos; p.U(U_LEND, s) = lend;
@@ -216,13 +217,13 @@ HD uint32_t wave_walk(const VGrid& g, const uint32_t* occ, bool occ_smem, const 
     const uint32_t xyz = p.U(U_XYZ, s);
     int X = (int)(xyz & 1023u), Y = (int)((xyz >> 10) & 1023u), Z = (int)(xyz >> 20);
     const int stepX = (fl & WF_NEGX) ? -1 : 1, stepY = (fl & WF_NEGY) ? -1 : 1, stepZ = (fl & WF_NEGZ) ? -1 : 1;
-    const int strideX = g.ny * g.nz, strideY = g.nz;
+    const int sX = stepX * g.ny * g.nz, sY = stepY * g.nz;
     uint32_t ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
     const bool have = (fl & WF_HAVE) != 0, blind = (fl & WF_BLIND) != 0;
     double bx = 0, by = 0, bz = 0;
     if (have) { const double tmin = p.D(D_TMIN, s); bx = R.x + R.dx * tmin; by = R.y + R.dy * tmin; bz = R.z + R.dz * tmin; }
     uint32_t fin = FIN_RUN, lpos = 0, lend = 0;
-    float fpx = 0, fpy = 0, fpz = 0;
+    bool found = false;
 #pragma unroll 1
     for (int guard = 0; guard < W_MAX; ++guard) {
         // list exhausted: Voxels[X,Y,Z].IsPointInBox(candidate)?   Voxel_Grid.cs:496-500
@@ -232,24 +233,34 @@ HD uint32_t wave_walk(const VGrid& g, const uint32_t* occ, bool occ_smem, const 
             if (in) { fin = FIN_HIT; break; }
         }
         // next voxel   Voxel_Grid.cs:504-550: X only if strictly below both, Y only if below Z, else Z
-        const bool xy = tMaxX < tMaxY, xz = tMaxX < tMaxZ, yz = tMaxY < tMaxZ;
-        const bool goX = xy & xz, goY = (!xy) & yz;
-        const bool goZ = !(goX | goY);
-        const double t_in = goX ? tMaxX : (goY ? tMaxY : tMaxZ);
-        const double nX = tMaxX + tDeltaX, nY = tMaxY + tDeltaY, nZ = tMaxZ + tDeltaZ;
-        tMaxX = goX ? nX : tMaxX; tMaxY = goY ? nY : tMaxY; tMaxZ = goZ ? nZ : tMaxZ;
-        X += goX ? stepX : 0; Y += goY ? stepY : 0; Z += goZ ? stepZ : 0;
-        ci += (uint32_t)(goX ? stepX * strideX : (goY ? stepY * strideY : stepZ));
-        if ((unsigned)X >= (unsigned)g.nx || (unsigned)Y >= (unsigned)g.ny || (unsigned)Z >= (unsigned)g.nz) { fin = FIN_MISS; break; }
-        wave_enter_cell<COUNT>(g, occ, occ_smem, blind, ci, R, t_in, lpos, lend, fpx, fpy, fpz, c);
-        if (lpos < lend) break;
+        bool oob;
+#if HARE_WAVE_BRANCHY_STEP
+        if (tMaxX < tMaxY && tMaxX < tMaxZ) { tMaxX = tMaxX + tDeltaX; X += stepX; ci += (uint32_t)sX; oob = (unsigned)X >= (unsigned)g.nx; }
+        else if (!(tMaxX < tMaxY) && tMaxY < tMaxZ) { tMaxY = tMaxY + tDeltaY; Y += stepY; ci += (uint32_t)sY; oob = (unsigned)Y >= (unsigned)g.ny; }
+        else { tMaxZ = tMaxZ + tDeltaZ; Z += stepZ; ci += (uint32_t)stepZ; oob = (unsigned)Z >= (unsigned)g.nz; }
+#else
+        {
+            const bool xy = tMaxX < tMaxY, xz = tMaxX < tMaxZ, yz = tMaxY < tMaxZ;
+            const bool goX = xy & xz, goY = (!xy) & yz;
+            const bool goZ = !(goX | goY);
+            const double nX = tMaxX + tDeltaX, nY = tMaxY + tDeltaY, nZ = tMaxZ + tDeltaZ;
+            tMaxX = goX ? nX : tMaxX; tMaxY = goY ? nY : tMaxY; tMaxZ = goZ ? nZ : tMaxZ;
+            X += goX ? stepX : 0; Y += goY ? stepY : 0; Z += goZ ? stepZ : 0;
+            ci += (uint32_t)(goX ? sX : (goY ? sY : stepZ));
+            oob = (unsigned)X >= (unsigned)g.nx || (unsigned)Y >= (unsigned)g.ny || (unsigned)Z >= (unsigned)g.nz;
+        }
+#endif
+        if (oob) { fin = FIN_MISS; break; }
+        // an occupied voxel ends the walk; its list header is fetched once, after the loop (no L2 round trip per step)
+        found = wave_occupied<COUNT>(occ, occ_smem, blind, ci, c);
+        if (found) break;
     }
+    if (found) { const uint2 h = hare_ldg(g.cells + ci); lpos = h.x; lend = h.x + h.y; }
     fl |= fin << WF_FIN_SHIFT;
     if (fin == FIN_RUN) {
         p.D(D_TMX, s) = tMaxX; p.D(D_TMY, s) = tMaxY; p.D(D_TMZ, s) = tMaxZ;
         p.U(U_XYZ, s) = (uint32_t)X | ((uint32_t)Y << 10) | ((uint32_t)Z << 20);
         p.U(U_LPOS, s) = lpos; p.U(U_LEND, s) = lend;
-        if (lpos < lend) { p.F(F_PX, s) = fpx; p.F(F_PY, s) = fpy; p.F(F_PZ, s) = fpz; }
     } else {
         p.U(U_FLAGS, s) = fl;
     }
@@ -262,41 +273,75 @@ HD uint32_t wave_cull(const VGrid& g, const WavePool<SLOTS>& p, int s, CntT<COUN
     uint32_t lpos = p.U(U_LPOS, s);
     const uint32_t lend = p.U(U_LEND, s);
     const uint32_t n = (lend - lpos) < 4u ? (lend - lpos) : 4u;
-    const uint32_t bid0 = hare_ldg(g.cell_poly + lpos);
-    const uint32_t bid1 = (n > 1) ? hare_ldg(g.cell_poly + lpos + 1) : bid0;
-    const uint32_t bid2 = (n > 2) ? hare_ldg(g.cell_poly + lpos + 2) : bid0;
-    const uint32_t bid3 = (n > 3) ? hare_ldg(g.cell_poly + lpos + 3) : bid0;
-    const float4 s0 = hare_ldg(g.sph + bid0), s1 = hare_ldg(g.sph + bid1), s2 = hare_ldg(g.sph + bid2), s3 = hare_ldg(g.sph + bid3);
-    lpos += n;
     if (COUNT) c.entries += n;
-    const float fdx = (float)p.D(D_DX, s), fdy = (float)p.D(D_DY, s), fdz = (float)p.D(D_DZ, s);
-    const float fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
-    const float fpx = p.F(F_PX, s), fpy = p.F(F_PY, s), fpz = p.F(F_PZ, s);
+    // the culls work in FP32 in a frame local to the voxel: their ray point is where the ray LEAVES the current voxel,
+    // min(tMax) -- like the entry point vg_walk.cuh uses, at most a voxel diagonal from anything listed here
+    const double dx = p.D(D_DX, s), dy = p.D(D_DY, s), dz = p.D(D_DZ, s);
+    const double te = fmin(fmin(p.D(D_TMX, s), p.D(D_TMY, s)), p.D(D_TMZ, s));
+    const float fpx = (float)fma(dx, te, p.D(D_OX, s)), fpy = (float)fma(dy, te, p.D(D_OY, s)), fpz = (float)fma(dz, te, p.D(D_OZ, s));
+    const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz;
     const int or1 = (int)p.U(U_OR1, s), or2 = (int)p.U(U_OR2, s), pid = (int)p.U(U_PID, s);
     const uint32_t last = p.U(U_LAST, s);
     // poly_origin skip (Voxel_Grid.cs:477); a polygon already tested for this ray cannot change the result
-    auto keep = [&](uint32_t i, const float4& sp) {
-        return !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) && !cull_sphere(sp, fpx, fpy, fpz, fdx, fdy, fdz, fdd);
-    };
-    const uint32_t bmask = (keep(bid0, s0) ? 1u : 0u) | ((n > 1 && keep(bid1, s1)) ? 2u : 0u) |
-                           ((n > 2 && keep(bid2, s2)) ? 4u : 0u) | ((n > 3 && keep(bid3, s3)) ? 8u : 0u);
+    auto fresh = [&](uint32_t i) { return !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid); };
+    uint32_t bid0, bid1, bid2, bid3, bmask;
+    if (g.lbox) {
+        // list entries carry their polygon's padded bounding box and its id: one contiguous 32 bytes per entry
+        const float4* e = g.lbox + 2 * (size_t)lpos;
+        const float4 l0 = hare_ldg(e), h0 = hare_ldg(e + 1);
+        const float4 l1 = (n > 1) ? hare_ldg(e + 2) : l0, h1 = (n > 1) ? hare_ldg(e + 3) : h0;
+        const float4 l2 = (n > 2) ? hare_ldg(e + 4) : l0, h2 = (n > 2) ? hare_ldg(e + 5) : h0;
+        const float4 l3 = (n > 3) ? hare_ldg(e + 6) : l0, h3 = (n > 3) ? hare_ldg(e + 7) : h0;
+        bid0 = hare_f2u(l0.w); bid1 = hare_f2u(l1.w); bid2 = hare_f2u(l2.w); bid3 = hare_f2u(l3.w);
+        const float ix = 1.0f / (fdx == 0.0f ? 1e-30f : fdx), iy = 1.0f / (fdy == 0.0f ? 1e-30f : fdy), iz = 1.0f / (fdz == 0.0f ? 1e-30f : fdz);
+        bmask = ((fresh(bid0) && !cull_box(l0, h0, fpx, fpy, fpz, ix, iy, iz)) ? 1u : 0u) |
+                ((n > 1 && fresh(bid1) && !cull_box(l1, h1, fpx, fpy, fpz, ix, iy, iz)) ? 2u : 0u) |
+                ((n > 2 && fresh(bid2) && !cull_box(l2, h2, fpx, fpy, fpz, ix, iy, iz)) ? 4u : 0u) |
+                ((n > 3 && fresh(bid3) && !cull_box(l3, h3, fpx, fpy, fpz, ix, iy, iz)) ? 8u : 0u);
+    } else {
+        bid0 = hare_ldg(g.cell_poly + lpos);
+        bid1 = (n > 1) ? hare_ldg(g.cell_poly + lpos + 1) : bid0;
+        bid2 = (n > 2) ? hare_ldg(g.cell_poly + lpos + 2) : bid0;
+        bid3 = (n > 3) ? hare_ldg(g.cell_poly + lpos + 3) : bid0;
+        const float4 s0 = hare_ldg(g.sph + bid0), s1 = hare_ldg(g.sph + bid1), s2 = hare_ldg(g.sph + bid2), s3 = hare_ldg(g.sph + bid3);
+        const float fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
+        bmask = ((fresh(bid0) && !cull_sphere(s0, fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? 1u : 0u) |
+                ((n > 1 && fresh(bid1) && !cull_sphere(s1, fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? 2u : 0u) |
+                ((n > 2 && fresh(bid2) && !cull_sphere(s2, fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? 4u : 0u) |
+                ((n > 3 && fresh(bid3) && !cull_sphere(s3, fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? 8u : 0u);
+    }
+#if HARE_WAVE_BIDS
+    lpos += n;
     p.U(U_LPOS, s) = lpos;
     if (bmask) {
         p.U(U_BID0, s) = bid0; p.U(U_BID1, s) = bid1; p.U(U_BID2, s) = bid2; p.U(U_BID3, s) = bid3;
         p.U(U_FLAGS, s) |= bmask << WF_BMASK_SHIFT;
         return PH_T;
     }
+#else
+    if (bmask) { p.U(U_FLAGS, s) |= bmask << WF_BMASK_SHIFT; return PH_T; }   // lpos stays on the batch until T has consumed it
+    lpos += n;
+    p.U(U_LPOS, s) = lpos;
+#endif
     return lpos < lend ? PH_C : PH_W;
 }
 
 // ---- T: one exact FP64 test of the lowest surviving entry
 template <bool COUNT, int SLOTS>
-HD uint32_t wave_test(const PolyRec* __restrict__ polys, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
+HD uint32_t wave_test(const VGrid& g, const PolyRec* __restrict__ polys, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
     uint32_t fl = p.U(U_FLAGS, s);
     const uint32_t bmask = (fl & WF_BMASK_MASK) >> WF_BMASK_SHIFT;
     const int k = (bmask & 1u) ? 0 : ((bmask & 2u) ? 1 : ((bmask & 4u) ? 2 : 3));   // lowest survivor first
+    uint32_t lpos = p.U(U_LPOS, s);
+    const uint32_t lend = p.U(U_LEND, s);
+#if HARE_WAVE_BIDS
     const uint32_t pend = p.U(U_BID0 + k, s);
     fl &= ~((1u << k) << WF_BMASK_SHIFT);
+#else
+    const uint32_t pend = hare_ldg(g.cell_poly + lpos + k);
+    fl &= ~((1u << k) << WF_BMASK_SHIFT);
+    if (!(fl & WF_BMASK_MASK)) { lpos += (lend - lpos) < 4u ? (lend - lpos) : 4u; p.U(U_LPOS, s) = lpos; }
+#endif
     c.test();
     const Ray3 R = { p.D(D_OX, s), p.D(D_OY, s), p.D(D_OZ, s), p.D(D_DX, s), p.D(D_DY, s), p.D(D_DZ, s) };
     double P[16], t = 0;
@@ -311,7 +356,7 @@ HD uint32_t wave_test(const PolyRec* __restrict__ polys, const WavePool<SLOTS>& 
     p.U(U_LAST, s) = pend;
     if (hit && t > 0.0000000001 && t < p.D(D_TMIN, s)) { p.D(D_TMIN, s) = t; p.U(U_PID, s) = pend; fl |= WF_HAVE; }
     p.U(U_FLAGS, s) = fl;
-    return wave_tag(fl, p.U(U_LPOS, s), p.U(U_LEND, s));
+    return wave_tag(fl, lpos, lend);
 }
 
 // number of the c-th ray consumed by warp gw out of tw warps: warps take rays in interleaved groups of 32
@@ -320,7 +365,7 @@ HD long long wave_ray_number(long long c, long long gw, long long tw) { return (
 #if defined(__CUDACC__)
 
 #ifndef HARE_WAVE_WARPS
-#define HARE_WAVE_WARPS 16
+#define HARE_WAVE_WARPS 20
 #endif
 
 template <bool CHAIN, bool COUNT, bool OCC_SMEM, int SLOTS, int W_MAX>
@@ -385,7 +430,7 @@ vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
         // 4. run it
         uint32_t nt = PH_DONE;
         if (ph == PH_T) {
-            if (act) nt = wave_test<COUNT, SLOTS>(polys, p, s, c);
+            if (act) nt = wave_test<COUNT, SLOTS>(g, polys, p, s, c);
         } else if (ph == PH_C) {
             if (act) nt = wave_cull<COUNT, SLOTS>(g, p, s, c);
         } else if (ph == PH_W) {

@@ -41,7 +41,7 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
             st.exec[ph] += 1; st.lanes[ph] += cnt; st.trips += 1;
             uint32_t nt[32];
             if (ph == PH_T) {
-                for (int l = 0; l < cnt; ++l) nt[l] = wave_test<true, SLOTS>(polys, p, sel[l], c);
+                for (int l = 0; l < cnt; ++l) nt[l] = wave_test<true, SLOTS>(g, polys, p, sel[l], c);
             } else if (ph == PH_C) {
                 for (int l = 0; l < cnt; ++l) nt[l] = wave_cull<true, SLOTS>(g, p, sel[l], c);
             } else if (ph == PH_W) {
@@ -89,7 +89,7 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
                         int chain, int order,
                         double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
                         int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
-                        int slots, int wmax, int n_warps, double* stats, unsigned long long* counters) {
+                        int slots, int wmax, int n_warps, int list_boxes, double* stats, unsigned long long* counters) {
     std::vector<PolyRec> recs((size_t)P);
     std::vector<float4> sph((size_t)P);
     for (int64_t i = 0; i < P; ++i) {
@@ -126,6 +126,21 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
     g.vdx = (obox[3] - obox[0]) / ct[0]; g.vdy = (obox[4] - obox[1]) / ct[1]; g.vdz = (obox[5] - obox[2]) / ct[2];
     g.nx = ct[0]; g.ny = ct[1]; g.nz = ct[2];
     g.cells = cells.data(); g.cell_poly = cell_poly; g.occ = occ.data(); g.sph = sph.data();
+    // per-entry padded boxes with the id in lo.w, as vg_gather_list_box makes them
+    std::vector<float4> lbox(2 * (size_t)cell_offset[ncells] + 2);
+    for (uint32_t k = 0; k < cell_offset[ncells]; ++k) {
+        const int64_t i = cell_poly[k];
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            double l = verts[12 * i + a], h = l;
+            for (int q = 1; q < vcount[i]; ++q) { l = std::fmin(l, verts[12 * i + 3 * q + a]); h = std::fmax(h, verts[12 * i + 3 * q + a]); }
+            const double pad = hare_box_pad(l, h);
+            lo[a] = (float)(l - pad); while ((double)lo[a] > l - pad) lo[a] = std::nextafter(lo[a], -INFINITY);
+            hi[a] = (float)(h + pad); while ((double)hi[a] < h + pad) hi[a] = std::nextafter(hi[a], INFINITY);
+        }
+        lbox[2 * k] = make_float4(lo[0], lo[1], lo[2], hare_u2f((uint32_t)i)); lbox[2 * k + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    g.lbox = list_boxes ? lbox.data() : nullptr;
     WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
     Stats st;
 #define RUN(S, W) if (slots == S && wmax == W) { if (chain) run<true, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, st, counters); \
