@@ -68,18 +68,28 @@ HD bool cull_sphere(const float4 s, float px, float py, float pz, float dx, floa
 // tighter than the sphere.  lo/hi are the FP32 box corners, padded by 1e-3 m + 1e-5 of the extent + 4e-7 |coordinate|
 // and rounded outwards (hare_box_pad); p, d as in cull_sphere (FP32 ray point near the voxel, FP32 direction).  A ray that hits the polygon at
 // q has q at least 1e-3 m inside the padded box on every axis, i.e. its parameter lies >= 1e-3/|d_a| inside each
-// slab interval, while the FP32 evaluation of the interval ends is good to ~2e-7 |coordinate| / |d_a|: the
+// slab interval, while the FP32 evaluation of the interval ends (lo/d - p/d, one FMA) is good to ~2e-7 |coordinate| / |d_a|: the
 // intervals computed here all contain it, so it is never rejected.  A zero direction component is replaced by
-// 1e-30 (the slab then spans (-huge, +huge) when p is inside it and is empty when p is outside).  NaN -> keep.
+// 1e-30 (cull_rcp; the slab then spans (-huge, +huge) when p is inside it and is empty when p is outside).  NaN -> keep.
 HD double hare_box_pad(double l, double h) { return 1e-3 + 1e-5 * (h - l) + 4e-7 * fmax(fabs(l), fabs(h)); }
 
-HD bool cull_box(const float4 lo, const float4 hi, float px, float py, float pz, float ix, float iy, float iz) {   // ix = 1/dx ...
-    const float ax = (lo.x - px) * ix, bx = (hi.x - px) * ix;
-    const float ay = (lo.y - py) * iy, by = (hi.y - py) * iy;
-    const float az = (lo.z - pz) * iz, bz = (hi.z - pz) * iz;
+HD bool cull_box(const float4 lo, const float4 hi, float pxi, float pyi, float pzi, float ix, float iy, float iz) {   // ix = 1/dx, pxi = px/dx ...
+    const float ax = fmaf(lo.x, ix, -pxi), bx = fmaf(hi.x, ix, -pxi);
+    const float ay = fmaf(lo.y, iy, -pyi), by = fmaf(hi.y, iy, -pyi);
+    const float az = fmaf(lo.z, iz, -pzi), bz = fmaf(hi.z, iz, -pzi);
     const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
     const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
     return tn > tf;
+}
+
+// 1/x for the culls: one MUFU.RCP (1 ulp) instead of the IEEE division sequence; a zero or denormal x becomes 1e-30
+HD float cull_rcp(float x) {
+    x = fabsf(x) < 1e-30f ? 1e-30f : x;
+#if defined(__CUDA_ARCH__)
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return 1.0f / x;
+#endif
 }
 
 // bit casts between a polygon id and the float lane it rides in (VGrid::lbox)

@@ -293,11 +293,12 @@ HD uint32_t wave_cull(const VGrid& g, const WavePool<SLOTS>& p, int s, CntT<COUN
         const float4 l2 = (n > 2) ? hare_ldg(e + 4) : l0, h2 = (n > 2) ? hare_ldg(e + 5) : h0;
         const float4 l3 = (n > 3) ? hare_ldg(e + 6) : l0, h3 = (n > 3) ? hare_ldg(e + 7) : h0;
         bid0 = hare_f2u(l0.w); bid1 = hare_f2u(l1.w); bid2 = hare_f2u(l2.w); bid3 = hare_f2u(l3.w);
-        const float ix = 1.0f / (fdx == 0.0f ? 1e-30f : fdx), iy = 1.0f / (fdy == 0.0f ? 1e-30f : fdy), iz = 1.0f / (fdz == 0.0f ? 1e-30f : fdz);
-        bmask = ((fresh(bid0) && !cull_box(l0, h0, fpx, fpy, fpz, ix, iy, iz)) ? 1u : 0u) |
-                ((n > 1 && fresh(bid1) && !cull_box(l1, h1, fpx, fpy, fpz, ix, iy, iz)) ? 2u : 0u) |
-                ((n > 2 && fresh(bid2) && !cull_box(l2, h2, fpx, fpy, fpz, ix, iy, iz)) ? 4u : 0u) |
-                ((n > 3 && fresh(bid3) && !cull_box(l3, h3, fpx, fpy, fpz, ix, iy, iz)) ? 8u : 0u);
+        const float ix = cull_rcp(fdx), iy = cull_rcp(fdy), iz = cull_rcp(fdz);
+        const float pxi = fpx * ix, pyi = fpy * iy, pzi = fpz * iz;
+        bmask = ((fresh(bid0) && !cull_box(l0, h0, pxi, pyi, pzi, ix, iy, iz)) ? 1u : 0u) |
+                ((n > 1 && fresh(bid1) && !cull_box(l1, h1, pxi, pyi, pzi, ix, iy, iz)) ? 2u : 0u) |
+                ((n > 2 && fresh(bid2) && !cull_box(l2, h2, pxi, pyi, pzi, ix, iy, iz)) ? 4u : 0u) |
+                ((n > 3 && fresh(bid3) && !cull_box(l3, h3, pxi, pyi, pzi, ix, iy, iz)) ? 8u : 0u);
     } else {
         bid0 = hare_ldg(g.cell_poly + lpos);
         bid1 = (n > 1) ? hare_ldg(g.cell_poly + lpos + 1) : bid0;
