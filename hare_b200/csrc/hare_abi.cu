@@ -69,6 +69,7 @@ struct hare_topo_s {
     std::vector<int> devs;
     std::vector<PolyRec*> d_polys;   // one replica per device
     std::vector<float> sph;          // host copy of the padded bounding spheres (P x 4)
+    std::vector<float> pbox;         // host copy of the padded FP32 bounding boxes (P x 6: lo xyz, hi xyz), see cull_box()
 };
 
 struct PartDev {
@@ -80,6 +81,7 @@ struct PartDev {
     float4* list_box = nullptr;   // per list entry: padded FP32 bounding box + polygon id (VGrid::lbox; vg_wave.cuh's cull)
     // trees
     void* nodes = nullptr; uint32_t* lists = nullptr; float4* csph = nullptr;   // csph: octree chunk spheres
+    float4* cbox = nullptr; float4* tbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id)
     // staging (per stream), sized for `cap` rays
     int64_t cap = 0;
     double *s_o[2] = {}, *s_d[2] = {}, *s_t[2] = {}, *s_xyz[2] = {}, *s_uv[2] = {}, *s_om[2] = {};
@@ -110,7 +112,7 @@ static void free_partdev(PartDev& d) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.tbox); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
@@ -252,6 +254,18 @@ extern "C" int hare_topology_create(const double* verts, const double* normals, 
         sph[4 * i] = cf[0]; sph[4 * i + 1] = cf[1]; sph[4 * i + 2] = cf[2]; sph[4 * i + 3] = rf;
     }
     t->sph = sph;
+    // padded FP32 bounding boxes (second conservative reject, cull_box): exact box -/+ hare_box_pad, rounded outwards
+    t->pbox.resize((size_t)P * 6);
+    for (int64_t i = 0; i < P; ++i)
+        for (int a = 0; a < 3; ++a) {
+            double l = verts[12 * i + a], h = l;
+            for (int k = 1; k < vcount[i]; ++k) { l = std::min(l, verts[12 * i + 3 * k + a]); h = std::max(h, verts[12 * i + 3 * k + a]); }
+            const double pad = hare_box_pad(l, h);
+            float lo = (float)(l - pad), hi = (float)(h + pad);
+            while ((double)lo > l - pad) lo = std::nextafter(lo, -INFINITY);
+            while ((double)hi < h + pad) hi = std::nextafter(hi, INFINITY);
+            t->pbox[6 * i + a] = lo; t->pbox[6 * i + 3 + a] = hi;
+        }
     { std::lock_guard<std::mutex> lk(g_mu); t->devs = g_devices; }
     for (int dev : t->devs) {
         PolyRec* d = nullptr;
@@ -502,6 +516,18 @@ static int oct_depth(const OctTree& t) {
     return best;
 }
 
+// per tree-list entry: the polygon's padded FP32 box with its id riding in lo.w (8 floats per entry)
+static std::vector<float> tree_entry_boxes(const std::vector<float>& pbox, const std::vector<uint32_t>& polys) {
+    std::vector<float> out(polys.size() * 8);
+    for (size_t k = 0; k < polys.size(); ++k) {
+        const float* q = &pbox[6 * (size_t)polys[k]];
+        float* r = &out[8 * k];
+        r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; std::memcpy(&r[3], &polys[k], 4);
+        r[4] = q[3]; r[5] = q[4]; r[6] = q[5]; r[7] = 0.f;
+    }
+    return out;
+}
+
 static int oct_to_device(hare_part_s* p) {
     const OctTree& t = p->oct;
     const size_t N = t.first_child.size();
@@ -552,6 +578,21 @@ static int oct_to_device(hare_part_s* p) {
             }
         }
     }
+    // The same runs' boxes (union of the members' padded boxes), and one (box, polygon id) record per list entry.
+    std::vector<float> cbox, lbox = tree_entry_boxes(p->topo->pbox, t.polys);
+    for (size_t i = 0; i < N; ++i) {
+        if (t.first_child[i] >= 0) continue;
+        for (uint32_t b = 0; b < t.list_cnt[i]; b += HARE_OCT_CHUNK) {
+            const uint32_t e = std::min<uint32_t>(b + HARE_OCT_CHUNK, t.list_cnt[i]);
+            float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+            for (uint32_t k = b; k < e; ++k) {
+                const float* q = &p->topo->pbox[6 * (size_t)t.polys[t.list_off[i] + k]];
+                for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], q[a2]); hi[a2] = std::max(hi[a2], q[3 + a2]); }
+            }
+            const float rec[8] = { lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f };
+            cbox.insert(cbox.end(), rec, rec + 8);
+        }
+    }
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         OctNode* dn = nullptr;
@@ -559,9 +600,12 @@ static int oct_to_device(hare_part_s* p) {
         CK(dmalloc(&d.lists, t.polys.size()));
         CK(dmalloc(&d.csph, csph.size() / 4));
         if (!csph.empty()) CK(cudaMemcpy(d.csph, csph.data(), csph.size() * 4, cudaMemcpyHostToDevice));
+        CK(dmalloc(&d.cbox, cbox.size() / 4)); CK(dmalloc(&d.tbox, lbox.size() / 4));
+        if (!cbox.empty()) CK(cudaMemcpy(d.cbox, cbox.data(), cbox.size() * 4, cudaMemcpyHostToDevice));
+        if (!lbox.empty()) CK(cudaMemcpy(d.tbox, lbox.data(), lbox.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
-        d.bytes = N * sizeof(OctNode) + t.polys.size() * 4;
+        d.bytes = N * sizeof(OctNode) + t.polys.size() * 36 + cbox.size() * 4 + csph.size() * 4;
     }
     return HARE_OK;
 }
@@ -801,6 +845,7 @@ static int kd_to_device(hare_part_s* p) {
         if (t.left[i] >= 0) n.split = t.split[i];
         else { uint64_t bits = (uint64_t)t.list_off[i] | ((uint64_t)t.list_cnt[i] << 32); std::memcpy(&n.split, &bits, 8); }
     }
+    const std::vector<float> lbox = tree_entry_boxes(p->topo->pbox, t.polys);
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         KdNode* dn = nullptr;
@@ -808,7 +853,9 @@ static int kd_to_device(hare_part_s* p) {
         CK(dmalloc(&d.lists, t.polys.size()));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(KdNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
-        d.bytes = N * sizeof(KdNode) + t.polys.size() * 4;
+        CK(dmalloc(&d.tbox, lbox.size() / 4));
+        if (!lbox.empty()) CK(cudaMemcpy(d.tbox, lbox.data(), lbox.size() * 4, cudaMemcpyHostToDevice));
+        d.bytes = N * sizeof(KdNode) + t.polys.size() * 36;
     }
     return HARE_OK;
 }
@@ -1045,13 +1092,13 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.tbox, p->oct.depth };
             if (use_oct_v1()) return launch_shoot_t(t, d, a, st);
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
         }
         case HARE_KDTREE: {
-            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth };
+            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.tbox, p->kd.depth };
             if (use_kd_v1()) return launch_shoot_t(t, d, a, st);
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_kd_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
@@ -1088,13 +1135,13 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.tbox, p->oct.depth };
             if (use_oct_v1()) return launch_chain_t(t, d, a, st);
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_KDTREE: {
-            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), p->kd.depth };
+            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.tbox, p->kd.depth };
             if (use_kd_v1()) return launch_chain_t(t, d, a, st);
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_kd_walk<true>(t, d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);

@@ -22,6 +22,10 @@ namespace hare {
 #define HARE_KD_THREADS 640
 #endif
 #define HARE_KD_CB 8
+// 1: leaf entries are culled on padded FP32 bounding boxes (cull_box; KdDev::lbox); 0: on spheres
+#ifndef HARE_KD_BOX
+#define HARE_KD_BOX 1
+#endif
 
 // Exact-t tie between two different polygons: the reference keeps the one its exhaustive DFS meets first
 // (strict t < closestT, mailbox = first occurrence only).  That order is reconstructed analytically: walk down
@@ -77,6 +81,9 @@ kd_walk_kernel(const KdDev T, const PolyRec* __restrict__ polys,
     double inv[3] = { 0, 0, 0 };                     // reciprocals for the conservative prune only
     double closest = DBL_MAX, eu = 0, ev = 0;
     float fdx = 0, fdy = 0, fdz = 0, fdd = 0, fpx = 0, fpy = 0, fpz = 0;
+#if HARE_KD_BOX
+    float fix = 0, fiy = 0, fiz = 0;   // FP32 reciprocal direction (cull_box); with it fpx.. hold p/d instead of p
+#endif
     int stack[HARE_KD_MAXSTACK];
     int sp = 0;
     int pid = -1, or1 = -1, or2 = -1, bounce = 0;
@@ -158,6 +165,9 @@ kd_walk_kernel(const KdDev T, const PolyRec* __restrict__ polys,
                 inv[0] = 1.0 / R.dx; inv[1] = 1.0 / R.dy; inv[2] = 1.0 / R.dz;
                 fdx = (float)R.dx; fdy = (float)R.dy; fdz = (float)R.dz;
                 fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
+#if HARE_KD_BOX
+                fix = cull_rcp(fdx); fiy = cull_rcp(fdy); fiz = cull_rcp(fdz);
+#endif
                 if (blind) fin = 0;   // Ray_ID == 0 against a fresh mailbox: every polygon is rejected (KDTree.cs:58-66, 224-229)
             }
         }
@@ -178,6 +188,9 @@ kd_walk_kernel(const KdDev T, const PolyRec* __restrict__ polys,
                     lpos = off; lend = off + cnt;
                     if (cnt) {
                         fpx = (float)fma(R.dx, t_in, R.x); fpy = (float)fma(R.dy, t_in, R.y); fpz = (float)fma(R.dz, t_in, R.z);
+#if HARE_KD_BOX
+                        fpx *= fix; fpy *= fiy; fpz *= fiz;
+#endif
                         break;
                     }
                 } else {
@@ -190,6 +203,30 @@ kd_walk_kernel(const KdDev T, const PolyRec* __restrict__ polys,
         // ------------------------------------------------------------------ C phase: cull a batch of leaf entries
         if (state == ST_WALK && fin == 2 && bmask == 0 && lpos < lend) {
             const uint32_t n = min((uint32_t)HARE_KD_CB, lend - lpos);
+            uint32_t m = 0;
+#if HARE_KD_BOX
+            // every list entry carries its polygon's padded box and its id (lo.w): 32 contiguous bytes, no dependent load
+            static_assert(HARE_KD_CB == 8, "two groups of four");
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 lo[4], hi[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4* e = T.lbox + 2 * (size_t)(lpos + (4 * h + j < (int)n ? 4 * h + j : 0));
+                    lo[j] = __ldg(e); hi[j] = __ldg(e + 1);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t i = __float_as_uint(lo[j].w);   // poly_origin skip (:220); mailbox: a polygon counts once (:224-229)
+                    bid[4 * h + j] = i;
+                    const bool keep = (4 * h + j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
+                                      !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz);
+                    m |= keep ? (1u << (4 * h + j)) : 0u;
+                }
+            }
+            lpos += n;
+            if (COUNT) c.entries += n;
+#else
 #pragma unroll
             for (int j = 0; j < HARE_KD_CB; ++j) bid[j] = __ldg(T.lists + lpos + (j < (int)n ? j : 0));
             float4 s[HARE_KD_CB];
@@ -197,7 +234,6 @@ kd_walk_kernel(const KdDev T, const PolyRec* __restrict__ polys,
             for (int j = 0; j < HARE_KD_CB; ++j) s[j] = __ldg(T.sph + bid[j]);
             lpos += n;
             if (COUNT) c.entries += n;
-            uint32_t m = 0;
 #pragma unroll
             for (int j = 0; j < HARE_KD_CB; ++j) {
                 const uint32_t i = bid[j];   // poly_origin skip (:220); mailbox: a polygon counts once (:224-229)
@@ -205,6 +241,7 @@ kd_walk_kernel(const KdDev T, const PolyRec* __restrict__ polys,
                                   !cull_sphere(s[j], fpx, fpy, fpz, fdx, fdy, fdz, fdd);
                 m |= keep ? (1u << j) : 0u;
             }
+#endif
             bmask = m;
         }
         // ------------------------------------------------------------------ T phase: the exact FP64 test (slow path: u, v)

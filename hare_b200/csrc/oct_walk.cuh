@@ -26,6 +26,10 @@ namespace hare {
 #ifndef HARE_OCT_CB
 #define HARE_OCT_CB 8   /* leaf entries culled per C round */
 #endif
+// 1: chunks and leaf entries are culled on padded FP32 bounding boxes (cull_box; OctDev::cbox / lbox); 0: on spheres
+#ifndef HARE_OCT_BOX
+#define HARE_OCT_BOX 1
+#endif
 #ifndef HARE_OCT_THREADS
 #define HARE_OCT_THREADS 640
 #endif
@@ -46,6 +50,9 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
     double closest = DBL_MAX, eu = 0, ev = 0;      // closestT and the u, v of the best event
     double ca = 0, cb = 0;                         // interval of the node being entered / of the current leaf
     float fdx = 0, fdy = 0, fdz = 0, fdd = 0, fpx = 0, fpy = 0, fpz = 0;
+#if HARE_OCT_BOX
+    float fix = 0, fiy = 0, fiz = 0;   // FP32 reciprocal direction (cull_box); with it fpx.. hold p/d instead of p
+#endif
     int fchild[HARE_OCT_MAXLVL]; double fa[HARE_OCT_MAXLVL], fb[HARE_OCT_MAXLVL]; uint32_t fq[HARE_OCT_MAXLVL];
     int sp = -1, cur = 0, sgn = 0;
     int pid = -1, or1 = -1, or2 = -1, bounce = 0;
@@ -139,6 +146,9 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                 cur = 0; have_cur = true;
                 fdx = (float)R.dx; fdy = (float)R.dy; fdz = (float)R.dz;
                 fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
+#if HARE_OCT_BOX
+                fix = cull_rcp(fdx); fiy = cull_rcp(fdy); fiz = cull_rcp(fdz);
+#endif
             }
         }
         // ------------------------------------------------------------------ N phase: walk to the next leaf
@@ -156,6 +166,9 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                                 // leaf-local FP32 frame for cull_sphere: the ray point where the leaf is entered
                                 const double te = ca > 0.0 ? ca : 0.0;
                                 fpx = (float)fma(R.dx, te, R.x); fpy = (float)fma(R.dy, te, R.y); fpz = (float)fma(R.dz, te, R.z);
+#if HARE_OCT_BOX
+                                fpx *= fix; fpy *= fiy; fpz *= fiz;
+#endif
                                 break;
                             }
                         } else if (sp + 1 < HARE_OCT_MAXLVL) {
@@ -187,33 +200,68 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
         if (state == ST_WALK && fin == 2 && bmask == 0 && (emask != 0 || lpos < lend)) {
             static_assert(HARE_OCT_CB == HARE_OCT_CHUNK, "one C round culls one chunk");
             if (emask == 0) {
-                // next group of (up to) eight chunks = 64 list entries: cull the chunk spheres first
+                // next group of (up to) eight chunks = 64 list entries: cull the chunks first
                 const uint32_t left = lend - lpos, nch = min(8u, (left + HARE_OCT_CHUNK - 1) / HARE_OCT_CHUNK);
+                uint32_t em = 0;
+#if HARE_OCT_BOX
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float4 lo[4], hi[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4* e = T.cbox + 2 * (size_t)(cidx + (4 * h + j < (int)nch ? 4 * h + j : 0));
+                        lo[j] = __ldg(e); hi[j] = __ldg(e + 1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        em |= (4 * h + j < (int)nch && !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz)) ? (1u << (4 * h + j)) : 0u;
+                }
+#else
                 float4 cs[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) cs[j] = __ldg(T.csph + cidx + (j < (int)nch ? j : 0));
-                uint32_t em = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) em |= (j < (int)nch && !cull_sphere(cs[j], fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? (1u << j) : 0u;
+#endif
                 emask = em; cpos = lpos; cidx += nch;
                 const uint32_t adv = min(left, 8u * HARE_OCT_CHUNK);
                 lpos += adv;
                 if (COUNT) c.entries += adv;
             }
             if (emask != 0) {
-                // lowest surviving chunk: its (up to) eight entries, ids then spheres as two groups of independent loads
+                // lowest surviving chunk: its (up to) eight entries
                 const int kc = __ffs(emask) - 1;
                 emask &= emask - 1u;
                 const uint32_t base = cpos + (uint32_t)kc * HARE_OCT_CHUNK;
                 const uint32_t n = min((uint32_t)HARE_OCT_CB, lend - base);
+                uint32_t m = 0;
+                // poly_origin skip (:218); a polygon already tested for this ray (it sits in several leaves) cannot
+                // change anything: its t is not below closestT any more, so neither the update nor the early return fires
+#if HARE_OCT_BOX
+                // every list entry carries its polygon's padded box and its id (lo.w): 32 contiguous bytes, no dependent load
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float4 lo[4], hi[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4* e = T.lbox + 2 * (size_t)(base + (4 * h + j < (int)n ? 4 * h + j : 0));
+                        lo[j] = __ldg(e); hi[j] = __ldg(e + 1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t i = __float_as_uint(lo[j].w);
+                        bid[4 * h + j] = i;
+                        const bool keep = (4 * h + j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
+                                          !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz);
+                        m |= keep ? (1u << (4 * h + j)) : 0u;
+                    }
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < HARE_OCT_CB; ++j) bid[j] = __ldg(T.lists + base + (j < (int)n ? j : 0));
                 float4 s[HARE_OCT_CB];
 #pragma unroll
                 for (int j = 0; j < HARE_OCT_CB; ++j) s[j] = __ldg(T.sph + bid[j]);
-                // poly_origin skip (:218); a polygon already tested for this ray (it sits in several leaves) cannot
-                // change anything: its t is not below closestT any more, so neither the update nor the early return fires
-                uint32_t m = 0;
 #pragma unroll
                 for (int j = 0; j < HARE_OCT_CB; ++j) {
                     const uint32_t i = bid[j];
@@ -221,6 +269,7 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                                       !cull_sphere(s[j], fpx, fpy, fpz, fdx, fdy, fdz, fdd);
                     m |= keep ? (1u << j) : 0u;
                 }
+#endif
                 bmask = m;
             }
         }

@@ -237,6 +237,8 @@ struct OctDev {
     const uint32_t* __restrict__ lists;
     const float4* __restrict__ sph;   // padded bounding spheres, see cull_sphere()
     const float4* __restrict__ csph;  // one sphere per run of HARE_OCT_CHUNK consecutive leaf-list entries (leaf.pad = first chunk)
+    const float4* __restrict__ cbox;  // the same runs' padded FP32 bounding boxes (lo, hi), see cull_box()
+    const float4* __restrict__ lbox;  // per leaf-list entry: its polygon's padded box, polygon id in lo.w
     int depth;   // deepest level (root = 0)
 };
 
@@ -363,6 +365,7 @@ struct KdDev {
     const KdNode* __restrict__ nodes;
     const uint32_t* __restrict__ lists;
     const float4* __restrict__ sph;   // padded bounding spheres, see cull_sphere()
+    const float4* __restrict__ lbox;  // per leaf-list entry: its polygon's padded box, polygon id in lo.w (cull_box)
     int depth;
 };
 
