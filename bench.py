@@ -336,7 +336,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args),
-                         "peak_kind": peak_kind, "kernel": "vg_walk_kernel<CHAIN>", "kernel_ms": kernel_ms,
+                         "peak_kind": peak_kind, "kernel": ("vg_walk_kernel<CHAIN>" if os.environ.get("HARE_VG_WAVE") == "0" else "vg_wave_kernel<CHAIN>"), "kernel_ms": kernel_ms,
                          "bytes_per_shoot": bytes_per_shoot, "per_shoot": avg,
                          "formula": "56 + 36 + 8*cells + 4*entries + 128*tests (SURVEY.md 8(d)), oracle-counted"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

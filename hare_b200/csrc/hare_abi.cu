@@ -833,14 +833,47 @@ static int kd_depth(const KdTree& t) {
     return best;
 }
 
+// HARE_KD_TIGHT=0 keeps the reference's node boxes on the device (A/B measurements)
+static bool use_kd_tight() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_KD_TIGHT"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
+
 static int kd_to_device(hare_part_s* p) {
     const KdTree& t = p->kd;
     const size_t N = t.axis.size();
     if (kd_depth(t) + 2 > HARE_KD_MAXSTACK) return fail(HARE_ERR_UNSUPPORTED, "kd-tree deeper than HARE_KD_MAXSTACK allows");
+    // Device node boxes = the reference's node box (KDTree.cs:68-83, 107-121) INTERSECTED with the bounding box of the polygons
+    // listed below the node.  The walk only uses a node box to decide that no polygon of the subtree can be hit at
+    // t <= closest inside it (kd_box_reachable); a hit point inside the node box lies on a listed polygon, hence inside
+    // that polygon's bounding box too, so the intersection prunes the same way -- it is just far tighter for the many
+    // leaves that hold a sliver of a wall in a box of air.  hare_kdtree_download still returns the reference's boxes.
+    std::vector<double> tight(t.box);
+    if (use_kd_tight()) {
+        const HostTopo& M = p->topo->host;
+        std::vector<double> content(6 * N);
+        std::vector<std::pair<int, int>> st; st.push_back({ 0, 0 });   // (node, 0 = enter / 1 = leave)
+        while (!st.empty()) {
+            auto [n, leave] = st.back(); st.pop_back();
+            double* cb = &content[6 * (size_t)n];
+            if (t.left[n] < 0) {
+                for (int a = 0; a < 3; ++a) { cb[a] = INFINITY; cb[3 + a] = -INFINITY; }
+                for (uint32_t k = 0; k < t.list_cnt[n]; ++k) {
+                    const int64_t q = t.polys[t.list_off[n] + k];
+                    for (int v = 0; v < M.vcount[q]; ++v)
+                        for (int a = 0; a < 3; ++a) { const double c = M.verts[12 * q + 3 * v + a]; cb[a] = std::min(cb[a], c); cb[3 + a] = std::max(cb[3 + a], c); }
+                }
+            } else if (!leave) {
+                st.push_back({ n, 1 }); st.push_back({ t.left[n], 0 }); st.push_back({ t.left[n] + 1, 0 });
+                continue;
+            } else {
+                const double *l = &content[6 * (size_t)t.left[n]], *r = l + 6;
+                for (int a = 0; a < 3; ++a) { cb[a] = std::min(l[a], r[a]); cb[3 + a] = std::max(l[3 + a], r[3 + a]); }
+            }
+            for (int a = 0; a < 3; ++a) { tight[6 * (size_t)n + a] = std::max(tight[6 * (size_t)n + a], cb[a]); tight[6 * (size_t)n + 3 + a] = std::min(tight[6 * (size_t)n + 3 + a], cb[3 + a]); }
+        }
+    }
     std::vector<KdNode> nodes(N);
     for (size_t i = 0; i < N; ++i) {
         KdNode& n = nodes[i];
-        n.mnx = t.box[6 * i]; n.mny = t.box[6 * i + 1]; n.mnz = t.box[6 * i + 2]; n.mxx = t.box[6 * i + 3]; n.mxy = t.box[6 * i + 4]; n.mxz = t.box[6 * i + 5];
+        n.mnx = tight[6 * i]; n.mny = tight[6 * i + 1]; n.mnz = tight[6 * i + 2]; n.mxx = tight[6 * i + 3]; n.mxy = tight[6 * i + 4]; n.mxz = tight[6 * i + 5];
         n.left = t.left[i]; n.axis = t.left[i] >= 0 ? t.axis[i] : 0;
         if (t.left[i] >= 0) n.split = t.split[i];
         else { uint64_t bits = (uint64_t)t.list_off[i] | ((uint64_t)t.list_cnt[i] << 32); std::memcpy(&n.split, &bits, 8); }
