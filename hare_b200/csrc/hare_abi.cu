@@ -81,7 +81,7 @@ struct PartDev {
     float4* list_box = nullptr;   // per list entry: padded FP32 bounding box + polygon id (VGrid::lbox; vg_wave.cuh's cull)
     // trees
     void* nodes = nullptr; uint32_t* lists = nullptr; float4* csph = nullptr;   // csph: octree chunk spheres
-    float4* cbox = nullptr; float4* tbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id)
+    float4* cbox = nullptr; float4* tbox = nullptr; float4* nbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id); octree node content boxes
     // staging (per stream), sized for `cap` rays
     int64_t cap = 0;
     double *s_o[2] = {}, *s_d[2] = {}, *s_t[2] = {}, *s_xyz[2] = {}, *s_uv[2] = {}, *s_om[2] = {};
@@ -112,7 +112,7 @@ static void free_partdev(PartDev& d) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.tbox); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
@@ -593,6 +593,24 @@ static int oct_to_device(hare_part_s* p) {
             cbox.insert(cbox.end(), rec, rec + 8);
         }
     }
+    // Node content boxes: union of the padded boxes of every polygon listed below the node (children have larger indices).
+    std::vector<float> nbox(N * 8);
+    for (size_t i = N; i-- > 0;) {
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        if (t.first_child[i] < 0) {
+            for (uint32_t k = 0; k < t.list_cnt[i]; ++k) {
+                const float* q = &p->topo->pbox[6 * (size_t)t.polys[t.list_off[i] + k]];
+                for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], q[a2]); hi[a2] = std::max(hi[a2], q[3 + a2]); }
+            }
+        } else {
+            for (int c = 0; c < 8; ++c) {
+                const float* q = &nbox[8 * ((size_t)t.first_child[i] + c)];
+                for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], q[a2]); hi[a2] = std::max(hi[a2], q[4 + a2]); }
+            }
+        }
+        const float rec[8] = { lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f };
+        std::memcpy(&nbox[8 * i], rec, sizeof rec);
+    }
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         OctNode* dn = nullptr;
@@ -600,7 +618,8 @@ static int oct_to_device(hare_part_s* p) {
         CK(dmalloc(&d.lists, t.polys.size()));
         CK(dmalloc(&d.csph, csph.size() / 4));
         if (!csph.empty()) CK(cudaMemcpy(d.csph, csph.data(), csph.size() * 4, cudaMemcpyHostToDevice));
-        CK(dmalloc(&d.cbox, cbox.size() / 4)); CK(dmalloc(&d.tbox, lbox.size() / 4));
+        CK(dmalloc(&d.cbox, cbox.size() / 4)); CK(dmalloc(&d.tbox, lbox.size() / 4)); CK(dmalloc(&d.nbox, nbox.size() / 4));
+        CK(cudaMemcpy(d.nbox, nbox.data(), nbox.size() * 4, cudaMemcpyHostToDevice));
         if (!cbox.empty()) CK(cudaMemcpy(d.cbox, cbox.data(), cbox.size() * 4, cudaMemcpyHostToDevice));
         if (!lbox.empty()) CK(cudaMemcpy(d.tbox, lbox.data(), lbox.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
@@ -1125,7 +1144,7 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.tbox, p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.tbox, d.nbox, p->oct.depth };
             if (use_oct_v1()) return launch_shoot_t(t, d, a, st);
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
@@ -1168,7 +1187,7 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.tbox, p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.tbox, d.nbox, p->oct.depth };
             if (use_oct_v1()) return launch_chain_t(t, d, a, st);
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);

@@ -147,7 +147,9 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                 fdx = (float)R.dx; fdy = (float)R.dy; fdz = (float)R.dz;
                 fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
 #if HARE_OCT_BOX
+                // cull_box frame: p = the ray origin (its error budget does not need a local frame), kept as p/d
                 fix = cull_rcp(fdx); fiy = cull_rcp(fdy); fiz = cull_rcp(fdz);
+                fpx = (float)R.x * fix; fpy = (float)R.y * fiy; fpz = (float)R.z * fiz;
 #endif
             }
         }
@@ -163,11 +165,10 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                         if ((int)m.x < 0) {
                             lpos = m.y; lend = m.y + m.z; cidx = m.w;
                             if (lpos < lend) {
+#if !HARE_OCT_BOX
                                 // leaf-local FP32 frame for cull_sphere: the ray point where the leaf is entered
                                 const double te = ca > 0.0 ? ca : 0.0;
                                 fpx = (float)fma(R.dx, te, R.x); fpy = (float)fma(R.dy, te, R.y); fpz = (float)fma(R.dz, te, R.z);
-#if HARE_OCT_BOX
-                                fpx *= fix; fpy *= fiy; fpz *= fiz;
 #endif
                                 break;
                             }
@@ -189,6 +190,12 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                 const int q = 31 - __clz(pm);                                         // pushed near->far, popped far->near
                 fq[sp] = pm & ~(1u << q);
                 const int child = fchild[sp] + (q ^ sgn);
+#if HARE_OCT_BOX
+                {   // the ray's line misses everything listed below this child: entering it could change nothing
+                    const float4* e = T.nbox + 2 * (size_t)child;
+                    if (cull_box(__ldg(e), __ldg(e + 1), fpx, fpy, fpz, fix, fiy, fiz)) continue;
+                }
+#endif
                 double lo, hi;
                 oct_interval_finite(T.nodes + child, R, ix, iy, iz, lo, hi);
                 const double pa = fa[sp], pb = fb[sp];

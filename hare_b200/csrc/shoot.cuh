@@ -65,13 +65,14 @@ HD bool cull_sphere(const float4 s, float px, float py, float pz, float dx, floa
 
 // Second conservative reject: true only when the ray's supporting line misses the polygon's padded axis-aligned
 // bounding box (slab test).  For the wall / floor / seat rectangles of a hall the box is flat, so this is far
-// tighter than the sphere.  lo/hi are the FP32 box corners, padded by 1e-3 m + 1e-5 of the extent + 4e-7 |coordinate|
+// tighter than the sphere.  lo/hi are the FP32 box corners, padded by 1e-3 m + 1e-5 of the extent + 1e-6 |coordinate|
 // and rounded outwards (hare_box_pad); p, d as in cull_sphere (FP32 ray point near the voxel, FP32 direction).  A ray that hits the polygon at
 // q has q at least 1e-3 m inside the padded box on every axis, i.e. its parameter lies >= 1e-3/|d_a| inside each
-// slab interval, while the FP32 evaluation of the interval ends (lo/d - p/d, one FMA) is good to ~2e-7 |coordinate| / |d_a|: the
+// slab interval, while the FP32 evaluation of the interval ends (lo/d - p/d, one FMA; p, d and 1/d rounded to FP32, p anywhere
+// on the ray inside the model) is good to ~6e-7 |coordinate| / |d_a|: the
 // intervals computed here all contain it, so it is never rejected.  A zero direction component is replaced by
 // 1e-30 (cull_rcp; the slab then spans (-huge, +huge) when p is inside it and is empty when p is outside).  NaN -> keep.
-HD double hare_box_pad(double l, double h) { return 1e-3 + 1e-5 * (h - l) + 4e-7 * fmax(fabs(l), fabs(h)); }
+HD double hare_box_pad(double l, double h) { return 1e-3 + 1e-5 * (h - l) + 1e-6 * fmax(fabs(l), fabs(h)); }
 
 HD bool cull_box(const float4 lo, const float4 hi, float pxi, float pyi, float pzi, float ix, float iy, float iz) {   // ix = 1/dx, pxi = px/dx ...
     const float ax = fmaf(lo.x, ix, -pxi), bx = fmaf(hi.x, ix, -pxi);
@@ -239,6 +240,8 @@ struct OctDev {
     const float4* __restrict__ csph;  // one sphere per run of HARE_OCT_CHUNK consecutive leaf-list entries (leaf.pad = first chunk)
     const float4* __restrict__ cbox;  // the same runs' padded FP32 bounding boxes (lo, hi), see cull_box()
     const float4* __restrict__ lbox;  // per leaf-list entry: its polygon's padded box, polygon id in lo.w
+    const float4* __restrict__ nbox;  // per node: padded FP32 box of every polygon listed below it (lo, hi); a ray whose line
+                                      // misses it cannot be affected by the subtree, which is then not entered
     int depth;   // deepest level (root = 0)
 };
 
