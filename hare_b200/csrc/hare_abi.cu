@@ -154,7 +154,11 @@ static int ensure_chain_staging(PartDev& d, int64_t n, int order) {
 // ---------------------------------------------------------------------------------------
 extern "C" const char* hare_version(void) { return "hare_b200 0.1 (sm_100a)"; }
 extern "C" const char* hare_last_error(void) { return g_err.c_str(); }
-extern "C" uint64_t hare_launch_count(void) { return g_launches.load(); }
+namespace hare {
+extern unsigned long long g_kd_build_launches;   // kd_build.cu
+int build_kdtree_gpu(const HostTopo& M, const PolyRec* d_polys, int dev, cudaStream_t st, int maxDepth, int maxPolys, KdTree& out, std::string& err);
+}
+extern "C" uint64_t hare_launch_count(void) { return g_launches.load() + hare::g_kd_build_launches; }
 
 extern "C" int hare_device_count(void) {
     int n = 0;
@@ -917,7 +921,15 @@ extern "C" int hare_kdtree_build(hare_topo_t topo, int maxDepth, int maxPolys, h
     hare_part_s* p = nullptr;
     int rc = new_part(topo, HARE_KDTREE, &p);
     if (rc) return rc;
-    build_kdtree(topo->host, maxDepth, maxPolys, p->kd);
+    {
+        const char* e = getenv("HARE_KD_HOST_BUILD");
+        if (p->dev.empty() || (e && *e == '1')) build_kdtree(topo->host, maxDepth, maxPolys, p->kd);   // host-only handles, or forced
+        else {
+            std::string msg;
+            rc = build_kdtree_gpu(topo->host, p->dev[0].polys, p->dev[0].dev, p->dev[0].stream[0], maxDepth, maxPolys, p->kd, msg);
+            if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return fail(HARE_ERR_CUDA, msg); }
+        }
+    }
     rc = kd_to_device(p);
     if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
     *out = p;

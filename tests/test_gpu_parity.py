@@ -357,3 +357,27 @@ def test_gpu_octree_build_matches_host_build_and_oracle(gpu, level, args):
     o = ho.Octree(To, *args)
     assert canon_octree(*g.arrays()) == canon_octree(*o.arrays())
     assert (g.info()["nodes"], g.info()["list_entries"], g.info()["lost"]) == o.info()
+
+
+@pytest.mark.parametrize("level,args", [("shoebox", (4, 1)), ("tiny", (8, 4)), ("2k", (14, 8)), ("10k", (18, 16)), ("50k", (24, 16)), ("50k", (3, 1))])
+def test_gpu_kdtree_build_matches_host_build_and_oracle(gpu, level, args):
+    """the KDTree is built on the GPU level by level (dense centroid ranks, one stable radix sort
+    per level, scan + order-preserving scatter); node boxes, split values, numbering and list order equal the host
+    builder's arrays exactly and the oracle's tree structurally."""
+    import os
+    from tests.util import canon_kdtree
+    mesh = meshes.shoebox() if level == "shoebox" else meshes.hall(level)
+    T, To = _pair(gpu, mesh)
+    g = gpu.KDTree([T], *args)
+    os.environ["HARE_KD_HOST_BUILD"] = "1"
+    try:
+        h = gpu.KDTree([T], *args)
+    finally:
+        del os.environ["HARE_KD_HOST_BUILD"]
+    for a, b in zip(g.arrays(), h.arrays()):
+        assert np.array_equal(a, b)
+    assert g.info() == h.info()
+    box, sp, ax, le, lo, lc, pol = g.arrays()
+    o = ho.KDTree(To, *args)
+    obox, osp, oax, ole, ori, olo, olc, opol = o.arrays()
+    assert canon_kdtree(box, sp, ax, le, le + 1, lo, lc, pol) == canon_kdtree(obox, osp, oax, ole, ori, olo, olc, opol)
