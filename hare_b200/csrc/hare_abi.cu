@@ -156,9 +156,12 @@ extern "C" const char* hare_version(void) { return "hare_b200 0.1 (sm_100a)"; }
 extern "C" const char* hare_last_error(void) { return g_err.c_str(); }
 namespace hare {
 extern unsigned long long g_kd_build_launches;   // kd_build.cu
+extern unsigned long long g_ingest_launches;     // ingest.cu
+int topology_ingest_gpu(int dev, const double* raw, const int32_t* vcount, int64_t P, const double minpt[3], const double maxpt[3],
+                        double* verts_out, double* normals_out, double minmax_out[6], int64_t* vertex_count_out, std::string& err);
 int build_kdtree_gpu(const HostTopo& M, const PolyRec* d_polys, int dev, cudaStream_t st, int maxDepth, int maxPolys, KdTree& out, std::string& err);
 }
-extern "C" uint64_t hare_launch_count(void) { return g_launches.load() + hare::g_kd_build_launches; }
+extern "C" uint64_t hare_launch_count(void) { return g_launches.load() + hare::g_kd_build_launches + hare::g_ingest_launches; }
 
 extern "C" int hare_device_count(void) {
     int n = 0;
@@ -203,7 +206,25 @@ extern "C" int hare_topology_ingest(const double* raw_verts, const int32_t* vcou
                                     double* verts_out, double* normals_out, double minmax_out[6], int64_t* vertex_count_out) {
     if (!raw_verts || !vcount || P < 0 || !minpt || !maxpt || !verts_out || !normals_out || !minmax_out)
         return fail(HARE_ERR_INVALID, "hare_topology_ingest: null argument");
-    int r = topology_ingest(raw_verts, vcount, P, minpt, maxpt, verts_out, normals_out, minmax_out, vertex_count_out);
+    // The welding, normals and bounds run on the GPU when one is in use (ingest.cu, bit-identical to the host routine; SURVEY.md
+    // 8(f) rank 2).  Ingest is build-time tooling that must also work on a machine without a device (hare_init(NULL, -1)), and
+    // input the device path declines (vertices outside the declared bounds, ...) keeps the host routine's behaviour: it is the
+    // same computation either way, not a fallback of the Shoot path.  HARE_INGEST_HOST=1 forces the host routine (A/B tests).
+    int r = 1;
+    {
+        const char* e = getenv("HARE_INGEST_HOST");
+        int dev = -1;
+        if (!(e && *e == '1') && P >= 4096 && ensure_init() == HARE_OK) {
+            std::lock_guard<std::mutex> lk(g_mu);
+            if (!g_host_only && !g_devices.empty()) dev = g_devices[0];
+        }
+        if (dev >= 0) {
+            std::string msg;
+            r = topology_ingest_gpu(dev, raw_verts, vcount, P, minpt, maxpt, verts_out, normals_out, minmax_out, vertex_count_out, msg);
+            if (r == -2) return fail(HARE_ERR_CUDA, msg);
+        }
+    }
+    if (r == 1) r = topology_ingest(raw_verts, vcount, P, minpt, maxpt, verts_out, normals_out, minmax_out, vertex_count_out);
     if (r == -3) return fail(HARE_ERR_UNSUPPORTED, "Hare Does not yet support polygons of more than 4 sides.");
     return r;
 }

@@ -320,10 +320,7 @@ int build_kdtree_gpu(const HostTopo& M, const PolyRec* d_polys, int dev, cudaStr
         }
         const long long n_next = next_start.back();
         // the sorted arrays live in [cur ^ 1]; the next level is written into [cur] (its old contents are dead) -- grow first
-        {
-            const uint32_t* keep_list = list[cur ^ 1].p; (void)keep_list;
-            KCK(list[cur].ensure((size_t)n_next)); KCK(seg[cur].ensure((size_t)n_next));
-        }
+        KCK(list[cur].ensure((size_t)n_next)); KCK(seg[cur].ensure((size_t)n_next));
         KCK(cudaMemcpyAsync(child_start.p, next_start.data(), next_start.size() * 4, cudaMemcpyHostToDevice, st));
         kd_level_scatter<<<grid_for(n), 256, 0, st>>>(list[cur ^ 1].p, seg[cur ^ 1].p, seg_start.p, seg_info.p, le.p, gt.p, sl.p, sg.p, child_start.p, n,
                                                       list[cur].p, seg[cur].p);

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from hare_b200.harness import meshes, rays_from_sources
+from hare_b200.harness.meshes import Mesh
 from oracle import hare_oracle as ho
 from tests.util import assert_events_equal
 
@@ -381,3 +382,41 @@ def test_gpu_kdtree_build_matches_host_build_and_oracle(gpu, level, args):
     o = ho.KDTree(To, *args)
     obox, osp, oax, ole, ori, olo, olc, opol = o.arrays()
     assert canon_kdtree(box, sp, ax, le, le + 1, lo, lc, pol) == canon_kdtree(obox, osp, oax, ole, ori, olo, olc, opol)
+
+
+@pytest.mark.parametrize("level", ["10k", "50k"])
+def test_gpu_topology_ingest_matches_host_ingest_and_oracle(gpu, level):
+    """Round(15), the 1 mm first-seen weld, normals and bounds on the GPU (ingest.cu) give the host
+    routine's arrays bit for bit -- also when many vertices share lattice cells with earlier ones."""
+    import os
+    mesh = meshes.hall(level)
+    raw = np.array(mesh.verts, dtype=np.float64).reshape(-1, 4, 3)
+    rng = np.random.default_rng(7)
+    jit = raw + rng.uniform(-4e-4, 4e-4, raw.shape) * (rng.random(raw.shape[:2])[..., None] < 0.3)   # sub-millimetre jitter on 30 % of the corners
+    for verts in (raw, jit):
+        m2 = Mesh(verts, mesh.vcount, mesh.minpt - 0.01, mesh.maxpt + 0.01, mesh.name)
+        Tg = gpu.Topology.from_mesh(m2)
+        os.environ["HARE_INGEST_HOST"] = "1"
+        try:
+            Th = gpu.Topology.from_mesh(m2)
+        finally:
+            del os.environ["HARE_INGEST_HOST"]
+        assert np.array_equal(Tg.verts, Th.verts) and np.array_equal(Tg.normals, Th.normals) and np.array_equal(Tg._mm, Th._mm)
+        assert Tg.Vertex_Count == Th.Vertex_Count
+        To = ho.Topology.from_mesh(m2)
+        v, n, c, mm = To.arrays()
+        assert np.array_equal(Tg.verts, v) and np.array_equal(Tg.normals, n) and np.array_equal(Tg._mm, mm) and Tg.Vertex_Count == To.Vertex_Count
+
+
+def test_gpu_topology_ingest_declines_out_of_bounds_vertices(gpu):
+    """A vertex outside the declared Topology bounds is not for the device path: the host routine runs, same result as with it forced."""
+    import os
+    mesh = meshes.hall("10k")
+    m2 = Mesh(mesh.verts, mesh.vcount, mesh.minpt + 1.0, mesh.maxpt + 1.0, mesh.name)
+    Tg = gpu.Topology.from_mesh(m2)
+    os.environ["HARE_INGEST_HOST"] = "1"
+    try:
+        Th = gpu.Topology.from_mesh(m2)
+    finally:
+        del os.environ["HARE_INGEST_HOST"]
+    assert np.array_equal(Tg.verts, Th.verts) and np.array_equal(Tg._mm, Th._mm) and Tg.Vertex_Count == Th.Vertex_Count
