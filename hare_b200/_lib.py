@@ -74,6 +74,8 @@ def lib():
     L.hare_kdtree_upload.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, pp]
     L.hare_kdtree_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.hare_kdtree_download.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.hare_part_save.argtypes = [vp, C.c_char_p]
+    L.hare_part_load.argtypes = [vp, C.c_char_p, pp]
     L.hare_part_kind.argtypes = [vp]
     L.hare_part_device_bytes.restype = i64
     L.hare_part_device_bytes.argtypes = [vp]

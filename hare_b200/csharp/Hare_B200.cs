@@ -50,6 +50,8 @@ namespace Hare.Geometry.Native
         public static extern int hare_kdtree_upload(IntPtr topo, double[] node_box, double[] split, int[] axis, int[] left, uint[] list_off, uint[] list_cnt,
                                                     uint[] polys, long n_nodes, long n_list, out IntPtr part);
         [DllImport(Lib, CallingConvention = CC)] public static extern int hare_part_destroy(IntPtr part);
+        [DllImport(Lib, CallingConvention = CC, CharSet = CharSet.Ansi)] public static extern int hare_part_save(IntPtr part, string path);
+        [DllImport(Lib, CallingConvention = CC, CharSet = CharSet.Ansi)] public static extern int hare_part_load(IntPtr topo, string path, out IntPtr part);
 
         [DllImport(Lib, CallingConvention = CC)]
         public static extern int hare_shoot_batch(IntPtr part, double[] o, double[] d, int[] origin1, int[] origin2, int[] ray_id, long N,

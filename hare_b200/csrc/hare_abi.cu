@@ -1006,6 +1006,98 @@ extern "C" int hare_kdtree_download(hare_part_t p, double* node_box, double* spl
     return HARE_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// On-disk form of a flattened partition (the reference has none): lets a large hall skip its
+// rebuild.  Little-endian, native types:
+//   "HAREB200" | u32 version | i32 kind | i64 P | u64 fnv1a(polygon vertices) | kind-specific arrays, each as (u64 count, data)
+// Loading goes through the same checks and device set-up as the *_upload entry points.
+// ---------------------------------------------------------------------------------------
+namespace {
+const char kMagic[8] = { 'H', 'A', 'R', 'E', 'B', '2', '0', '0' };
+const uint32_t kFileVersion = 1;
+
+uint64_t topo_fingerprint(const HostTopo& M) {
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(M.verts.data());
+    for (size_t i = 0, n = M.verts.size() * sizeof(double); i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+template <class T> bool put(FILE* f, const T* v, uint64_t n) { return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v, sizeof(T), n, f) == n); }
+template <class T> bool put(FILE* f, const std::vector<T>& v) { return put(f, v.data(), (uint64_t)v.size()); }
+template <class T> bool get(FILE* f, std::vector<T>& v, uint64_t limit) {
+    uint64_t n = 0;
+    if (fread(&n, 8, 1, f) != 1 || n > limit) return false;
+    v.resize((size_t)n);
+    return n == 0 || fread(v.data(), sizeof(T), (size_t)n, f) == n;
+}
+}  // namespace
+
+extern "C" int hare_part_save(hare_part_t p, const char* path) {
+    if (!p || !path) return fail(HARE_ERR_INVALID, "hare_part_save: bad argument");
+    std::lock_guard<std::mutex> lk(p->mu);
+    std::vector<uint32_t> off, pol;
+    if (p->kind == HARE_VOXEL_GRID) {
+        if (p->dev.empty()) return fail(HARE_ERR_CUDA, "hare_part_save: host-only Voxel_Grid handle");
+        const int64_t ncells = (int64_t)p->ct[0] * p->ct[1] * p->ct[2];
+        off.resize((size_t)ncells + 1); pol.resize((size_t)p->npairs);
+        PartDev& d = p->dev[0];
+        CK(cudaSetDevice(d.dev));
+        CK(cudaMemcpy(off.data(), d.cell_offset, off.size() * 4, cudaMemcpyDeviceToHost));
+        if (p->npairs) CK(cudaMemcpy(pol.data(), d.cell_poly, pol.size() * 4, cudaMemcpyDeviceToHost));
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(HARE_ERR_INVALID, std::string("hare_part_save: cannot open ") + path);
+    const int32_t kind = p->kind; const int64_t P = p->topo->host.P; const uint64_t fp = topo_fingerprint(p->topo->host);
+    bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(&kFileVersion, 4, 1, f) == 1 && fwrite(&kind, 4, 1, f) == 1 && fwrite(&P, 8, 1, f) == 1 && fwrite(&fp, 8, 1, f) == 1;
+    if (kind == HARE_VOXEL_GRID) ok = ok && put(f, p->obox, 6) && put(f, p->ct, 3) && put(f, off) && put(f, pol);
+    else if (kind == HARE_OCTREE) ok = ok && put(f, p->oct.box) && put(f, p->oct.first_child) && put(f, p->oct.list_off) && put(f, p->oct.list_cnt) && put(f, p->oct.polys) && put(f, &p->oct.lost, 1);
+    else ok = ok && put(f, p->kd.box) && put(f, p->kd.split) && put(f, p->kd.axis) && put(f, p->kd.left) && put(f, p->kd.list_off) && put(f, p->kd.list_cnt) && put(f, p->kd.polys);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(HARE_ERR_INVALID, std::string("hare_part_save: write failed: ") + path);
+    return HARE_OK;
+}
+
+extern "C" int hare_part_load(hare_topo_t topo, const char* path, hare_part_t* out) {
+    if (!topo || !path || !out) return fail(HARE_ERR_INVALID, "hare_part_load: bad argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(HARE_ERR_INVALID, std::string("hare_part_load: cannot open ") + path);
+    char magic[8]; uint32_t ver = 0; int32_t kind = 0; int64_t P = 0; uint64_t fp = 0;
+    bool ok = fread(magic, 8, 1, f) == 1 && fread(&ver, 4, 1, f) == 1 && fread(&kind, 4, 1, f) == 1 && fread(&P, 8, 1, f) == 1 && fread(&fp, 8, 1, f) == 1;
+    auto bail = [&](const std::string& why) { fclose(f); return fail(HARE_ERR_INVALID, "hare_part_load: " + why); };
+    if (!ok || std::memcmp(magic, kMagic, 8) != 0) return bail("not a hare_b200 partition file");
+    if (ver != kFileVersion) return bail("unsupported file version");
+    if (P != topo->host.P || fp != topo_fingerprint(topo->host)) return bail("the file was written for a different Topology");
+    const uint64_t lim = 1ull << 33;
+    int rc;
+    if (kind == HARE_VOXEL_GRID) {
+        std::vector<double> obox; std::vector<int32_t> ct; std::vector<uint32_t> off, pol;
+        if (!(get(f, obox, 6) && get(f, ct, 3) && get(f, off, lim) && get(f, pol, lim)) || obox.size() != 6 || ct.size() != 3) return bail("truncated Voxel_Grid record");
+        if (ct[0] < 1 || ct[1] < 1 || ct[2] < 1 || (uint64_t)ct[0] * ct[1] * ct[2] + 1 != off.size() || off.back() != pol.size()) return bail("inconsistent Voxel_Grid record");
+        fclose(f);
+        rc = hare_voxelgrid_upload(topo, obox.data(), ct.data(), off.data(), pol.data(), out);
+    } else if (kind == HARE_OCTREE) {
+        OctTree t; std::vector<int64_t> lost;
+        if (!(get(f, t.box, lim) && get(f, t.first_child, lim) && get(f, t.list_off, lim) && get(f, t.list_cnt, lim) && get(f, t.polys, lim) && get(f, lost, 1)) || lost.size() != 1)
+            return bail("truncated Octree record");
+        const size_t N = t.first_child.size();
+        if (N < 1 || t.box.size() != 6 * N || t.list_off.size() != N || t.list_cnt.size() != N) return bail("inconsistent Octree record");
+        fclose(f);
+        rc = hare_octree_upload(topo, t.box.data(), t.first_child.data(), t.list_off.data(), t.list_cnt.data(), t.polys.data(), (int64_t)N, (int64_t)t.polys.size(), out);
+        if (rc == HARE_OK) (*out)->oct.lost = lost[0];
+    } else if (kind == HARE_KDTREE) {
+        KdTree t;
+        if (!(get(f, t.box, lim) && get(f, t.split, lim) && get(f, t.axis, lim) && get(f, t.left, lim) && get(f, t.list_off, lim) && get(f, t.list_cnt, lim) && get(f, t.polys, lim)))
+            return bail("truncated KDTree record");
+        const size_t N = t.axis.size();
+        if (N < 1 || t.box.size() != 6 * N || t.split.size() != N || t.left.size() != N || t.list_off.size() != N || t.list_cnt.size() != N) return bail("inconsistent KDTree record");
+        fclose(f);
+        rc = hare_kdtree_upload(topo, t.box.data(), t.split.data(), t.axis.data(), t.left.data(), t.list_off.data(), t.list_cnt.data(), t.polys.data(), (int64_t)N, (int64_t)t.polys.size(), out);
+    } else {
+        return bail("unknown partition kind");
+    }
+    return rc;
+}
+
 extern "C" int hare_part_kind(hare_part_t p) { return p ? p->kind : HARE_ERR_INVALID; }
 extern "C" int64_t hare_part_device_bytes(hare_part_t p) { return (p && !p->dev.empty()) ? (int64_t)p->dev[0].bytes : -1; }
 

@@ -15,6 +15,7 @@ plus the new batched overload Shoot_Batch and Reflect_Chain.
 All computation happens in libhare_b200.so (CUDA, sm_100a); nothing here computes results.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -135,6 +136,26 @@ class Spatial_Partition:
         self.Char_Step = 0.0
         self._h = C.c_void_p()
 
+    # ---- on-disk form (none in the reference) ------------------------
+    def Save(self, path):
+        """Write the flattened partition (cells or nodes and lists) to `path`."""
+        check(_lib.lib().hare_part_save(self._h, os.fsencode(path)), "hare_part_save")
+
+    @classmethod
+    def Load(cls, Model, path):
+        """Rebuild a partition saved by Save() for the same Topology, without re-running its constructor."""
+        self = cls.__new__(cls)
+        Spatial_Partition.__init__(self, Model)
+        check(_lib.lib().hare_part_load(self.Model[0]._h, os.fsencode(path), C.byref(self._h)), "hare_part_load")
+        kind = {1: "Voxel_Grid", 2: "Octree", 3: "KDTree"}[_lib.lib().hare_part_kind(self._h)]
+        if kind != cls.__name__:
+            h, self._h = self._h, C.c_void_p()
+            _lib.lib().hare_part_destroy(h)
+            raise ValueError(f"{path} holds a {kind}, not a {cls.__name__}")
+        if hasattr(self, "_after_load"):
+            self._after_load()
+        return self
+
     # ---- reference-shaped single-ray overloads ------------------------------------------
     def Shoot(self, R, top_index=0, poly_origin1=None, poly_origin2=-1):
         """bool Shoot(Ray R, int top_index, out X_Event[, int poly_origin1, int poly_origin2 = -1]).
@@ -219,6 +240,9 @@ class Voxel_Grid(Spatial_Partition):
         check(_lib.lib().hare_voxelgrid_upload(self.Model[0]._h, ptr(obox), ptr(ct), ptr(off), ptr(pol), C.byref(self._h)), "hare_voxelgrid_upload")
         self._post()
         return self
+
+    def _after_load(self):
+        self._post()
 
     def _post(self):
         obox, vd, ct, n = self.info()

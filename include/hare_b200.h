@@ -120,6 +120,12 @@ int hare_kdtree_info(hare_part_t part, int64_t* n_nodes, int64_t* n_list, int32_
 int hare_kdtree_download(hare_part_t part, double* node_box, double* split, int32_t* axis, int32_t* left,
                          uint32_t* list_off, uint32_t* list_cnt, uint32_t* polys);
 
+/* On-disk form of a flattened partition (the reference has none): a large hall can skip its rebuild.
+ * The file records the Topology it was built for (polygon count + a hash of the vertices); hare_part_load refuses another
+ * one and otherwise applies the checks and device set-up of the *_upload entry points. */
+int hare_part_save(hare_part_t part, const char* path);
+int hare_part_load(hare_topo_t topo, const char* path, hare_part_t* out);
+
 int hare_part_kind(hare_part_t part);
 int64_t hare_part_device_bytes(hare_part_t part);
 int hare_part_destroy(hare_part_t part);

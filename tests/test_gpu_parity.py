@@ -420,3 +420,19 @@ def test_gpu_topology_ingest_declines_out_of_bounds_vertices(gpu):
     finally:
         del os.environ["HARE_INGEST_HOST"]
     assert np.array_equal(Tg.verts, Th.verts) and np.array_equal(Tg._mm, Th._mm) and Tg.Vertex_Count == Th.Vertex_Count
+
+
+def test_partition_save_load_shoots_identically(gpu, tmp_path):
+    """hare_part_save / hare_part_load: a reloaded Voxel_Grid, Octree and KDTree answer exactly like the one that was built."""
+    mesh = meshes.hall("10k")
+    T, To = _pair(gpu, mesh)
+    o, d = rays_from_sources(20_000, meshes.sources(4), stream=5)
+    for cls, args in ((gpu.Voxel_Grid, (24,)), (gpu.Octree, (6, 16)), (gpu.KDTree, (18, 16))):
+        part = cls([T], *args)
+        f = str(tmp_path / (cls.__name__ + ".hare"))
+        part.Save(f)
+        back = cls.Load([T], f)
+        a, b = part.Shoot_Batch(o, d), back.Shoot_Batch(o, d)
+        for k in ("poly_id", "t", "xyz", "uv"):
+            assert np.array_equal(a[k], b[k]), (cls.__name__, k)
+    assert back.Char_Step == 0.0 and gpu.Voxel_Grid.Load([T], str(tmp_path / "Voxel_Grid.hare")).Char_Step > 0

@@ -135,3 +135,27 @@ def test_missing_extension_raises(tmp_path):
             "try:\n    hare_b200.lib()\nexcept hare_b200.HareError as e:\n    print('RAISED', e)\n") % (str(tmp_path / "nope.so"), _lib.ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout
     assert "RAISED" in out and "no CPU fallback" in out
+
+
+@pytest.mark.parametrize("kind,args", [("Octree", (5, 8)), ("KDTree", (12, 8))])
+def test_partition_save_load_roundtrip(host_only, tmp_path, kind, args):
+    """On-disk form of a flattened partition: load == what was saved, for the same Topology only."""
+    mesh = meshes.hall("2k")
+    T = hb.Topology.from_mesh(mesh)
+    part = getattr(hb, kind)([T], *args)
+    f = str(tmp_path / "part.hare")
+    part.Save(f)
+    back = getattr(hb, kind).Load([T], f)
+    for a, b in zip(part.arrays(), back.arrays()):
+        assert np.array_equal(a, b)
+    assert part.info() == back.info()
+    other = {"Octree": hb.KDTree, "KDTree": hb.Octree}[kind]
+    with pytest.raises(ValueError):
+        other.Load([T], f)
+    T2 = hb.Topology.from_mesh(meshes.hall("tiny"))
+    with pytest.raises(hb.HareError):
+        getattr(hb, kind).Load([T2], f)
+    with open(f, "r+b") as fh:                      # a truncated file is refused, not read past its end
+        fh.truncate(200)
+    with pytest.raises(hb.HareError):
+        getattr(hb, kind).Load([T], f)
