@@ -81,7 +81,7 @@ struct PartDev {
     float4* list_box = nullptr;   // per list entry: padded FP32 bounding box + polygon id (VGrid::lbox; vg_wave.cuh's cull)
     // trees
     void* nodes = nullptr; uint32_t* lists = nullptr; float4* csph = nullptr;   // csph: octree chunk spheres
-    float4* cbox = nullptr; float4* tbox = nullptr; float4* nbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id); octree node content boxes
+    float4* cbox = nullptr; float4* gbox = nullptr; float4* tbox = nullptr; float4* nbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id); octree node content boxes
     // staging (per stream), sized for `cap` rays
     int64_t cap = 0;
     double *s_o[2] = {}, *s_d[2] = {}, *s_t[2] = {}, *s_xyz[2] = {}, *s_uv[2] = {}, *s_om[2] = {};
@@ -112,7 +112,7 @@ static void free_partdev(PartDev& d) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
@@ -583,6 +583,7 @@ static int oct_to_device(hare_part_s* p) {
         const std::vector<float>& ps = p->topo->sph;
         for (size_t i = 0; i < N; ++i) {
             if (t.first_child[i] >= 0) continue;
+            while ((csph.size() / 4) % 8) { const float z[4] = { 0.f, 0.f, 0.f, 0.f }; csph.insert(csph.end(), z, z + 4); }   // a leaf's chunks start a group of 8
             nodes[i].pad = (uint32_t)(csph.size() / 4);
             for (uint32_t b = 0; b < t.list_cnt[i]; b += HARE_OCT_CHUNK) {
                 const uint32_t e = std::min<uint32_t>(b + HARE_OCT_CHUNK, t.list_cnt[i]);
@@ -604,9 +605,12 @@ static int oct_to_device(hare_part_s* p) {
         }
     }
     // The same runs' boxes (union of the members' padded boxes), and one (box, polygon id) record per list entry.
-    std::vector<float> cbox, lbox = tree_entry_boxes(p->topo->pbox, t.polys);
+    // Chunks are numbered as for csph (every leaf starts a multiple of 8); gbox[g] encloses chunks 8g .. 8g+7.
+    std::vector<float> cbox, gbox, lbox = tree_entry_boxes(p->topo->pbox, t.polys);
+    const float kEmptyBox[8] = { INFINITY, INFINITY, INFINITY, 0.f, -INFINITY, -INFINITY, -INFINITY, 0.f };
     for (size_t i = 0; i < N; ++i) {
         if (t.first_child[i] >= 0) continue;
+        while ((cbox.size() / 8) % 8) cbox.insert(cbox.end(), kEmptyBox, kEmptyBox + 8);
         for (uint32_t b = 0; b < t.list_cnt[i]; b += HARE_OCT_CHUNK) {
             const uint32_t e = std::min<uint32_t>(b + HARE_OCT_CHUNK, t.list_cnt[i]);
             float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
@@ -617,6 +621,12 @@ static int oct_to_device(hare_part_s* p) {
             const float rec[8] = { lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f };
             cbox.insert(cbox.end(), rec, rec + 8);
         }
+    }
+    for (size_t g = 0; g * 64 < cbox.size(); ++g) {
+        float rec[8] = { INFINITY, INFINITY, INFINITY, 0.f, -INFINITY, -INFINITY, -INFINITY, 0.f };
+        for (size_t c = 8 * g; c < 8 * g + 8 && c * 8 < cbox.size(); ++c)
+            for (int a2 = 0; a2 < 3; ++a2) { rec[a2] = std::min(rec[a2], cbox[8 * c + a2]); rec[4 + a2] = std::max(rec[4 + a2], cbox[8 * c + 4 + a2]); }
+        gbox.insert(gbox.end(), rec, rec + 8);
     }
     // Node content boxes: union of the padded boxes of every polygon listed below the node (children have larger indices).
     std::vector<float> nbox(N * 8);
@@ -646,6 +656,8 @@ static int oct_to_device(hare_part_s* p) {
         CK(dmalloc(&d.cbox, cbox.size() / 4)); CK(dmalloc(&d.tbox, lbox.size() / 4)); CK(dmalloc(&d.nbox, nbox.size() / 4));
         CK(cudaMemcpy(d.nbox, nbox.data(), nbox.size() * 4, cudaMemcpyHostToDevice));
         if (!cbox.empty()) CK(cudaMemcpy(d.cbox, cbox.data(), cbox.size() * 4, cudaMemcpyHostToDevice));
+        CK(dmalloc(&d.gbox, gbox.size() / 4));
+        if (!gbox.empty()) CK(cudaMemcpy(d.gbox, gbox.data(), gbox.size() * 4, cudaMemcpyHostToDevice));
         if (!lbox.empty()) CK(cudaMemcpy(d.tbox, lbox.data(), lbox.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
@@ -1269,7 +1281,7 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.tbox, d.nbox, p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.gbox, d.tbox, d.nbox, p->oct.depth };
             if (use_oct_v1()) return launch_shoot_t(t, d, a, st);
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
@@ -1312,7 +1324,7 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.tbox, d.nbox, p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.gbox, d.tbox, d.nbox, p->oct.depth };
             if (use_oct_v1()) return launch_chain_t(t, d, a, st);
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);

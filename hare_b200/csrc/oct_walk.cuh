@@ -211,6 +211,9 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                 const uint32_t left = lend - lpos, nch = min(8u, (left + HARE_OCT_CHUNK - 1) / HARE_OCT_CHUNK);
                 uint32_t em = 0;
 #if HARE_OCT_BOX
+                // the whole group of 64 entries first: most groups of a long leaf list are nowhere near the ray
+                const float4* ge = T.gbox + 2 * (size_t)(cidx >> 3);
+                if (!cull_box(__ldg(ge), __ldg(ge + 1), fpx, fpy, fpz, fix, fiy, fiz))
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float4 lo[4], hi[4];
