@@ -147,9 +147,14 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
                 fdx = (float)R.dx; fdy = (float)R.dy; fdz = (float)R.dz;
                 fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
 #if HARE_OCT_BOX
-                // cull_box frame: p = the ray origin (its error budget does not need a local frame), kept as p/d
-                fix = cull_rcp(fdx); fiy = cull_rcp(fdy); fiz = cull_rcp(fdz);
-                fpx = (float)R.x * fix; fpy = (float)R.y * fiy; fpz = (float)R.z * fiz;
+                // cull_box frame: p = the point where the ray enters the root cube (the origin itself when it starts inside),
+                // formed in FP64 and then rounded -- a ray shot from far outside the model must not lose the millimetres
+                // the padding allows to FP32; kept as p/d
+                {
+                    const double te = ca > 0.0 ? ca : 0.0;
+                    fix = cull_rcp(fdx); fiy = cull_rcp(fdy); fiz = cull_rcp(fdz);
+                    fpx = (float)fma(R.dx, te, R.x) * fix; fpy = (float)fma(R.dy, te, R.y) * fiy; fpz = (float)fma(R.dz, te, R.z) * fiz;
+                }
 #endif
             }
         }

@@ -436,3 +436,19 @@ def test_partition_save_load_shoots_identically(gpu, tmp_path):
         for k in ("poly_id", "t", "xyz", "uv"):
             assert np.array_equal(a[k], b[k]), (cls.__name__, k)
     assert back.Char_Step == 0.0 and gpu.Voxel_Grid.Load([T], str(tmp_path / "Voxel_Grid.hare")).Char_Step > 0
+
+
+def test_rays_from_far_outside_the_model(gpu):
+    """The conservative FP32 culls work in a frame near the model (voxel exit point, root-cube / leaf entry point formed in
+    FP64): rays shot from 1e5 m and 1e8 m away give the reference's events bit for bit on every partition."""
+    mesh = meshes.hall("10k")
+    T, To = _pair(gpu, mesh)
+    o, d = rays_from_sources(6_000, meshes.sources(4), stream=6)
+    for back in (1e5, 1e8):
+        of = o - d * back
+        for kind, gargs, oargs in (("Voxel_Grid", (24,), (24, "fast")), ("Octree", (6, 16), (6, 16)), ("KDTree", (18, 16), (18, 16))):
+            n = 6_000 if kind != "KDTree" else 1_500          # the reference's KDTree walk is exhaustive
+            got = getattr(gpu, kind)([T], *gargs).Shoot_Batch(of[:n], d[:n])
+            ref = getattr(ho, kind)(To, *oargs).Shoot(of[:n], d[:n], nthreads=8)
+            assert_events_equal(got, ref, uv=kind != "Voxel_Grid", what=f"{kind} from {back:g} m")
+            assert (ref["poly_id"] >= 0).mean() > 0.9

@@ -67,3 +67,16 @@ def test_wave_empty_and_tiny_batches(hall):
         if n:
             ref = g.Shoot(o, d)
             assert np.array_equal(got["poly_id"], ref["poly_id"]) and np.array_equal(got["t"], ref["t"])
+
+
+def test_wave_far_origins_and_scaled_directions(hall):
+    """The box cull works in FP32 around the current voxel's exit point: rays shot from 1e5 m / 1e9 m away, and rays with very
+    short or very long direction vectors, still give the oracle's events bit for bit."""
+    from tests.emu import wave_emu
+    T, g, ta, gi, csr = hall
+    o, d = rays_from_sources(2000, meshes.sources(4), stream=6)
+    for oo, dd in ((o - d * 1e5, d), (o - d * 1e9, d), (o, d * 1e-3), (o, d * 1e-30), (o, d * 1e6)):
+        ref = g.Shoot(oo, dd, nthreads=4)
+        got = wave_emu.run(ta, gi, csr, oo, dd, slots=64, wmax=8, n_warps=2)
+        for k in ("poly_id", "t", "xyz", "o"):
+            assert np.array_equal(got[k], ref[k]), k
