@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_build.hpp"
@@ -29,6 +30,17 @@ static std::vector<int> g_devices;   // empty = not initialised
 static bool g_host_only = false;     // hare_init(NULL, -1): build-time tooling without a device
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// host-side loops over polygons / nodes (record packing, bounding volumes): contiguous blocks on up to 16 threads
+template <class F>
+static void parallel_for(int64_t n, F&& body /* (begin, end, thread index) */) {
+    const int64_t kMinBlock = 1 << 15;
+    int nt = (int)std::min<int64_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u), (n + kMinBlock - 1) / kMinBlock);
+    if (nt <= 1) { body((int64_t)0, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int k = 0; k < nt; ++k) th.emplace_back([&, k] { body(n * k / nt, n * (k + 1) / nt, k); });
+    for (auto& x : th) x.join();
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -245,52 +257,48 @@ extern "C" int hare_topology_create(const double* verts, const double* normals, 
     std::memcpy(t->host.minmax, minmax, 6 * sizeof(double));
     for (int a = 0; a < 3; ++a) { t->host.vmin[a] = INFINITY; t->host.vmax[a] = -INFINITY; }
     std::vector<PolyRec> recs((size_t)P);
-    for (int64_t i = 0; i < P; ++i) {
-        for (int k = 0; k < 12; ++k) recs[i].v[k] = verts[12 * i + k];
-        if (vcount[i] == 3) for (int a = 0; a < 3; ++a) recs[i].v[9 + a] = verts[12 * i + 6 + a];
-        for (int a = 0; a < 3; ++a) recs[i].v[12 + a] = normals[3 * i + a];
-        recs[i].v[15] = (double)vcount[i];
-        for (int k = 0; k < vcount[i]; ++k)
-            for (int a = 0; a < 3; ++a) {
-                double c = verts[12 * i + 3 * k + a];
-                if (c < t->host.vmin[a]) t->host.vmin[a] = c;
-                if (c > t->host.vmax[a]) t->host.vmax[a] = c;
-            }
-    }
-    // padded bounding spheres in FP32 (centre of the vertex box, radius to the farthest vertex, padded by 1e-3 + 1e-5 relative,
-    // which covers the FP32 evaluation in cull_sphere()): a conservative reject used by the traversal
-    // kernels, stored right after the polygon records
     std::vector<float> sph((size_t)P * 4);
-    for (int64_t i = 0; i < P; ++i) {
-        double lo[3], hi[3];
-        for (int a = 0; a < 3; ++a) { lo[a] = hi[a] = verts[12 * i + a]; }
-        for (int k = 1; k < vcount[i]; ++k)
-            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], verts[12 * i + 3 * k + a]); hi[a] = std::max(hi[a], verts[12 * i + 3 * k + a]); }
-        float cf[3]; double r2 = 0;
-        for (int a = 0; a < 3; ++a) cf[a] = (float)(0.5 * (lo[a] + hi[a]));
-        for (int k = 0; k < vcount[i]; ++k) {
-            double q = 0;
-            for (int a = 0; a < 3; ++a) { double dlt = verts[12 * i + 3 * k + a] - (double)cf[a]; q += dlt * dlt; }
-            r2 = std::max(r2, q);
-        }
-        const double r = std::sqrt(r2) * (1.0 + 1e-5) + 1e-3;
-        float rf = (float)r;
-        while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
-        sph[4 * i] = cf[0]; sph[4 * i + 1] = cf[1]; sph[4 * i + 2] = cf[2]; sph[4 * i + 3] = rf;
-    }
-    t->sph = sph;
-    // padded FP32 bounding boxes (second conservative reject, cull_box): exact box -/+ hare_box_pad, rounded outwards
     t->pbox.resize((size_t)P * 6);
-    for (int64_t i = 0; i < P; ++i)
-        for (int a = 0; a < 3; ++a) {
-            double l = verts[12 * i + a], h = l;
-            for (int k = 1; k < vcount[i]; ++k) { l = std::min(l, verts[12 * i + 3 * k + a]); h = std::max(h, verts[12 * i + 3 * k + a]); }
-            const double pad = hare_box_pad(l, h);
-            float lo = (float)(l - pad), hi = (float)(h + pad);
-            while ((double)lo > l - pad) lo = std::nextafter(lo, -INFINITY);
-            while ((double)hi < h + pad) hi = std::nextafter(hi, INFINITY);
-            t->pbox[6 * i + a] = lo; t->pbox[6 * i + 3 + a] = hi;
+    double part_min[16][3], part_max[16][3];
+    for (int k = 0; k < 16; ++k) for (int a = 0; a < 3; ++a) { part_min[k][a] = INFINITY; part_max[k][a] = -INFINITY; }
+    parallel_for(P, [&](int64_t i0, int64_t i1, int tid) {
+        double* vmn = part_min[tid]; double* vmx = part_max[tid];
+        for (int64_t i = i0; i < i1; ++i) {
+            for (int k = 0; k < 12; ++k) recs[i].v[k] = verts[12 * i + k];
+            if (vcount[i] == 3) for (int a = 0; a < 3; ++a) recs[i].v[9 + a] = verts[12 * i + 6 + a];
+            for (int a = 0; a < 3; ++a) recs[i].v[12 + a] = normals[3 * i + a];
+            recs[i].v[15] = (double)vcount[i];
+            double lo[3], hi[3];
+            for (int a = 0; a < 3; ++a) { lo[a] = hi[a] = verts[12 * i + a]; }
+            for (int k = 1; k < vcount[i]; ++k)
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], verts[12 * i + 3 * k + a]); hi[a] = std::max(hi[a], verts[12 * i + 3 * k + a]); }
+            for (int a = 0; a < 3; ++a) { if (lo[a] < vmn[a]) vmn[a] = lo[a]; if (hi[a] > vmx[a]) vmx[a] = hi[a]; }
+            // padded bounding sphere in FP32 (centre of the vertex box, radius to the farthest vertex, padded by 1e-3 + 1e-5
+            // relative, which covers the FP32 evaluation in cull_sphere()): a conservative reject, stored right after the records
+            float cf[3]; double r2 = 0;
+            for (int a = 0; a < 3; ++a) cf[a] = (float)(0.5 * (lo[a] + hi[a]));
+            for (int k = 0; k < vcount[i]; ++k) {
+                double q = 0;
+                for (int a = 0; a < 3; ++a) { double dlt = verts[12 * i + 3 * k + a] - (double)cf[a]; q += dlt * dlt; }
+                r2 = std::max(r2, q);
+            }
+            const double r = std::sqrt(r2) * (1.0 + 1e-5) + 1e-3;
+            float rf = (float)r;
+            while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
+            sph[4 * i] = cf[0]; sph[4 * i + 1] = cf[1]; sph[4 * i + 2] = cf[2]; sph[4 * i + 3] = rf;
+            // padded FP32 bounding box (second conservative reject, cull_box): exact box -/+ hare_box_pad, rounded outwards
+            for (int a = 0; a < 3; ++a) {
+                const double pad = hare_box_pad(lo[a], hi[a]);
+                float bl = (float)(lo[a] - pad), bh = (float)(hi[a] + pad);
+                while ((double)bl > lo[a] - pad) bl = std::nextafter(bl, -INFINITY);
+                while ((double)bh < hi[a] + pad) bh = std::nextafter(bh, INFINITY);
+                t->pbox[6 * i + a] = bl; t->pbox[6 * i + 3 + a] = bh;
+            }
         }
+    });
+    for (int k = 0; k < 16; ++k)
+        for (int a = 0; a < 3; ++a) { t->host.vmin[a] = std::min(t->host.vmin[a], part_min[k][a]); t->host.vmax[a] = std::max(t->host.vmax[a], part_max[k][a]); }
+    t->sph = sph;
     { std::lock_guard<std::mutex> lk(g_mu); t->devs = g_devices; }
     for (int dev : t->devs) {
         PolyRec* d = nullptr;
@@ -541,16 +549,16 @@ static int oct_depth(const OctTree& t) {
     return best;
 }
 
-// per tree-list entry: the polygon's padded FP32 box with its id riding in lo.w (8 floats per entry)
-static std::vector<float> tree_entry_boxes(const std::vector<float>& pbox, const std::vector<uint32_t>& polys) {
-    std::vector<float> out(polys.size() * 8);
-    for (size_t k = 0; k < polys.size(); ++k) {
-        const float* q = &pbox[6 * (size_t)polys[k]];
-        float* r = &out[8 * k];
-        r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; std::memcpy(&r[3], &polys[k], 4);
-        r[4] = q[3]; r[5] = q[4]; r[6] = q[5]; r[7] = 0.f;
-    }
-    return out;
+// per tree-list entry: the polygon's padded FP32 box with its id riding in lo.w -- gathered on the device from the records
+// (same kernel as the Voxel_Grid cell lists)
+static int tree_entry_boxes(PartDev& d, size_t n_list) {
+    CK(dmalloc(&d.tbox, 2 * n_list));
+    if (n_list == 0) return HARE_OK;
+    vg_gather_list_box<<<(unsigned)((n_list + 255) / 256), 256, 0, d.stream[0]>>>(d.lists, d.polys, (uint32_t)n_list, d.tbox);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(d.stream[0]));
+    return HARE_OK;
 }
 
 static int oct_to_device(hare_part_s* p) {
@@ -606,7 +614,7 @@ static int oct_to_device(hare_part_s* p) {
     }
     // The same runs' boxes (union of the members' padded boxes), and one (box, polygon id) record per list entry.
     // Chunks are numbered as for csph (every leaf starts a multiple of 8); gbox[g] encloses chunks 8g .. 8g+7.
-    std::vector<float> cbox, gbox, lbox = tree_entry_boxes(p->topo->pbox, t.polys);
+    std::vector<float> cbox, gbox;
     const float kEmptyBox[8] = { INFINITY, INFINITY, INFINITY, 0.f, -INFINITY, -INFINITY, -INFINITY, 0.f };
     for (size_t i = 0; i < N; ++i) {
         if (t.first_child[i] >= 0) continue;
@@ -653,14 +661,14 @@ static int oct_to_device(hare_part_s* p) {
         CK(dmalloc(&d.lists, t.polys.size()));
         CK(dmalloc(&d.csph, csph.size() / 4));
         if (!csph.empty()) CK(cudaMemcpy(d.csph, csph.data(), csph.size() * 4, cudaMemcpyHostToDevice));
-        CK(dmalloc(&d.cbox, cbox.size() / 4)); CK(dmalloc(&d.tbox, lbox.size() / 4)); CK(dmalloc(&d.nbox, nbox.size() / 4));
+        CK(dmalloc(&d.cbox, cbox.size() / 4)); CK(dmalloc(&d.nbox, nbox.size() / 4));
         CK(cudaMemcpy(d.nbox, nbox.data(), nbox.size() * 4, cudaMemcpyHostToDevice));
         if (!cbox.empty()) CK(cudaMemcpy(d.cbox, cbox.data(), cbox.size() * 4, cudaMemcpyHostToDevice));
         CK(dmalloc(&d.gbox, gbox.size() / 4));
         if (!gbox.empty()) CK(cudaMemcpy(d.gbox, gbox.data(), gbox.size() * 4, cudaMemcpyHostToDevice));
-        if (!lbox.empty()) CK(cudaMemcpy(d.tbox, lbox.data(), lbox.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
+        { int r = tree_entry_boxes(d, t.polys.size()); if (r) return r; }
         d.bytes = N * sizeof(OctNode) + t.polys.size() * 36 + cbox.size() * 4 + csph.size() * 4;
     }
     return HARE_OK;
@@ -934,7 +942,6 @@ static int kd_to_device(hare_part_s* p) {
         if (t.left[i] >= 0) n.split = t.split[i];
         else { uint64_t bits = (uint64_t)t.list_off[i] | ((uint64_t)t.list_cnt[i] << 32); std::memcpy(&n.split, &bits, 8); }
     }
-    const std::vector<float> lbox = tree_entry_boxes(p->topo->pbox, t.polys);
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         KdNode* dn = nullptr;
@@ -942,8 +949,7 @@ static int kd_to_device(hare_part_s* p) {
         CK(dmalloc(&d.lists, t.polys.size()));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(KdNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
-        CK(dmalloc(&d.tbox, lbox.size() / 4));
-        if (!lbox.empty()) CK(cudaMemcpy(d.tbox, lbox.data(), lbox.size() * 4, cudaMemcpyHostToDevice));
+        { int r = tree_entry_boxes(d, t.polys.size()); if (r) return r; }
         d.bytes = N * sizeof(KdNode) + t.polys.size() * 36;
     }
     return HARE_OK;
