@@ -155,3 +155,25 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
     }
     return 0;
 }
+
+// ---- cull_box exactly as the kernels use it, for the property test of its conservativeness (tests/test_wave_emu.py) ----------
+// verts: n x 4 x 3 (a triangle repeats vertex 2), o/d: n x 3 rays, t_frame: n ray parameters of the FP32 frame point.
+// out[i] = 1 when the polygon's padded box is rejected for ray i.
+extern "C" void emu_cull_box(const double* verts, const int32_t* vcount, const double* o, const double* d, const double* t_frame, int64_t n,
+                             unsigned char* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            double l = verts[12 * i + a], h = l;
+            for (int q = 1; q < vcount[i]; ++q) { l = std::fmin(l, verts[12 * i + 3 * q + a]); h = std::fmax(h, verts[12 * i + 3 * q + a]); }
+            const double pad = hare_box_pad(l, h);
+            lo[a] = (float)(l - pad); while ((double)lo[a] > l - pad) lo[a] = std::nextafter(lo[a], -INFINITY);
+            hi[a] = (float)(h + pad); while ((double)hi[a] < h + pad) hi[a] = std::nextafter(hi[a], INFINITY);
+        }
+        const float fdx = (float)d[3 * i], fdy = (float)d[3 * i + 1], fdz = (float)d[3 * i + 2];
+        const float ix = cull_rcp(fdx), iy = cull_rcp(fdy), iz = cull_rcp(fdz);
+        const float px = (float)fma(d[3 * i], t_frame[i], o[3 * i]), py = (float)fma(d[3 * i + 1], t_frame[i], o[3 * i + 1]),
+                    pz = (float)fma(d[3 * i + 2], t_frame[i], o[3 * i + 2]);
+        out[i] = cull_box(make_float4(lo[0], lo[1], lo[2], 0.f), make_float4(hi[0], hi[1], hi[2], 0.f), px * ix, py * iy, pz * iz, ix, iy, iz) ? 1 : 0;
+    }
+}

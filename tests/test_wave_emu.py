@@ -80,3 +80,40 @@ def test_wave_far_origins_and_scaled_directions(hall):
         got = wave_emu.run(ta, gi, csr, oo, dd, slots=64, wmax=8, n_warps=2)
         for k in ("poly_id", "t", "xyz", "o"):
             assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("scale,size", [(1.0, 0.05), (30.0, 1.0), (30.0, 40.0), (1000.0, 0.02), (1000.0, 300.0)])
+def test_cull_box_never_rejects_a_polygon_the_ray_hits(scale, size):
+    """cull_box is not in the reference, so it must be conservative: for rays constructed THROUGH a point of the polygon, from
+    origins up to 2 km away, with the FP32 frame point anywhere between the origin and the far side of the model and with
+    axis-parallel directions mixed in, the padded box is never rejected.  (hare_box_pad: 1e-3 m + 1e-5 extent + 1e-6 |coordinate|.)"""
+    import ctypes as C
+    from tests.emu import wave_emu
+    L = wave_emu.lib()
+    rng = np.random.default_rng(int(scale * 7 + size * 1000))
+    n = 200_000
+    c = rng.uniform(-scale, scale, (n, 1, 3))
+    verts = c + rng.uniform(-size, size, (n, 4, 3))
+    vcount = rng.integers(3, 5, n).astype(np.int32)
+    verts[vcount == 3, 3] = verts[vcount == 3, 2]
+    # a point of the polygon: convex combination of its first three vertices
+    w = rng.dirichlet([1, 1, 1], n)
+    hitp = (verts[:, :3] * w[:, :, None]).sum(axis=1)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ax = rng.random(n) < 0.2                                        # 20 %: axis-parallel rays (zero direction components)
+    k = rng.integers(0, 3, n)
+    d[ax] = 0.0; d[ax, k[ax]] = rng.choice([-1.0, 1.0], int(ax.sum()))
+    d *= rng.choice([1.0, 0.37, 3.0], (n, 1))                       # reflected directions are not renormalised
+    dist = rng.choice([0.0, 1.0, 50.0, 2000.0], n) * rng.random(n)
+    o = hitp - d * dist[:, None]
+    t_frame = rng.random(n) * (dist / np.linalg.norm(d, axis=1) + rng.choice([0.0, 3.0 * scale], n))
+    out = np.zeros(n, np.uint8)
+    L.emu_cull_box(verts.ctypes.data_as(C.c_void_p), vcount.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                   t_frame.ctypes.data_as(C.c_void_p), C.c_int64(n), out.ctypes.data_as(C.c_void_p))
+    assert out.sum() == 0, f"{int(out.sum())} of {n} hit polygons rejected"
+    # ... and the test has teeth: the same rays moved sideways by 20 polygon sizes are mostly rejected
+    side = np.cross(d, rng.normal(size=(n, 3))); side /= np.linalg.norm(side, axis=1, keepdims=True) + 1e-300
+    o2 = o + side * (20.0 * size + 1.0)
+    L.emu_cull_box(verts.ctypes.data_as(C.c_void_p), vcount.ctypes.data_as(C.c_void_p), o2.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                   t_frame.ctypes.data_as(C.c_void_p), C.c_int64(n), out.ctypes.data_as(C.c_void_p))
+    assert out.mean() > 0.9
