@@ -93,7 +93,7 @@ struct PartDev {
     float4* list_box = nullptr;   // per list entry: padded FP32 bounding box + polygon id (VGrid::lbox; vg_wave.cuh's cull)
     // trees
     void* nodes = nullptr; uint32_t* lists = nullptr; float4* csph = nullptr;   // csph: octree chunk spheres
-    float4* cbox = nullptr; float4* gbox = nullptr; float4* tbox = nullptr; float4* nbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id); octree node content boxes
+    float4* cbox = nullptr; float4* gbox = nullptr; float4* tbox = nullptr; float4* nbox = nullptr; float4* pbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id); octree node content boxes
     // staging (per stream), sized for `cap` rays
     int64_t cap = 0;
     double *s_o[2] = {}, *s_d[2] = {}, *s_t[2] = {}, *s_xyz[2] = {}, *s_uv[2] = {}, *s_om[2] = {};
@@ -124,7 +124,7 @@ static void free_partdev(PartDev& d) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.pbox); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
@@ -551,10 +551,15 @@ static int oct_depth(const OctTree& t) {
 
 // per tree-list entry: the polygon's padded FP32 box with its id riding in lo.w -- gathered on the device from the records
 // (same kernel as the Voxel_Grid cell lists)
-static int tree_entry_boxes(PartDev& d, size_t n_list) {
-    CK(dmalloc(&d.tbox, 2 * n_list));
-    if (n_list == 0) return HARE_OK;
-    vg_gather_list_box<<<(unsigned)((n_list + 255) / 256), 256, 0, d.stream[0]>>>(d.lists, d.polys, (uint32_t)n_list, d.tbox);
+static int tree_entry_boxes(PartDev& d, size_t n_list, int64_t P, bool per_polygon) {
+    if (per_polygon) {   // one box per polygon, read by id
+        CK(dmalloc(&d.pbox, 2 * (size_t)P));
+        poly_box_table<<<(unsigned)((P + 255) / 256), 256, 0, d.stream[0]>>>(d.polys, (uint32_t)P, d.pbox);
+    } else {             // one (box, id) record per list entry, read in list order
+        CK(dmalloc(&d.tbox, 2 * n_list));
+        if (n_list == 0) return HARE_OK;
+        vg_gather_list_box<<<(unsigned)((n_list + 255) / 256), 256, 0, d.stream[0]>>>(d.lists, d.polys, (uint32_t)n_list, d.tbox);
+    }
     ++g_launches;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(d.stream[0]));
@@ -668,8 +673,8 @@ static int oct_to_device(hare_part_s* p) {
         if (!gbox.empty()) CK(cudaMemcpy(d.gbox, gbox.data(), gbox.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
-        { int r = tree_entry_boxes(d, t.polys.size()); if (r) return r; }
-        d.bytes = N * sizeof(OctNode) + t.polys.size() * 36 + cbox.size() * 4 + csph.size() * 4;
+        { int r = tree_entry_boxes(d, t.polys.size(), p->topo->host.P, HARE_OCT_ENTRY_PBOX != 0); if (r) return r; }
+        d.bytes = N * sizeof(OctNode) + t.polys.size() * (HARE_OCT_ENTRY_PBOX ? 4 : 36) + (HARE_OCT_ENTRY_PBOX ? (size_t)p->topo->host.P * 32 : 0) + cbox.size() * 4 + csph.size() * 4;
     }
     return HARE_OK;
 }
@@ -949,8 +954,8 @@ static int kd_to_device(hare_part_s* p) {
         CK(dmalloc(&d.lists, t.polys.size()));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(KdNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
-        { int r = tree_entry_boxes(d, t.polys.size()); if (r) return r; }
-        d.bytes = N * sizeof(KdNode) + t.polys.size() * 36;
+        { int r = tree_entry_boxes(d, t.polys.size(), p->topo->host.P, HARE_KD_ENTRY_PBOX != 0); if (r) return r; }
+        d.bytes = N * sizeof(KdNode) + t.polys.size() * (HARE_KD_ENTRY_PBOX ? 4 : 36) + (HARE_KD_ENTRY_PBOX ? (size_t)p->topo->host.P * 32 : 0);
     }
     return HARE_OK;
 }
@@ -1287,13 +1292,13 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.gbox, d.tbox, d.nbox, p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.gbox, d.tbox, d.pbox, d.nbox, p->oct.depth };
             if (use_oct_v1()) return launch_shoot_t(t, d, a, st);
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
         }
         case HARE_KDTREE: {
-            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.tbox, p->kd.depth };
+            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.tbox, d.pbox, p->kd.depth };
             if (use_kd_v1()) return launch_shoot_t(t, d, a, st);
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_kd_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
@@ -1330,13 +1335,13 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.gbox, d.tbox, d.nbox, p->oct.depth };
+            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.gbox, d.tbox, d.pbox, d.nbox, p->oct.depth };
             if (use_oct_v1()) return launch_chain_t(t, d, a, st);
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_KDTREE: {
-            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.tbox, p->kd.depth };
+            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.tbox, d.pbox, p->kd.depth };
             if (use_kd_v1()) return launch_chain_t(t, d, a, st);
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_kd_walk<true>(t, d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);

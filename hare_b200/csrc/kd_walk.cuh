@@ -23,6 +23,10 @@ namespace hare {
 #endif
 #define HARE_KD_CB 8
 // 1: leaf entries are culled on padded FP32 bounding boxes (cull_box; KdDev::lbox); 0: on spheres
+// 1: per-entry boxes come from the per-POLYGON table (KdDev::pbox, by id) instead of a per-entry copy (see oct_walk.cuh)
+#ifndef HARE_KD_ENTRY_PBOX
+#define HARE_KD_ENTRY_PBOX 0
+#endif
 #ifndef HARE_KD_BOX
 #define HARE_KD_BOX 1
 #endif
@@ -210,14 +214,26 @@ kd_walk_kernel(const KdDev T, const PolyRec* __restrict__ polys,
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float4 lo[4], hi[4];
+#if HARE_KD_ENTRY_PBOX
+                uint32_t ids[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ids[j] = __ldg(T.lists + lpos + (4 * h + j < (int)n ? 4 * h + j : 0));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float4* e = T.pbox + 2 * (size_t)ids[j]; lo[j] = __ldg(e); hi[j] = __ldg(e + 1); }
+#else
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4* e = T.lbox + 2 * (size_t)(lpos + (4 * h + j < (int)n ? 4 * h + j : 0));
                     lo[j] = __ldg(e); hi[j] = __ldg(e + 1);
                 }
+#endif
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+#if HARE_KD_ENTRY_PBOX
+                    const uint32_t i = ids[j];   // poly_origin skip (:220); mailbox: a polygon counts once (:224-229)
+#else
                     const uint32_t i = __float_as_uint(lo[j].w);   // poly_origin skip (:220); mailbox: a polygon counts once (:224-229)
+#endif
                     bid[4 * h + j] = i;
                     const bool keep = (4 * h + j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
                                       !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz);

@@ -364,6 +364,24 @@ vg_gather_list_box(const uint32_t* __restrict__ cell_poly, const PolyRec* __rest
     lbox[2 * (size_t)k + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
 }
 
+// per polygon: padded FP32 bounding box (lo, hi), indexed by polygon id (tree kernels, HARE_*_ENTRY_PBOX)
+__global__ void __launch_bounds__(256)
+poly_box_table(const PolyRec* __restrict__ polys, uint32_t P, float4* __restrict__ pbox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    double V[16];
+    load_poly(polys, i, V);
+    float lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double l = fmin(fmin(V[a], V[3 + a]), fmin(V[6 + a], V[9 + a])), h = fmax(fmax(V[a], V[3 + a]), fmax(V[6 + a], V[9 + a]));
+        const double pad = hare_box_pad(l, h);
+        lo[a] = __double2float_rd(l - pad); hi[a] = __double2float_ru(h + pad);
+    }
+    pbox[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+    pbox[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+}
+
 // host-uploaded CSR -> packed headers + occupancy
 __global__ void __launch_bounds__(256)
 vg_pack_cells(const uint32_t* __restrict__ cell_offset, long long ncells, uint2* __restrict__ cells, uint32_t* __restrict__ occ) {

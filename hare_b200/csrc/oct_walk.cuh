@@ -30,6 +30,11 @@ namespace hare {
 #ifndef HARE_OCT_BOX
 #define HARE_OCT_BOX 1
 #endif
+// 1: the per-entry box is read from the per-POLYGON table (OctDev::pbox, by id) instead of a per-entry copy: a dependent load, but
+// only for entries of the few chunks that survive, and the 32 bytes per list entry no longer compete for L2
+#ifndef HARE_OCT_ENTRY_PBOX
+#define HARE_OCT_ENTRY_PBOX 1
+#endif
 #ifndef HARE_OCT_THREADS
 #define HARE_OCT_THREADS 640
 #endif
@@ -257,14 +262,26 @@ oct_walk_kernel(const OctDev T, const PolyRec* __restrict__ polys,
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float4 lo[4], hi[4];
+#if HARE_OCT_ENTRY_PBOX
+                    uint32_t ids[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ids[j] = __ldg(T.lists + base + (4 * h + j < (int)n ? 4 * h + j : 0));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float4* e = T.pbox + 2 * (size_t)ids[j]; lo[j] = __ldg(e); hi[j] = __ldg(e + 1); }
+#else
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4* e = T.lbox + 2 * (size_t)(base + (4 * h + j < (int)n ? 4 * h + j : 0));
                         lo[j] = __ldg(e); hi[j] = __ldg(e + 1);
                     }
+#endif
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+#if HARE_OCT_ENTRY_PBOX
+                        const uint32_t i = ids[j];
+#else
                         const uint32_t i = __float_as_uint(lo[j].w);
+#endif
                         bid[4 * h + j] = i;
                         const bool keep = (4 * h + j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
                                           !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz);

@@ -240,7 +240,8 @@ struct OctDev {
     const float4* __restrict__ csph;  // one sphere per run of HARE_OCT_CHUNK consecutive leaf-list entries (leaf.pad = first chunk)
     const float4* __restrict__ cbox;  // the same runs' padded FP32 bounding boxes (lo, hi), see cull_box()
     const float4* __restrict__ gbox;  // boxes of groups of 8 runs (a leaf's first run is a multiple of 8): gbox[run / 8]
-    const float4* __restrict__ lbox;  // per leaf-list entry: its polygon's padded box, polygon id in lo.w
+    const float4* __restrict__ lbox;  // per leaf-list entry: its polygon's padded box, polygon id in lo.w (or null, see pbox)
+    const float4* __restrict__ pbox;  // per polygon: padded box (lo, hi), indexed by polygon id
     const float4* __restrict__ nbox;  // per node: padded FP32 box of every polygon listed below it (lo, hi); a ray whose line
                                       // misses it cannot be affected by the subtree, which is then not entered
     int depth;   // deepest level (root = 0)
@@ -370,6 +371,7 @@ struct KdDev {
     const uint32_t* __restrict__ lists;
     const float4* __restrict__ sph;   // padded bounding spheres, see cull_sphere()
     const float4* __restrict__ lbox;  // per leaf-list entry: its polygon's padded box, polygon id in lo.w (cull_box)
+    const float4* __restrict__ pbox;  // per polygon: padded box (lo, hi), indexed by polygon id
     int depth;
 };
 
