@@ -117,3 +117,22 @@ def test_cull_box_never_rejects_a_polygon_the_ray_hits(scale, size):
     L.emu_cull_box(verts.ctypes.data_as(C.c_void_p), vcount.ctypes.data_as(C.c_void_p), o2.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
                    t_frame.ctypes.data_as(C.c_void_p), C.c_int64(n), out.ctypes.data_as(C.c_void_p))
     assert out.mean() > 0.9
+
+
+def test_wave_degenerate_rays(hall):
+    """Zero, tiny and huge directions, -0.0 components (Q7), origins on vertices / on walls / far outside, rays that miss the
+    grid or fault at its boundary: the wavefront state machine gives the oracle's literal IEEE behaviour."""
+    from tests.emu import wave_emu
+    T, g, ta, gi, csr = hall
+    v = ta[0].reshape(-1, 3)
+    o = np.array([[15.0, 6.0, 5.0]] * 6 + [v[10], v[500], v[1500], [15.0, 6.0, 0.0], [1e6, 1e6, 1e6], [-1e3, 20.0, 8.0], [15.0, 6.0, 5.0], [15.0, 6.0, 5.0],
+                                          [-5.0, 6.0, 5.0], [15.0, 6.0, 5.0]], dtype=np.float64)
+    d = np.array([[0, 0, 0], [1e-30, 0, 0], [1e30, 2e30, -1e30], [1e-12, 1e-12, 1], [3, -4, 12], [1e-300, 1e-300, 1e-300],
+                  [0.3, 0.4, 0.5], [-0.3, 0.4, 0.5], [0.0, 0.0, 1.0], [0.6, 0.0, 0.8], [-1, -1, -1], [1, 0, 0], [0, -0.0, -1], [1, 1, 0],
+                  [-1, 0, 0], [-0.0, 1, 0]], dtype=np.float64)
+    assert o.shape == d.shape
+    ref = g.Shoot(o, d)
+    for slots, wmax in ((64, 8), (32, 4)):
+        got = wave_emu.run(ta, gi, csr, o, d, slots=slots, wmax=wmax, n_warps=1)
+        for k in ("poly_id", "t", "xyz", "o"):
+            assert np.array_equal(got[k], ref[k]), k
