@@ -78,7 +78,9 @@ def test_golden_vectors(gpu, name):
 
 
 # ---------------------------------------------------------------- procedural halls
-@pytest.mark.parametrize("level,domain,nrays", [("tiny", 8, 20_000), ("2k", 16, 50_000), ("10k", 32, 100_000), ("50k", 64, 200_000)])
+# 100^3: the occupancy bitmap only fits shared memory next to fewer ray pools (12 warps); 128^3: it does not fit at all (L1 path)
+@pytest.mark.parametrize("level,domain,nrays", [("tiny", 8, 20_000), ("2k", 16, 50_000), ("10k", 32, 100_000), ("50k", 64, 200_000),
+                                                ("50k", 100, 100_000), ("10k", 128, 100_000)])
 def test_hall_voxelgrid(gpu, level, domain, nrays):
     mesh = meshes.hall(level)
     T, To = _pair(gpu, mesh)
@@ -229,7 +231,7 @@ def test_upload_matches_build(gpu):
 
 
 # ---------------------------------------------------------------- reflection chains (C2 in small)
-@pytest.mark.parametrize("level,domain,nrays,order", [("2k", 16, 4_000, 20), ("10k", 32, 10_000, 50)])
+@pytest.mark.parametrize("level,domain,nrays,order", [("2k", 16, 4_000, 20), ("10k", 32, 10_000, 50), ("10k", 128, 4_000, 30)])
 def test_reflect_chain_voxelgrid(gpu, level, domain, nrays, order):
     mesh = meshes.hall(level)
     T, To = _pair(gpu, mesh)
