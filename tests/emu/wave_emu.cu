@@ -20,7 +20,7 @@ struct Stats { double exec[4] = { 0, 0, 0, 0 }, lanes[4] = { 0, 0, 0, 0 }, wstep
 
 template <bool CHAIN, int SLOTS, int W_MAX>
 void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d, const int32_t* o1a, const int32_t* o2a,
-         const int32_t* rid, long long N, int order, const WalkOut& out, int tw, Stats& st, unsigned long long* counters) {
+         const int32_t* rid, long long N, int order, const WalkOut& out, int tw, int wexit, Stats& st, unsigned long long* counters) {
     std::vector<unsigned char> mem(WavePool<SLOTS>::STRIDE + 64);
     CntT<true> c;
     unsigned long long total = 0;
@@ -45,9 +45,21 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
             } else if (ph == PH_C) {
                 for (int l = 0; l < cnt; ++l) nt[l] = wave_cull<true, SLOTS>(g, p, sel[l], c);
             } else if (ph == PH_W) {
-                unsigned mx = 0; bool anyhave = false;
+                if (wexit > 0) {
+                    // what-if: leave the walk loop as soon as fewer than `wexit` lanes are still stepping (lockstep replay, one
+                    // voxel step per lane and round; a lane's state survives in its slot, so W_MAX = 1 calls compose exactly)
+                    bool live[32];
+                    for (int l = 0; l < cnt; ++l) { live[l] = true; nt[l] = PH_W; }
+                    for (int r = 0; r < W_MAX; ++r) {
+                        int act = 0;
+                        for (int l = 0; l < cnt; ++l) if (live[l]) ++act;
+                        if (act == 0 || (r > 0 && act < wexit)) break;
+                        st.wsteps_warp += 1; st.wsteps_lane += act;
+                        for (int l = 0; l < cnt; ++l) if (live[l]) { nt[l] = wave_walk<true, SLOTS, 1>(g, g.occ, false, p, sel[l], c); live[l] = nt[l] == PH_W; }
+                    }
+                } else {
+                unsigned mx = 0;
                 for (int l = 0; l < cnt; ++l) {
-                    if (p.U(U_FLAGS, sel[l]) & WF_HAVE) { anyhave = true; st.whave_lane += 1; }
                     const unsigned before = c.cells;
                     const bool had = (p.U(U_FLAGS, sel[l]) & WF_HAVE) != 0;
                     nt[l] = wave_walk<true, SLOTS, W_MAX>(g, g.occ, false, p, sel[l], c);
@@ -55,7 +67,8 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
                     if (steps == 0 || (had && nt[l] == PH_SF)) steps += 1;   // an accept / exit iteration enters no cell
                     st.wsteps_lane += steps; if (steps > mx) mx = steps;
                 }
-                st.wsteps_warp += mx; if (anyhave) st.whave_exec += 1;
+                st.wsteps_warp += mx;
+                }
             } else {
                 for (int l = 0; l < cnt; ++l) wave_finish<CHAIN, true, SLOTS>(polys, p, sel[l], order, out, shots, c);
                 int rank = 0;
@@ -81,7 +94,7 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
 
 }  // namespace
 
-// Host arrays in, host arrays out.  slots in {40, 48, 64, 96}, wmax in {2, 4, 8}.  stats: 14 doubles
+// Host arrays in, host arrays out.  (slots, wmax) from the RUN list below; wexit > 0 = what-if replay of an adaptive walk exit.  stats: 14 doubles
 // (exec[4], lanes[4] in phase order SF, W, C, T; warp-level W iterations; lane-level W iterations; trips; 3 spare).
 extern "C" int wave_emu(const double* verts, const double* normals, const int32_t* vcount, int64_t P,
                         const double obox[6], const int32_t ct[3], const uint32_t* cell_offset, const uint32_t* cell_poly,
@@ -89,7 +102,7 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
                         int chain, int order,
                         double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
                         int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
-                        int slots, int wmax, int n_warps, int list_boxes, double* stats, unsigned long long* counters) {
+                        int slots, int wmax, int n_warps, int list_boxes, int wexit, double* stats, unsigned long long* counters) {
     std::vector<PolyRec> recs((size_t)P);
     std::vector<float4> sph((size_t)P);
     for (int64_t i = 0; i < P; ++i) {
@@ -143,10 +156,10 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
     g.lbox = list_boxes ? lbox.data() : nullptr;
     WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
     Stats st;
-#define RUN(S, W) if (slots == S && wmax == W) { if (chain) run<true, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, st, counters); \
-                                                 else run<false, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, st, counters); ok = 1; }
+#define RUN(S, W) if (slots == S && wmax == W) { if (chain) run<true, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, wexit, st, counters); \
+                                                 else run<false, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, wexit, st, counters); ok = 1; }
     int ok = 0;
-    RUN(40, 4) RUN(48, 4) RUN(64, 4) RUN(96, 4) RUN(64, 2) RUN(64, 8) RUN(48, 8) RUN(48, 2) RUN(32, 4)
+    RUN(40, 4) RUN(48, 4) RUN(64, 4) RUN(96, 4) RUN(64, 2) RUN(64, 8) RUN(48, 8) RUN(48, 2) RUN(32, 4) RUN(64, 16) RUN(96, 8)
 #undef RUN
     if (!ok) return -1;
     if (stats) {
