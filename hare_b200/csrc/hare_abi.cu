@@ -89,7 +89,7 @@ struct PartDev {
     cudaStream_t stream[2] = { nullptr, nullptr };
     const PolyRec* polys = nullptr;
     // voxel grid
-    uint2* cells = nullptr; uint32_t* cell_poly = nullptr; uint32_t* occ = nullptr; uint32_t* cell_offset = nullptr;
+    uint2* cells = nullptr; uint32_t* cell_poly = nullptr; uint32_t* occ = nullptr; uint32_t* occp = nullptr; uint32_t* cell_offset = nullptr;
     float4* list_box = nullptr;   // per list entry: padded FP32 bounding box + polygon id (VGrid::lbox; vg_wave.cuh's cull)
     // trees
     void* nodes = nullptr; uint32_t* lists = nullptr; float4* csph = nullptr;   // csph: octree chunk spheres
@@ -124,7 +124,7 @@ static void free_partdev(PartDev& d) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.pbox); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occp); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.pbox); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
@@ -346,7 +346,7 @@ static VGrid make_vgrid(const hare_part_s* p, const PartDev& d) {
     g.ominx = p->obox[0]; g.ominy = p->obox[1]; g.ominz = p->obox[2]; g.omaxx = p->obox[3]; g.omaxy = p->obox[4]; g.omaxz = p->obox[5];
     g.vdx = p->vd[0]; g.vdy = p->vd[1]; g.vdz = p->vd[2];
     g.nx = p->ct[0]; g.ny = p->ct[1]; g.nz = p->ct[2];
-    g.cells = d.cells; g.cell_poly = d.cell_poly; g.occ = d.occ;
+    g.cells = d.cells; g.cell_poly = d.cell_poly; g.occ = d.occ; g.occp = d.occp;
     g.sph = reinterpret_cast<const float4*>(d.polys + p->topo->host.P);   // spheres follow the records
     g.lbox = d.list_box;
     return g;
@@ -376,7 +376,16 @@ static int vg_set_dims(hare_part_s* p, const double obox[6], const int32_t ct[3]
 // HARE_VG_LBOX=0 leaves the per-entry boxes out (A/B measurements; 32 bytes per list entry); the cull then uses the spheres
 static bool use_lbox() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_LBOX"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
 
-static int vg_make_list_box(PartDev& d, uint32_t total, cudaStream_t st) {
+static int vg_make_list_box(PartDev& d, uint32_t total, cudaStream_t st, const int ct[3]) {
+    {   // the wavefront kernel's border-padded occupancy bitmap
+        const int64_t padded = ((int64_t)ct[0] + 2) * ((int64_t)ct[1] + 2) * ((int64_t)ct[2] + 2);
+        if (padded < (1LL << 32)) {
+            CK(dmalloc(&d.occp, (size_t)((padded + 31) / 32 + 1)));
+            vg_pad_occupancy<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(d.occ, ct[0], ct[1], ct[2], d.occp);
+            ++g_launches;
+            CK(cudaGetLastError());
+        }
+    }
     if (!use_lbox() || total == 0) return HARE_OK;
     CK(dmalloc(&d.list_box, 2 * (size_t)total));
     vg_gather_list_box<<<(unsigned)(((int64_t)total + 255) / 256), 256, 0, st>>>(d.cell_poly, d.polys, total, d.list_box);
@@ -431,7 +440,7 @@ extern "C" int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* o
             vg_finish_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(d.cell_offset, count, ncells, d.cell_poly, d.cells, d.occ);
             g_launches += 2;
             CK(cudaGetLastError());
-            r = vg_make_list_box(d, total, st);
+            r = vg_make_list_box(d, total, st, ct);
             if (r) return r;
             CK(cudaStreamSynchronize(st));
             cudaFree(count); cudaFree(cursor); cudaFree(tiles);
@@ -502,7 +511,7 @@ extern "C" int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], con
             vg_pack_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(d.cell_offset, ncells, d.cells, d.occ);
             ++g_launches;
             CK(cudaGetLastError());
-            int r = vg_make_list_box(d, total, st);
+            int r = vg_make_list_box(d, total, st, ct);
             if (r) return r;
             CK(cudaStreamSynchronize(st));
             d.bytes = (size_t)ncells * 12 + (size_t)total * (d.list_box ? 36 : 4) + (size_t)ncells / 8;
@@ -1202,16 +1211,16 @@ static int launch_vg_wave2(const VGrid& g, const PartDev& d, const double* o, co
 
 static const size_t kSmemMax = 227 * 1024;
 
-// the wavefront kernel packs voxel coordinates into 10 bits each, ray numbers into 32 and the bounce into 16
+// the wavefront kernel needs the padded bitmap (grids below 2^32 padded voxels), packs ray numbers into 32 bits and the bounce into 16
 static bool wave_eligible(const VGrid& g, int64_t N, int order) {
-    return use_wave() && g.nx <= 1024 && g.ny <= 1024 && g.nz <= 1024 && N < (1LL << 32) && order < 65536;
+    return use_wave() && g.occp && N < (1LL << 32) && order < 65536;
 }
 
 template <bool CHAIN>
 static int launch_vg_wave(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
                           const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
     const size_t pool = WavePool<HARE_WAVE_SLOTS>::STRIDE;
-    const size_t occ_bytes = ((((size_t)g.nx * g.ny * g.nz + 31) / 32 + 3) & ~(size_t)3) * 4;
+    const size_t occ_bytes = ((((size_t)(g.nx + 2) * (g.ny + 2) * (g.nz + 2) + 31) / 32 + 3) & ~(size_t)3) * 4;   // padded grid, see vg_wave.cuh
     // the occupancy bitmap rides in shared memory next to the pools; a larger grid gives up warps for it (down to half),
     // and beyond that the bitmap is read through L1
     int warps = HARE_WAVE_WARPS;

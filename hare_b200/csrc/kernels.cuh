@@ -382,6 +382,25 @@ poly_box_table(const PolyRec* __restrict__ polys, uint32_t P, float4* __restrict
     pbox[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
 }
 
+// occupancy bitmap of the grid padded by one voxel on every side: bit = list non-empty, or border voxel (vg_wave.cuh)
+__global__ void __launch_bounds__(256)
+vg_pad_occupancy(const uint32_t* __restrict__ occ, int nx, int ny, int nz, uint32_t* __restrict__ occp) {
+    const uint32_t py = (uint32_t)ny + 2u, pz = (uint32_t)nz + 2u;
+    const uint32_t total = ((uint32_t)nx + 2u) * py * pz;
+    const uint32_t cp = blockIdx.x * blockDim.x + threadIdx.x;
+    bool bit = false;
+    if (cp < total) {
+        const uint32_t xp = cp / (py * pz), r = cp - xp * py * pz, yp = r / pz, zp = r - yp * pz;
+        if (xp == 0 || xp == (uint32_t)nx + 1u || yp == 0 || yp == (uint32_t)ny + 1u || zp == 0 || zp == (uint32_t)nz + 1u) bit = true;
+        else {
+            const uint32_t ci = ((xp - 1u) * (uint32_t)ny + (yp - 1u)) * (uint32_t)nz + (zp - 1u);
+            bit = (occ[ci >> 5] >> (ci & 31)) & 1u;
+        }
+    }
+    const unsigned int bits = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31) == 0 && cp < total) occp[cp >> 5] = bits;
+}
+
 // host-uploaded CSR -> packed headers + occupancy
 __global__ void __launch_bounds__(256)
 vg_pack_cells(const uint32_t* __restrict__ cell_offset, long long ncells, uint2* __restrict__ cells, uint32_t* __restrict__ occ) {

@@ -119,6 +119,7 @@ struct VGrid {
     const uint2* __restrict__ cells;        // (offset, count) per cell, index ((x*ny+y)*nz+z)
     const uint32_t* __restrict__ cell_poly; // ascending polygon indices per cell
     const uint32_t* __restrict__ occ;       // 1 bit per cell: list non-empty
+    const uint32_t* __restrict__ occp;      // 1 bit per cell of the grid padded by one voxel on every side: list non-empty, or border (vg_wave.cuh)
     const float4* __restrict__ sph;         // per polygon: padded bounding sphere (cx, cy, cz, r), see cull_sphere()
     const float4* __restrict__ lbox;        // per LIST ENTRY (cell_poly order): padded FP32 bounding box (lo.xyz, polygon id in lo.w; hi.xyz), or null -- cull_box()
 };

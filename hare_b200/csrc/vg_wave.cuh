@@ -16,7 +16,7 @@
 // Phases (the arithmetic of each is the same, operation for operation, as in vg_walk.cuh / shoot_one, i.e.
 // Voxel_Grid.Shoot, Voxel_Grid.cs:351-552):
 //   SF  finish a Shoot (write the event, reflect), fetch a new ray if the slot is empty, DDA set-up
-//   W   up to W_MAX voxel steps (empty voxels skipped on the occupancy bitmap in shared memory)
+//   W   up to W_MAX voxel steps on the border-padded occupancy bitmap in shared memory (no coordinates, no bounds checks)
 //   C   next <= 4 list entries: ids + bounding spheres, FP32 conservative sphere cull
 //   T   one exact FP64 polygon test (128-byte record, Ray_Side, Moller-Trumbore)
 //
@@ -44,16 +44,13 @@ enum : uint32_t { FIN_RUN = 0, FIN_HIT = 1, FIN_MISS = 2, FIN_FAULT = 3 };
 enum { D_OX, D_OY, D_OZ, D_DX, D_DY, D_DZ, D_TMX, D_TMY, D_TMZ, D_TDX, D_TDY, D_TDZ, D_TMIN, D_TSTART, D_COUNT };
 // HARE_WAVE_BIDS = 1 keeps the ids of a culled batch's survivors in the slot (16 bytes); 0 re-reads them from the
 // cell list in T (the list position stays on the batch until its survivors are consumed)
-#ifndef HARE_WAVE_BRANCHY_STEP
-#define HARE_WAVE_BRANCHY_STEP 0
-#endif
 #ifndef HARE_WAVE_BIDS
 #define HARE_WAVE_BIDS 0
 #endif
 #if HARE_WAVE_BIDS
-enum { U_XYZ, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_BID0, U_BID1, U_BID2, U_BID3, U_COUNT };
+enum { U_XYZ /* padded voxel index cp */, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_BID0, U_BID1, U_BID2, U_BID3, U_COUNT };
 #else
-enum { U_XYZ, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_COUNT };
+enum { U_XYZ /* padded voxel index cp */, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_COUNT };
 #endif
 
 template <int SLOTS>
@@ -88,12 +85,38 @@ HD int wave_pick(const int n[PH_COUNT]) {
     return bn > 0 ? best : -1;
 }
 
-// is voxel ci occupied (for this ray)?  One bit per voxel, staged in shared memory when it fits.
-template <bool COUNT>
-HD bool wave_occupied(const uint32_t* occ, bool occ_smem, bool blind, uint32_t ci, CntT<COUNT>& c) {
-    c.cell();
-    const uint32_t word = occ_smem ? occ[ci >> 5] : hare_ldg(occ + (ci >> 5));
-    return !blind && ((word >> (ci & 31)) & 1u);
+// The walk addresses voxels by their index in a grid PADDED by one voxel on every side, cp = ((X+1)*(ny+2) + (Y+1))*(nz+2) + (Z+1),
+// and tests one bit per padded voxel (VGrid::occp: list non-empty, or border).  Leaving the grid then shows up as a set bit, so a
+// voxel step needs neither the three coordinates nor their bounds checks; coordinates are decoded from cp only where they are
+// needed (an occupied voxel, the border, the in-voxel test of a carried candidate).
+struct WaveGeom { uint32_t d1, pz; double inv1, inv2; };   // d1 = (ny+2)*(nz+2), pz = nz+2 and their reciprocals
+
+HD WaveGeom wave_geom(const VGrid& g) {
+    WaveGeom w;
+    w.pz = (uint32_t)g.nz + 2u; w.d1 = ((uint32_t)g.ny + 2u) * w.pz;
+    w.inv1 = 1.0 / (double)w.d1; w.inv2 = 1.0 / (double)w.pz;
+    return w;
+}
+
+HD uint32_t wave_cp(const VGrid& g, int X, int Y, int Z) {
+    return ((uint32_t)(X + 1) * ((uint32_t)g.ny + 2u) + (uint32_t)(Y + 1)) * ((uint32_t)g.nz + 2u) + (uint32_t)(Z + 1);
+}
+
+// cp -> unpadded coordinates (-1 or n on the border).  The FP64 quotient is off by at most one; the remainder fixes it.
+HD void wave_decode(const WaveGeom& w, uint32_t cp, int& X, int& Y, int& Z) {
+    uint32_t xp = (uint32_t)((double)cp * w.inv1);
+    int32_t r = (int32_t)(cp - xp * w.d1);
+    if (r < 0) { --xp; r += (int32_t)w.d1; } else if ((uint32_t)r >= w.d1) { ++xp; r -= (int32_t)w.d1; }
+    uint32_t yp = (uint32_t)((double)r * w.inv2);
+    int32_t z = r - (int32_t)(yp * w.pz);
+    if (z < 0) { --yp; z += (int32_t)w.pz; } else if ((uint32_t)z >= w.pz) { ++yp; z -= (int32_t)w.pz; }
+    X = (int)xp - 1; Y = (int)yp - 1; Z = (int)z - 1;
+}
+
+// bit of padded voxel cp: one bit per voxel, staged in shared memory when it fits
+HD bool wave_bit(const uint32_t* occ, bool occ_smem, uint32_t cp) {
+    const uint32_t word = occ_smem ? occ[cp >> 5] : hare_ldg(occ + (cp >> 5));
+    return (word >> (cp & 31)) & 1u;
 }
 
 // ---- SF, part 1: the Shoot in slot s is over -> write its event; a chain reflects and goes on, or ends.
@@ -169,7 +192,7 @@ HD void wave_fetch(const WavePool<SLOTS>& p, int s, long long ray, const double*
 
 // ---- SF, part 3: DDA set-up of the ray in slot s   Voxel_Grid.cs:357-422.  Returns the slot's new tag.
 template <bool COUNT, int SLOTS>
-HD uint32_t wave_setup(const VGrid& g, const uint32_t* occ, bool occ_smem, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
+HD uint32_t wave_setup(const VGrid& g, const uint32_t* occ, bool occ_smem, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {   // occ = g.occp or its shared-memory copy
     uint32_t fl = p.U(U_FLAGS, s) & (WF_BLIND | (0xffffu << WF_BOUNCE_SHIFT));
     Ray3 R = { p.D(D_OX, s), p.D(D_OY, s), p.D(D_OZ, s), p.D(D_DX, s), p.D(D_DY, s), p.D(D_DZ, s) };
     double t_start = 0;
@@ -198,9 +221,13 @@ HD uint32_t wave_setup(const VGrid& g, const uint32_t* occ, bool occ_smem, const
         p.D(D_TDX, s) = g.vdx / R.dx * (nx_ ? -1.0 : 1.0);
         p.D(D_TDY, s) = g.vdy / R.dy * (ny_ ? -1.0 : 1.0);
         p.D(D_TDZ, s) = g.vdz / R.dz * (nz_ ? -1.0 : 1.0);
-        p.U(U_XYZ, s) = (uint32_t)X | ((uint32_t)Y << 10) | ((uint32_t)Z << 20);
-        const uint32_t ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
-        if (wave_occupied<COUNT>(occ, occ_smem, (fl & WF_BLIND) != 0, ci, c)) { const uint2 h = hare_ldg(g.cells + ci); lpos = h.x; lend = h.x + h.y; }
+        const uint32_t cp = wave_cp(g, X, Y, Z);
+        p.U(U_XYZ, s) = cp;
+        c.cell();
+        if (!(fl & WF_BLIND) && wave_bit(occ, occ_smem, cp)) {
+            const uint32_t ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
+            const uint2 h = hare_ldg(g.cells + ci); lpos = h.x; lend = h.x + h.y;
+        }
     }
     fl |= fin << WF_FIN_SHIFT;
     p.U(U_FLAGS, s) = fl; p.U(U_LPOS, s) = lpos; p.U(U_LEND, s) = lend;
@@ -209,57 +236,62 @@ HD uint32_t wave_setup(const VGrid& g, const uint32_t* occ, bool occ_smem, const
 
 // ---- W: the slot's list is exhausted -> accept the carried candidate or step the 3D-DDA (<= W_MAX voxels)
 template <bool COUNT, int SLOTS, int W_MAX>
-HD uint32_t wave_walk(const VGrid& g, const uint32_t* occ, bool occ_smem, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
+HD uint32_t wave_walk(const VGrid& g, const WaveGeom& w, const uint32_t* occ, bool occ_smem, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
     uint32_t fl = p.U(U_FLAGS, s);
     const Ray3 R = { p.D(D_OX, s), p.D(D_OY, s), p.D(D_OZ, s), p.D(D_DX, s), p.D(D_DY, s), p.D(D_DZ, s) };
     double tMaxX = p.D(D_TMX, s), tMaxY = p.D(D_TMY, s), tMaxZ = p.D(D_TMZ, s);
     const double tDeltaX = p.D(D_TDX, s), tDeltaY = p.D(D_TDY, s), tDeltaZ = p.D(D_TDZ, s);
-    const uint32_t xyz = p.U(U_XYZ, s);
-    int X = (int)(xyz & 1023u), Y = (int)((xyz >> 10) & 1023u), Z = (int)(xyz >> 20);
-    const int stepX = (fl & WF_NEGX) ? -1 : 1, stepY = (fl & WF_NEGY) ? -1 : 1, stepZ = (fl & WF_NEGZ) ? -1 : 1;
-    const int sX = stepX * g.ny * g.nz, sY = stepY * g.nz;
-    uint32_t ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
+    uint32_t cp = p.U(U_XYZ, s);
+    const int sX = (fl & WF_NEGX) ? -(int)w.d1 : (int)w.d1, sY = (fl & WF_NEGY) ? -(int)w.pz : (int)w.pz, sZ = (fl & WF_NEGZ) ? -1 : 1;
     const bool have = (fl & WF_HAVE) != 0, blind = (fl & WF_BLIND) != 0;
     double bx = 0, by = 0, bz = 0;
     if (have) { const double tmin = p.D(D_TMIN, s); bx = R.x + R.dx * tmin; by = R.y + R.dy * tmin; bz = R.z + R.dz * tmin; }
     uint32_t fin = FIN_RUN, lpos = 0, lend = 0;
-    bool found = false;
+    bool stop = false;   // the walk ended on a set bit: an occupied voxel or the border
 #pragma unroll 1
     for (int guard = 0; guard < W_MAX; ++guard) {
         // list exhausted: Voxels[X,Y,Z].IsPointInBox(candidate)?   Voxel_Grid.cs:496-500
         if (have) {
+            int X, Y, Z;
+            wave_decode(w, cp, X, Y, Z);
             const bool in = !(bx < vox_min(X, g.vdx, g.ominx)) & !(by < vox_min(Y, g.vdy, g.ominy)) & !(bz < vox_min(Z, g.vdz, g.ominz)) &
                             !(bx > vox_max(X, g.vdx, g.ominx)) & !(by > vox_max(Y, g.vdy, g.ominy)) & !(bz > vox_max(Z, g.vdz, g.ominz));
             if (in) { fin = FIN_HIT; break; }
         }
         // next voxel   Voxel_Grid.cs:504-550: X only if strictly below both, Y only if below Z, else Z
-        bool oob;
-#if HARE_WAVE_BRANCHY_STEP
-        if (tMaxX < tMaxY && tMaxX < tMaxZ) { tMaxX = tMaxX + tDeltaX; X += stepX; ci += (uint32_t)sX; oob = (unsigned)X >= (unsigned)g.nx; }
-        else if (!(tMaxX < tMaxY) && tMaxY < tMaxZ) { tMaxY = tMaxY + tDeltaY; Y += stepY; ci += (uint32_t)sY; oob = (unsigned)Y >= (unsigned)g.ny; }
-        else { tMaxZ = tMaxZ + tDeltaZ; Z += stepZ; ci += (uint32_t)stepZ; oob = (unsigned)Z >= (unsigned)g.nz; }
-#else
         {
             const bool xy = tMaxX < tMaxY, xz = tMaxX < tMaxZ, yz = tMaxY < tMaxZ;
             const bool goX = xy & xz, goY = (!xy) & yz;
             const bool goZ = !(goX | goY);
             const double nX = tMaxX + tDeltaX, nY = tMaxY + tDeltaY, nZ = tMaxZ + tDeltaZ;
             tMaxX = goX ? nX : tMaxX; tMaxY = goY ? nY : tMaxY; tMaxZ = goZ ? nZ : tMaxZ;
-            X += goX ? stepX : 0; Y += goY ? stepY : 0; Z += goZ ? stepZ : 0;
-            ci += (uint32_t)(goX ? sX : (goY ? sY : stepZ));
-            oob = (unsigned)X >= (unsigned)g.nx || (unsigned)Y >= (unsigned)g.ny || (unsigned)Z >= (unsigned)g.nz;
+            cp += (uint32_t)(goX ? sX : (goY ? sY : sZ));
         }
-#endif
-        if (oob) { fin = FIN_MISS; break; }
-        // an occupied voxel ends the walk; its list header is fetched once, after the loop (no L2 round trip per step)
-        found = wave_occupied<COUNT>(occ, occ_smem, blind, ci, c);
-        if (found) break;
+        c.cell();
+        // a set bit ends the walk: an occupied voxel (its list header is fetched once, after the loop) or the border.  A blind
+        // ray (Ray_ID == 0) ignores lists, so only the border stops it.
+        if (wave_bit(occ, occ_smem, cp)) {
+            if (!blind) { stop = true; break; }
+            int X, Y, Z;
+            wave_decode(w, cp, X, Y, Z);
+            if ((unsigned)X >= (unsigned)g.nx || (unsigned)Y >= (unsigned)g.ny || (unsigned)Z >= (unsigned)g.nz) { stop = true; break; }
+        }
     }
-    if (found) { const uint2 h = hare_ldg(g.cells + ci); lpos = h.x; lend = h.x + h.y; }
+    if (stop) {
+        int X, Y, Z;
+        wave_decode(w, cp, X, Y, Z);
+        if ((unsigned)X >= (unsigned)g.nx || (unsigned)Y >= (unsigned)g.ny || (unsigned)Z >= (unsigned)g.nz) {
+            fin = FIN_MISS;                       // left the grid: a miss even if a candidate is held (Voxel_Grid.cs:509-513)
+            if (COUNT) --c.cells;                 // the reference never enters that voxel
+        } else {
+            const uint32_t ci = ((uint32_t)X * (uint32_t)g.ny + (uint32_t)Y) * (uint32_t)g.nz + (uint32_t)Z;
+            const uint2 h = hare_ldg(g.cells + ci); lpos = h.x; lend = h.x + h.y;
+        }
+    }
     fl |= fin << WF_FIN_SHIFT;
     if (fin == FIN_RUN) {
         p.D(D_TMX, s) = tMaxX; p.D(D_TMY, s) = tMaxY; p.D(D_TMZ, s) = tMaxZ;
-        p.U(U_XYZ, s) = (uint32_t)X | ((uint32_t)Y << 10) | ((uint32_t)Z << 20);
+        p.U(U_XYZ, s) = cp;
         p.U(U_LPOS, s) = lpos; p.U(U_LEND, s) = lend;
     } else {
         p.U(U_FLAGS, s) = fl;
@@ -379,11 +411,12 @@ vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
     uint32_t* s_occ = reinterpret_cast<uint32_t*>(s_raw);
     uint32_t occ_words = 0;
     if (OCC_SMEM) {
-        occ_words = ((uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz + 31u) >> 5;
-        for (uint32_t w = threadIdx.x; w < occ_words; w += blockDim.x) s_occ[w] = __ldg(g.occ + w);
+        occ_words = (((uint32_t)g.nx + 2u) * ((uint32_t)g.ny + 2u) * ((uint32_t)g.nz + 2u) + 31u) >> 5;
+        for (uint32_t w = threadIdx.x; w < occ_words; w += blockDim.x) s_occ[w] = __ldg(g.occp + w);
         occ_words = (occ_words + 3u) & ~3u;
     }
-    const uint32_t* occ = OCC_SMEM ? s_occ : g.occ;
+    const uint32_t* occ = OCC_SMEM ? s_occ : g.occp;
+    const WaveGeom wg = wave_geom(g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WavePool<SLOTS> p;
     p.bind(s_raw + (size_t)occ_words * 4 + (size_t)warp * WavePool<SLOTS>::STRIDE);
@@ -435,7 +468,7 @@ vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
         } else if (ph == PH_C) {
             if (act) nt = wave_cull<COUNT, SLOTS>(g, p, s, c);
         } else if (ph == PH_W) {
-            if (act) nt = wave_walk<COUNT, SLOTS, W_MAX>(g, occ, OCC_SMEM, p, s, c);
+            if (act) nt = wave_walk<COUNT, SLOTS, W_MAX>(g, wg, occ, OCC_SMEM, p, s, c);
         } else {
             if (act) wave_finish<CHAIN, COUNT, SLOTS>(polys, p, s, order, out, shots, c);
             const bool noray = act && (p.U(U_FLAGS, s) & WF_NORAY);

@@ -23,6 +23,7 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
          const int32_t* rid, long long N, int order, const WalkOut& out, int tw, int wexit, Stats& st, unsigned long long* counters) {
     std::vector<unsigned char> mem(WavePool<SLOTS>::STRIDE + 64);
     CntT<true> c;
+    const WaveGeom wg = wave_geom(g);
     unsigned long long total = 0;
     for (long long gw = 0; gw < tw; ++gw) {
         WavePool<SLOTS> p;
@@ -55,14 +56,14 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
                         for (int l = 0; l < cnt; ++l) if (live[l]) ++act;
                         if (act == 0 || (r > 0 && act < wexit)) break;
                         st.wsteps_warp += 1; st.wsteps_lane += act;
-                        for (int l = 0; l < cnt; ++l) if (live[l]) { nt[l] = wave_walk<true, SLOTS, 1>(g, g.occ, false, p, sel[l], c); live[l] = nt[l] == PH_W; }
+                        for (int l = 0; l < cnt; ++l) if (live[l]) { nt[l] = wave_walk<true, SLOTS, 1>(g, wg, g.occp, false, p, sel[l], c); live[l] = nt[l] == PH_W; }
                     }
                 } else {
                 unsigned mx = 0;
                 for (int l = 0; l < cnt; ++l) {
                     const unsigned before = c.cells;
                     const bool had = (p.U(U_FLAGS, sel[l]) & WF_HAVE) != 0;
-                    nt[l] = wave_walk<true, SLOTS, W_MAX>(g, g.occ, false, p, sel[l], c);
+                    nt[l] = wave_walk<true, SLOTS, W_MAX>(g, wg, g.occp, false, p, sel[l], c);
                     unsigned steps = c.cells - before;
                     if (steps == 0 || (had && nt[l] == PH_SF)) steps += 1;   // an accept / exit iteration enters no cell
                     st.wsteps_lane += steps; if (steps > mx) mx = steps;
@@ -80,7 +81,7 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
                         if (ray < N) wave_fetch<SLOTS>(p, sel[l], ray, o, d, o1a, o2a, rid);
                         else ready = false;
                     }
-                    nt[l] = ready ? wave_setup<true, SLOTS>(g, g.occ, false, p, sel[l], c) : (uint32_t)PH_DONE;
+                    nt[l] = ready ? wave_setup<true, SLOTS>(g, g.occp, false, p, sel[l], c) : (uint32_t)PH_DONE;
                 }
                 cur += rank;
             }
@@ -138,7 +139,16 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
     g.ominx = obox[0]; g.ominy = obox[1]; g.ominz = obox[2]; g.omaxx = obox[3]; g.omaxy = obox[4]; g.omaxz = obox[5];
     g.vdx = (obox[3] - obox[0]) / ct[0]; g.vdy = (obox[4] - obox[1]) / ct[1]; g.vdz = (obox[5] - obox[2]) / ct[2];
     g.nx = ct[0]; g.ny = ct[1]; g.nz = ct[2];
-    g.cells = cells.data(); g.cell_poly = cell_poly; g.occ = occ.data(); g.sph = sph.data();
+    // border-padded occupancy bitmap, as vg_pad_occupancy makes it
+    const int64_t px = ct[0] + 2, py = ct[1] + 2, pz = ct[2] + 2;
+    std::vector<uint32_t> occp((size_t)(px * py * pz + 31) / 32 + 1, 0u);
+    for (int64_t xp = 0; xp < px; ++xp) for (int64_t yp = 0; yp < py; ++yp) for (int64_t zp = 0; zp < pz; ++zp) {
+        const int64_t cp = (xp * py + yp) * pz + zp;
+        bool bit = xp == 0 || xp == px - 1 || yp == 0 || yp == py - 1 || zp == 0 || zp == pz - 1;
+        if (!bit) { const int64_t ci = ((xp - 1) * ct[1] + (yp - 1)) * ct[2] + (zp - 1); bit = cells[ci].y != 0; }
+        if (bit) occp[cp >> 5] |= 1u << (cp & 31);
+    }
+    g.cells = cells.data(); g.cell_poly = cell_poly; g.occ = occ.data(); g.occp = occp.data(); g.sph = sph.data();
     // per-entry padded boxes with the id in lo.w, as vg_gather_list_box makes them
     std::vector<float4> lbox(2 * (size_t)cell_offset[ncells] + 2);
     for (uint32_t k = 0; k < cell_offset[ncells]; ++k) {
