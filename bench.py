@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- Mrays/s of closest-hit Shoot on BASELINE.json's configs[1] (C2):
-procedural auditorium (~50k polygons), Voxel_Grid, 10M rays x 50-order specular chains.
+"""bench.py -- Mrays/s of closest-hit Shoot on the BASELINE.json configurations.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path, default --config C3
+    python bench.py --impl reference --gpus N --steps K ...       # the CPU restatement of the reference, same config
 
-One "step" = one pass of the hot path over the whole ray batch: every ray's chain of up to
-`order` Shoots (each bounce is one Shoot).  `value` is device-resident
-throughput (rays already in HBM), `e2e` goes through the host-buffer C-ABI call
-(hare_reflect_chain) with the H2D / D2H copies inside the timed region.
+Configurations (`--config`):
+    C3   (default) hall-500k, Octree(Model, 7, 32), 100 M rays in total, one Shoot each.  The batch is block-sharded over
+         the N ranks (STRONG scaling); every rank's traversal kernel stores its X_Event rows (poly_id, t, X_Point, u, v = 52 B)
+         straight into rank 0's buffers over NVLink inside the timed region -- the path's only cross-GPU step.
+    C2   hall-50k, Voxel_Grid 64^3, 10 M rays x 50-order specular chains per GPU (weak scaling).
+    C4vg / C4kd   hall-2m, Voxel_Grid 256^3 / KDTree(24, 16), 100 M rays.
+    C5   Voxel_Grid build: 2 M polygons -> 256^3 cell lists (count / scan / scatter).
+    C1   shoebox, Voxel_Grid 10^3, 100 k rays: parity configuration; also prints the boundary's cliffs (single-ray Shoot
+         latency, pageable vs page-locked hare_shoot_batch).
+At N = 1 the default run appends short C2 / C4 / C5 / C1 lines under "other_configs" (--no-extras skips them).
 
-For N > 1 (torchrun, one rank per GPU) the geometry is replicated, every rank owns its own
-batch of `--rays` chains (weak scaling) and the per-chain results are gathered to rank 0 over
-NCCL inside the timed region (the path's only cross-GPU step).
+One "step" = one pass of the hot path over the whole ray batch.  `value` is device-resident throughput (rays already in
+HBM, CUDA events, max over ranks); `e2e` goes through the host-buffer C-ABI call (hare_shoot_batch / hare_reflect_chain,
+page-locked host arrays) with the H2D / D2H copies inside the timed region.  Before a line is printed the GPU results of
+the first rays are compared bit for bit with the oracle's (the same run that is timed as cpu_baseline).
 """
 import argparse
 import ctypes as C
@@ -29,6 +35,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PEAKS_FALLBACK_HBM = 6650.0   # GB/s, B200_PROFILING.md fallback
+METRIC = "Mrays/s closest-hit Shoot"
+
+CONFIGS = {
+    # kind, mesh level, partition, ctor args, rays, ray stream, sources, scaling, CPU sample cap, parity sample floor
+    "C1": dict(kind="shoot", mesh="shoebox", part="Voxel_Grid", args=(10,), rays=100_000, stream=1, nsrc=1, scaling="strong", cpu_cap=100_000, cpu_min=100_000),
+    "C2": dict(kind="chain", mesh="50k", part="Voxel_Grid", args=(64,), rays=10_000_000, order=50, stream=2, nsrc=4, scaling="weak", cpu_cap=400_000, cpu_min=20_000),
+    "C3": dict(kind="shoot", mesh="500k", part="Octree", args=(7, 32), rays=100_000_000, stream=3, nsrc=8, scaling="strong", cpu_cap=4_000_000, cpu_min=200_000),
+    "C4vg": dict(kind="shoot", mesh="2m", part="Voxel_Grid", args=(256,), rays=100_000_000, stream=4, nsrc=8, scaling="strong", cpu_cap=4_000_000, cpu_min=200_000),
+    "C4kd": dict(kind="shoot", mesh="2m", part="KDTree", args=(24, 16), rays=100_000_000, stream=4, nsrc=8, scaling="strong", cpu_cap=20_000, cpu_min=2_000),
+    "C5": dict(kind="build", mesh="2m", part="Voxel_Grid", args=(256,), scaling="strong"),
+}
+HEADER_BYTES = {"Voxel_Grid": 8, "Octree": 64, "KDTree": 16}     # h of SURVEY.md 8(d)
+EVENT_BYTES = {"Voxel_Grid": 36, "Octree": 52, "KDTree": 52}    # E
 
 
 def parse():
@@ -37,38 +56,54 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=int, default=10_000_000, help="chains per GPU per step (C2: 10M)")
-    ap.add_argument("--order", type=int, default=50)
-    ap.add_argument("--mesh", default="50k")
-    ap.add_argument("--domain", type=int, default=64, help="Voxel_Grid Domain (C2 sweeps 32/64/96)")
-    ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs: skip the CPU leg")
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--rays", type=int, default=None, help="override the configuration's ray count (C2: per GPU; others: total)")
+    ap.add_argument("--order", type=int, default=None)
+    ap.add_argument("--mesh", default=None)
+    ap.add_argument("--args", type=int, nargs="+", default=None, help="override the partition's constructor arguments")
+    ap.add_argument("--part", default=None, choices=["Voxel_Grid", "Octree", "KDTree"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs: skip the CPU leg (and with it the parity gate)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--no-extras", action="store_true", help="do not append the short lines of the other configurations at N = 1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer stores into rank 0 (default) or NCCL gather after the kernel")
     return ap.parse_args()
 
 
-def ncu_traffic(args):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the traversal kernel, per launch, from the committed
-    `ncu --set full` capture of this same configuration (profiles/); None for any other configuration."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_bench_kernel.json")
-    try:
-        j = json.load(open(p))
-        c = j["config"]
-        if (c["mesh"], c["domain"], c["rays"], c["order"]) == (args.mesh, args.domain, args.rays, args.order):
-            return float(j["traffic_bytes_per_launch"])
-    except Exception:
-        pass
-    return None
+def cfg_of(args, name=None):
+    c = dict(CONFIGS[name or args.config])
+    c["name"] = name or args.config
+    if name is None:   # overrides only apply to the configuration named on the command line
+        for k in ("rays", "order", "mesh", "part"):
+            if getattr(args, k) is not None:
+                c[k] = getattr(args, k)
+        if args.args is not None:
+            c["args"] = tuple(args.args)
+    return c
 
 
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured"
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return PEAKS_FALLBACK_HBM, "fallback"
+    return PEAKS_FALLBACK_HBM, "fallback (B200_PROFILING.md)"
+
+
+def ncu_actual(cfg):
+    """Counters of the dominant kernel from the committed `ncu --set full` capture of this configuration at HEAD
+    (profiles/r2_ncu_<config>.json, written by tools/ncu_kernel_json.py), or None."""
+    p = os.path.join(ROOT, "profiles", f"r2_ncu_{cfg['name']}.json")
+    try:
+        j = json.load(open(p))
+    except Exception:
+        return None
+    c = j.get("config", {})
+    if (c.get("mesh"), c.get("part"), tuple(c.get("args", ()))) != (cfg["mesh"], cfg["part"], tuple(cfg["args"])):
+        return None
+    return j
 
 
 class ClockSampler:
@@ -81,7 +116,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -113,239 +148,549 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(args, rank):
-    from hare_b200.harness import meshes, rays_from_sources
-    mesh = meshes.hall(args.mesh)
-    # rank r shoots its own block of the global ray sequence (streams 2..5 = the four sources of C2)
-    o, d = rays_from_sources(args.rays, meshes.sources(4), stream=2, first=rank * args.rays)
-    return mesh, o, d
+# --------------------------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------------------------
+def get_mesh(cfg):
+    from hare_b200.harness import meshes
+    return meshes.shoebox() if cfg["mesh"] == "shoebox" else meshes.hall(cfg["mesh"])
 
 
-def algorithmic_bytes(counters, shots, kind="Voxel_Grid"):
-    """B = 56 + E + h*C + 4*L + 128*T per Shoot, C/L/T counted by the CPU oracle."""
-    E, h = (36, 8) if kind == "Voxel_Grid" else (52, 64)
-    C_, L_, T_ = (float(counters[k]) / shots for k in range(3))
-    return 56 + E + h * C_ + 4 * L_ + 128 * T_, dict(cells=C_, entries=L_, tests=T_)
+def get_sources(cfg):
+    from hare_b200.harness import meshes
+    return np.array([[5.0, 3.5, 1.5]]) if cfg["mesh"] == "shoebox" else meshes.sources(cfg["nsrc"])
 
 
-def cpu_leg(args, mesh, o, d, seconds, nthreads):
-    """Time the oracle (C++ restatement of the reference's CPU path) on a bounded sample."""
+def shard(cfg, rank, world):
+    """[lo, hi) of the global ray sequence this rank shoots."""
+    if cfg["scaling"] == "weak":
+        return rank * cfg["rays"], (rank + 1) * cfg["rays"]
+    return (cfg["rays"] * rank) // world, (cfg["rays"] * (rank + 1)) // world
+
+
+def total_rays(cfg, world):
+    return cfg["rays"] * world if cfg["scaling"] == "weak" else cfg["rays"]
+
+
+def workload_config(cfg, mesh, world, extra=None):
+    ctor = f"{cfg['part']}(Model, {', '.join(map(str, cfg['args']))})"
+    if cfg["kind"] == "build":
+        w = f"{cfg['name']}: Voxel_Grid build, procedural hall-{cfg['mesh']} ({mesh.P} polygons) -> {cfg['args'][0]}^3 cell lists"
+    elif cfg["kind"] == "chain":
+        w = (f"{cfg['name']}: procedural auditorium hall-{cfg['mesh']} ({mesh.P} polygons), {ctor}, "
+             f"{cfg['rays']} rays x {cfg['order']}-order specular chains per GPU")
+    else:
+        w = (f"{cfg['name']}: procedural hall {mesh.name} ({mesh.P} polygons), {ctor}, {total_rays(cfg, world)} rays in total, one closest-hit Shoot each, "
+             f"block-sharded over {world} GPU(s)" + (", X_Event rows delivered to rank 0 over NVLink inside the timed region" if world > 1 else ""))
+    c = {"workload": w, "partition": cfg["part"], "ctor_args": list(cfg["args"]), "polygons": mesh.P,
+         "rays_total": total_rays(cfg, world) if cfg["kind"] != "build" else None,
+         "l2": "ray inputs and event outputs stream through HBM every step (far larger than the 126 MB L2); geometry is re-read from L2/HBM as the walk needs it"}
+    if cfg["kind"] == "chain":
+        c["order"] = cfg["order"]
+    if extra:
+        c.update(extra)
+    return c
+
+
+def oracle_partition(cfg, mesh, nthreads):
     from oracle import hare_oracle as ho
     To = ho.Topology.from_mesh(mesh)
-    g = ho.Voxel_Grid(To, args.domain, mode="fast")
-    n0 = min(len(o), 4000 * nthreads)
-    t0 = time.perf_counter(); r = g.reflect_chain(o[:n0], d[:n0], args.order, events=False, nthreads=nthreads); dt = time.perf_counter() - t0
-    rate = r["nshots"].sum() / dt
-    n = int(min(len(o), max(n0, seconds * rate / args.order)))
-    t0 = time.perf_counter(); r = g.reflect_chain(o[:n], d[:n], args.order, events=False, nthreads=nthreads); dt = time.perf_counter() - t0
-    shots = int(r["nshots"].sum())
-    return dict(mrays=shots / dt / 1e6, shots=shots, n=n, seconds=dt, counters=r["counters"], part=g)
+    if cfg["part"] == "Voxel_Grid":
+        return ho.Voxel_Grid(To, cfg["args"][0], mode="fast", nthreads=nthreads)
+    return getattr(ho, cfg["part"])(To, *cfg["args"])
 
 
+def algorithmic_bytes(counters, shots, part):
+    """B = 56 + E + h*C + 4*L + 128*T per Shoot."""
+    C_, L_, T_ = (float(counters[k]) / max(1, shots) for k in range(3))
+    return 56 + EVENT_BYTES[part] + HEADER_BYTES[part] * C_ + 4 * L_ + 128 * T_, dict(cells_or_nodes=C_, entries=L_, tests=T_)
+
+
+def cpu_leg(cfg, mesh, o, d, seconds, nthreads):
+    """Time the oracle (C++ restatement of the reference's CPU path) on a bounded sample: the first n rays of the batch."""
+    t0 = time.perf_counter()
+    part = oracle_partition(cfg, mesh, nthreads)
+    build_s = time.perf_counter() - t0
+    n0 = int(min(len(o), max(256, cfg["cpu_min"] // 8)))
+    if cfg["kind"] == "chain":
+        run = lambda n: part.reflect_chain(o[:n], d[:n], cfg["order"], events=False, nthreads=nthreads)
+        shots_of = lambda r: int(r["nshots"].sum())
+    else:
+        run = lambda n: part.Shoot(o[:n], d[:n], nthreads=nthreads)
+        shots_of = lambda r: len(r["poly_id"])
+    t0 = time.perf_counter(); r = run(n0); dt = time.perf_counter() - t0
+    per_ray = dt / n0
+    n = int(min(len(o), cfg["cpu_cap"], max(cfg["cpu_min"], seconds / max(per_ray, 1e-12))))
+    t0 = time.perf_counter(); r = run(n); dt = time.perf_counter() - t0
+    shots = shots_of(r)
+    return dict(mrays=shots / dt / 1e6, shots=shots, n=n, seconds=dt, build_seconds=build_s, counters=r["counters"], result=r, part=part)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement on all host threads
+# --------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = cfg_of(args)
     cores = os.cpu_count() or 1
-    mesh, o, d = make_workload(args, 0)
+    mesh = get_mesh(cfg)
+    world = args.gpus
+    if cfg["kind"] == "build":
+        return run_reference_build(args, cfg, mesh, cores)
+    from hare_b200.harness import rays_from_sources
     per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-    from oracle import hare_oracle as ho
-    To = ho.Topology.from_mesh(mesh)
-    g = ho.Voxel_Grid(To, args.domain, mode="fast")
-    n0 = min(len(o), 4000 * cores)
-    t0 = time.perf_counter(); r = g.reflect_chain(o[:n0], d[:n0], args.order, events=False, nthreads=cores); dt = time.perf_counter() - t0
-    n = int(min(len(o), max(n0, per_step * (r["nshots"].sum() / dt) / args.order)))
+    n_gen = int(min(cfg["rays"], cfg["cpu_cap"]))
+    o, d = rays_from_sources(n_gen, get_sources(cfg), stream=cfg["stream"])
+    part = oracle_partition(cfg, mesh, cores)
+    chain = cfg["kind"] == "chain"
+    run = (lambda n: int(part.reflect_chain(o[:n], d[:n], cfg["order"], events=False, nthreads=cores)["nshots"].sum())) if chain else \
+          (lambda n: len(part.Shoot(o[:n], d[:n], nthreads=cores)["poly_id"]))
+    n0 = int(min(n_gen, max(256, cfg["cpu_min"] // 8)))
+    t0 = time.perf_counter(); run(n0); dt = time.perf_counter() - t0
+    n = int(min(n_gen, max(n0, per_step / (dt / n0))))
     for _ in range(args.warmup):
-        g.reflect_chain(o[:n], d[:n], args.order, events=False, nthreads=cores)
+        run(n)
     t0 = time.perf_counter(); shots = 0
     for _ in range(args.steps):
-        shots += int(g.reflect_chain(o[:n], d[:n], args.order, events=False, nthreads=cores)["nshots"].sum())
+        shots += run(n)
     dt = time.perf_counter() - t0
     val = shots / dt / 1e6
-    sample = f"{n} chains x {args.order} Shoots per step ({shots // max(1, args.steps)} Shoots/step) of the {args.rays}-chain workload"
+    sample = (f"first {n} rays" + (f" x {cfg['order']}-order chains" if chain else "") +
+              f" per step ({shots // max(1, args.steps)} Shoots/step) of the {total_rays(cfg, world)}-ray workload")
     print(json.dumps({
-        "impl": "reference", "metric": "Mrays/s closest-hit Shoot", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, mesh),
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(cfg, mesh, world),
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "C++ restatement of Hare's Voxel_Grid.Shoot CPU path (oracle/), std::thread over rays; no .NET runtime exists on this box",
+        "note": f"C++ restatement of Hare's {cfg['part']}.Shoot CPU path (oracle/), std::thread over rays in contiguous chunks; no .NET runtime exists on this box",
     }))
 
 
-def workload_config(args, mesh):
-    return {"workload": f"C2: procedural auditorium hall-{args.mesh} ({mesh.P} polygons), Voxel_Grid Domain {args.domain}, "
-                        f"{args.rays} rays x {args.order}-order specular chains per GPU",
-            "partition": "Voxel_Grid", "domain": args.domain, "polygons": mesh.P, "rays_per_gpu": args.rays, "order": args.order,
-            "l2": "ray inputs (48 B/ray) exceed L2 each step; geometry (polygons + cells) is L2-resident by design"}
+def run_reference_build(args, cfg, mesh, cores):
+    from oracle import hare_oracle as ho
+    To = ho.Topology.from_mesh(mesh)
+    dom = cfg["args"][0]
+    md = int(round(np.log2(dom)))
+    t0 = time.perf_counter()
+    g = ho.Voxel_Grid(To, md, mode="hier", avg_polys=0, nthreads=cores)
+    dt = time.perf_counter() - t0
+    val = mesh.P / dt / 1e6
+    print(json.dumps({
+        "impl": "reference", "metric": "Mpolys/s Voxel_Grid build", "value": val, "unit": "Mpolys/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(cfg, mesh, 1),
+        "cpu_baseline": {"value": val, "unit": "Mpolys/s", "cores": cores, "kind": "port",
+                         "sample": f"one full hierarchical build Voxel_Grid(Model, MaxDomain={md}, Avg_polys=0) of all {mesh.P} polygons ({g.info()[3]} pairs)"},
+        "e2e": {"value": val, "unit": "Mpolys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
 
 
-def run_b200(args):
+# --------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def make_ctx(args):
     import torch
     import torch.distributed as dist
     import hare_b200 as hb
-    from hare_b200._lib import check, lib
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    from hare_b200._lib import lib
+    x = Ctx()
+    x.world = int(os.environ.get("WORLD_SIZE", "1")); x.rank = int(os.environ.get("RANK", "0")); x.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if x.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    hb.init([local])
-    L = lib()
+    torch.cuda.set_device(x.local)
+    x.dev = torch.device("cuda", x.local)
+    if x.world > 1:
+        dist.init_process_group("nccl", device_id=x.dev)
+    hb.init([x.local])
+    x.L, x.hb, x.torch, x.dist = lib(), hb, torch, dist
+    x.cores = max(1, (os.cpu_count() or 1) // (x.world if x.world > 1 else 1))
+    return x
 
-    mesh, o, d = make_workload(args, rank)
-    N, order = args.rays, args.order
-    cpu_res = None
-    if rank == 0 and not args.no_cpu_baseline:
-        # the CPU leg runs first, on an otherwise idle host (before pinned buffers and GPU work exist)
-        cpu_res = cpu_leg(args, mesh, o, d, args.cpu_seconds, os.cpu_count() or 1)
-    if world > 1:
+
+def cur_stream(torch):
+    # torch's default stream is the legacy default stream (handle 0); the C ABI treats NULL as "the partition's own
+    # stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1).
+    s = torch.cuda.current_stream().cuda_stream
+    return s if s else 1
+
+
+def sync_all(x):
+    if x.world > 1:
+        x.dist.barrier()
+    x.torch.cuda.synchronize()
+
+
+def pinned(x, shape, dtype):
+    """numpy array over page-locked host memory from the library (hare_host_alloc)."""
+    n = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    from hare_b200._lib import check
+    check(x.L.hare_host_alloc(max(n, 8), C.byref(p)), "hare_host_alloc")
+    buf = (C.c_char * max(n, 8)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    x.pins.append(p)
+    return a
+
+
+def free_pins(x):
+    for p in x.pins:
+        x.L.hare_host_free(p)
+    x.pins = []
+
+
+def reduce_max_sum(x, ms, count):
+    torch, dist = x.torch, x.dist
+    tms = torch.tensor([ms], dtype=torch.float64, device=x.dev); sh = torch.tensor([count], dtype=torch.int64, device=x.dev)
+    if x.world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX); dist.all_reduce(sh, op=dist.ReduceOp.SUM)
+    return float(tms.item()), int(sh.item())
+
+
+def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_cpu=True, gather="peer"):
+    """Single-Shoot batch (C1 / C3 / C4) or reflection chains (C2).  Returns the JSON line (rank 0) or None."""
+    torch, dist, L, hb = x.torch, x.dist, x.L, x.hb
+    from hare_b200._lib import check
+    from hare_b200.harness import rays_from_sources
+    from hare_b200 import dist as hd
+    chain = cfg["kind"] == "chain"
+    order = cfg.get("order", 1)
+    mesh = get_mesh(cfg)
+    lo, hi = shard(cfg, x.rank, x.world)
+    N = hi - lo
+    x.pins = []
+    # rays of this rank's block, generated straight into page-locked host arrays (the e2e leg shoots from them)
+    o = pinned(x, (N, 3), np.float64); d = pinned(x, (N, 3), np.float64)
+    rays_from_sources(N, get_sources(cfg), stream=cfg["stream"], first=lo, threads=x.cores, out=(o, d))
+    cpu = None
+    if x.rank == 0 and do_cpu:
+        # the CPU leg runs first, on an otherwise idle host
+        cpu = cpu_leg(cfg, mesh, o, d, cpu_seconds, os.cpu_count() or 1)
+    if x.world > 1:
         dist.barrier()
+    t0 = time.perf_counter()
     T = hb.Topology.from_mesh(mesh)
-    part = hb.Voxel_Grid([T], args.domain)
+    part = getattr(hb, cfg["part"])([T], *cfg["args"])
+    build_s = time.perf_counter() - t0
 
-    # ---------------- device-resident leg: rays already in HBM --------------------------------------
-    o_d = torch.from_numpy(o).to(dev); d_d = torch.from_numpy(d).to(dev)
-    fin_o = torch.empty_like(o_d); fin_d = torch.empty_like(d_d)
-    nshots = torch.empty(N, dtype=torch.int32, device=dev)
-    total = torch.zeros(1, dtype=torch.int64, device=dev)
-    if world > 1:
-        g_fin_o = torch.empty((world * N, 3), dtype=torch.float64, device=dev) if rank == 0 else None
-        g_fin_d = torch.empty((world * N, 3), dtype=torch.float64, device=dev) if rank == 0 else None
-        g_ns = torch.empty(world * N, dtype=torch.int32, device=dev) if rank == 0 else None
+    # ---------------- device-resident leg: rays already in HBM ---------------------------------------------------
+    o_d = torch.from_numpy(o).to(x.dev); d_d = torch.from_numpy(d).to(x.dev)
+    total = torch.zeros(1, dtype=torch.int64, device=x.dev)
+    peer = None
+    if chain:
+        fin_o = torch.empty_like(o_d); fin_d = torch.empty_like(d_d); nshots = torch.empty(N, dtype=torch.int32, device=x.dev)
+        outs = [fin_o, fin_d, nshots]
+    else:
+        ntot = total_rays(cfg, x.world)
+        if x.world > 1 and gather == "peer":
+            try:
+                peer = hd.PeerResults(ntot, x.local, dst=0)
+            except Exception as e:   # no peer access between these devices: NCCL gather after the kernel instead
+                if x.rank == 0:
+                    print(f"# peer result buffers unavailable ({e}); using NCCL gather", file=sys.stderr)
+                peer = None
+            ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=x.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                peer = None
+        if peer is not None:
+            pt, pxyz, ppid, puv = peer.out_ptrs(lo)
+        else:
+            t_d = torch.empty(N, dtype=torch.float64, device=x.dev); xyz_d = torch.empty((N, 3), dtype=torch.float64, device=x.dev)
+            pid_d = torch.empty(N, dtype=torch.int32, device=x.dev); uv_d = torch.empty((N, 2), dtype=torch.float64, device=x.dev)
+            pt, pxyz, ppid, puv = t_d.data_ptr(), xyz_d.data_ptr(), pid_d.data_ptr(), uv_d.data_ptr()
+            outs = [pid_d, t_d, xyz_d, uv_d]
+    sizes = [shard(cfg, r, x.world)[1] - shard(cfg, r, x.world)[0] for r in range(x.world)]
+    gathered = None
 
-    def gather():   # X_Event rows of every rank -> rank 0, in rank order (hare_b200/dist.py; same helper as the gloo test)
-        dist.gather(fin_o, list(g_fin_o.chunk(world)) if rank == 0 else None, dst=0)
-        dist.gather(fin_d, list(g_fin_d.chunk(world)) if rank == 0 else None, dst=0)
-        dist.gather(nshots, list(g_ns.chunk(world)) if rank == 0 else None, dst=0)
+    def kernel():
+        stream = cur_stream(torch)
+        if chain:
+            check(L.hare_reflect_chain_device(part._h, o_d.data_ptr(), d_d.data_ptr(), N, order, None, None, fin_o.data_ptr(), fin_d.data_ptr(),
+                                              nshots.data_ptr(), total.data_ptr(), None, C.c_void_p(stream)), "hare_reflect_chain_device")
+        else:
+            check(L.hare_shoot_batch_device(part._h, o_d.data_ptr(), d_d.data_ptr(), None, None, None, N, C.c_void_p(pt), C.c_void_p(pxyz),
+                                            C.c_void_p(ppid), C.c_void_p(puv), None, None, C.c_void_p(stream)), "hare_shoot_batch_device")
 
-    def cur_stream():
-        # torch's default stream is the legacy default stream (handle 0); the C ABI treats NULL as "the
-        # partition's own stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1).
-        s = torch.cuda.current_stream().cuda_stream
-        return s if s else 1
+    def deliver():
+        nonlocal gathered
+        if x.world == 1:
+            return
+        if peer is not None:
+            peer.fence()
+        else:
+            gathered = [hd.gather_rows(a, 0, sizes) for a in outs]
 
-    def step_device():
-        stream = cur_stream()
-        check(L.hare_reflect_chain_device(part._h, o_d.data_ptr(), d_d.data_ptr(), N, order, None, None,
-                                          fin_o.data_ptr(), fin_d.data_ptr(), nshots.data_ptr(), total.data_ptr(), None, C.c_void_p(stream)),
-              "hare_reflect_chain_device")
-        if world > 1:   # gather of per-chain results to rank 0 over NVLink (NCCL)
-            gather()
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step_device()
-    sync_all()
+    for _ in range(warmup):
+        kernel(); deliver()
+    sync_all(x)
     total.zero_()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(x.local) if x.rank == 0 else None
     if sampler:
         sampler.start()
     launches0 = hb.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sync_all(x)
     ev[0].record()
-    for k in range(args.steps):
-        # inner events bracket the traversal kernel alone (for the roofline line); outer ones the step
-        kev[k][0].record()
-        stream = cur_stream()
-        check(L.hare_reflect_chain_device(part._h, o_d.data_ptr(), d_d.data_ptr(), N, order, None, None,
-                                          fin_o.data_ptr(), fin_d.data_ptr(), nshots.data_ptr(), total.data_ptr(), None, C.c_void_p(stream)),
-              "hare_reflect_chain_device")
-        kev[k][1].record()
-        if world > 1:
-            gather()
+    for k in range(steps):
+        kev[k][0].record(); kernel(); kev[k][1].record()   # inner events bracket the traversal kernel alone (roofline); outer ones the step
+        deliver()
         ev[k + 1].record()
-    sync_all()
+    sync_all(x)
     launches = hb.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     ms_total = ev[0].elapsed_time(ev[-1])
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    shots_rank = int(total.item())
-    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    sh = torch.tensor([shots_rank], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sh, op=dist.ReduceOp.SUM)
-    ms_total = float(tms.item()); shots_all = int(sh.item())
+    shots_rank = int(total.item()) if chain else N * steps
+    ms_total, shots_all = reduce_max_sum(x, ms_total, shots_rank)
+    kernel_ms_max, _ = reduce_max_sum(x, kernel_ms, 0)
     value = shots_all / (ms_total * 1e-3) / 1e6
 
-    # ---------------- end-to-end leg: host buffers through the public C-ABI call --------------------------
-    e2e = None
-    if not args.no_e2e:
-        o_h = torch.from_numpy(o).pin_memory(); d_h = torch.from_numpy(d).pin_memory()
-        fo_h = torch.empty((N, 3), dtype=torch.float64).pin_memory(); fd_h = torch.empty((N, 3), dtype=torch.float64).pin_memory()
-        ns_h = torch.empty(N, dtype=torch.int32).pin_memory()
-        tot = C.c_uint64()
+    # results of the device leg on the host (rank 0: everything that was delivered to it)
+    if chain:
+        dev_res = dict(nshots=nshots.cpu().numpy(), o=fin_o[:cfg["cpu_cap"]].cpu().numpy())
+    elif peer is not None:
+        dev_res = {k: peer.arrays[k].torch() for k in ("poly_id", "t", "xyz", "uv")} if x.rank == 0 else None
+    elif x.world > 1:
+        dev_res = dict(zip(("poly_id", "t", "xyz", "uv"), gathered)) if x.rank == 0 else None
+    else:
+        dev_res = dict(poly_id=pid_d, t=t_d, xyz=xyz_d, uv=uv_d)
 
-        def step_host():
-            check(L.hare_reflect_chain(part._h, o_h.data_ptr(), d_h.data_ptr(), N, order, None, None,
-                                       fo_h.data_ptr(), fd_h.data_ptr(), ns_h.data_ptr(), C.byref(tot), None), "hare_reflect_chain")
-            return tot.value
-        for _ in range(min(args.warmup, 2)):
+    # ---------------- end-to-end leg: host buffers through the public C-ABI call ------------------------------------
+    e2e = None
+    if do_e2e:
+        if chain:
+            fo_h = pinned(x, (N, 3), np.float64); fd_h = pinned(x, (N, 3), np.float64); ns_h = pinned(x, (N,), np.int32)
+            tot = C.c_uint64()
+
+            def step_host():
+                check(L.hare_reflect_chain(part._h, o.ctypes.data, d.ctypes.data, N, order, None, None, fo_h.ctypes.data, fd_h.ctypes.data,
+                                           ns_h.ctypes.data, C.byref(tot), None), "hare_reflect_chain")
+                return tot.value
+            h2d, d2h, api = 48, 52, "hare_reflect_chain (host buffers, page-locked)"
+        else:
+            t_h = pinned(x, (N,), np.float64); xyz_h = pinned(x, (N, 3), np.float64); pid_h = pinned(x, (N,), np.int32); uv_h = pinned(x, (N, 2), np.float64)
+
+            def step_host():
+                check(L.hare_shoot_batch(part._h, o.ctypes.data, d.ctypes.data, None, None, None, N, t_h.ctypes.data, xyz_h.ctypes.data,
+                                         pid_h.ctypes.data, uv_h.ctypes.data, None, None), "hare_shoot_batch")
+                return N
+            h2d, d2h, api = 48, 52, "hare_shoot_batch (host buffers, page-locked)"
+        for _ in range(min(warmup, 2)):
             step_host()
-        sync_all()
-        e_steps = max(1, min(args.steps, 3))
+        sync_all(x)
+        e_steps = max(1, min(steps, 3))
         t0 = time.perf_counter(); e_shots = 0
         for _ in range(e_steps):
             e_shots += step_host()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev); es = torch.tensor([e_shots], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(es, op=dist.ReduceOp.SUM)
-        e2e = {"value": int(es.item()) / float(tt.item()) / 1e6, "unit": "Mrays/s",
-               "h2d_bytes_per_step": int(world * N * 48), "d2h_bytes_per_step": int(world * N * 52),
-               "steps": e_steps, "api": "hare_reflect_chain (host buffers, pinned)"}
-        assert np.array_equal(ns_h.numpy(), nshots.cpu().numpy()), "host-buffer and device-resident legs disagree"
+        dt, e_all = reduce_max_sum(x, dt, e_shots)
+        e2e = {"value": e_all / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(total_rays(cfg, x.world) * h2d),
+               "d2h_bytes_per_step": int(total_rays(cfg, x.world) * d2h), "steps": e_steps, "api": api,
+               "note": "every rank shoots its block from and into its own page-locked host arrays" if x.world > 1 else None}
+        if chain:
+            assert np.array_equal(ns_h, dev_res["nshots"]), "host-buffer and device-resident legs disagree"
+        elif x.world == 1:
+            assert np.array_equal(pid_h, dev_res["poly_id"].cpu().numpy()) and np.array_equal(t_h, dev_res["t"].cpu().numpy()), \
+                "host-buffer and device-resident legs disagree"
 
-    if rank == 0:
+    line = None
+    if x.rank == 0:
         peak, peak_kind = peak_hbm()
-        cpu = None
-        bytes_per_shoot, avg = None, None
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            c = cpu_res
-            bytes_per_shoot, avg = algorithmic_bytes(c["counters"], c["shots"])
-            cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": cores, "kind": "port",
-                   "sample": f"first {c['n']} chains x {order} Shoots ({c['shots']} Shoots, {c['seconds']:.1f} s) of the {N}-chain workload"}
-            # parity spot-check of the timed device leg against the same oracle run (not timed)
-            ref = c["part"].reflect_chain(o[:20000], d[:20000], order, events=False, nthreads=cores)
-            assert np.array_equal(ref["nshots"], nshots[:20000].cpu().numpy()) and np.array_equal(ref["o"], fin_o[:20000].cpu().numpy()), \
-                "bench result differs from the oracle"
+        cores = os.cpu_count() or 1
+        cpu_line, parity = None, None
+        # GPU's own walk counters on a sample (nodes/cells entered, list entries scanned, exact tests)
+        ns = min(N, 200_000)
+        if chain:
+            r = part.Reflect_Chain(o[:ns], d[:ns], order, events=False, counters=True)
+            gpu_cnt, gpu_shots = r["counters"], r["total_shots"]
         else:
-            # counters from the GPU's own walk (cells identical to the oracle's; entries/tests are upper bounds of the mailboxed reference)
-            r = part.Reflect_Chain(o[:200000], d[:200000], order, events=False, counters=True)
-            bytes_per_shoot, avg = algorithmic_bytes(r["counters"], r["total_shots"])
-        shots_per_launch = shots_rank / args.steps
-        achieved = shots_per_launch * bytes_per_shoot / (kernel_ms * 1e-3) / 1e9
-        line = {
-            "metric": "Mrays/s closest-hit Shoot", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args),
-                         "peak_kind": peak_kind, "kernel": ("vg_walk_kernel<CHAIN>" if os.environ.get("HARE_VG_WAVE") == "0" else "vg_wave_kernel<CHAIN>"), "kernel_ms": kernel_ms,
-                         "bytes_per_shoot": bytes_per_shoot, "per_shoot": avg,
-                         "formula": "56 + 36 + 8*cells + 4*entries + 128*tests (SURVEY.md 8(d)), oracle-counted"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "shots_per_step": shots_all // args.steps,
-        }
+            r = part.Shoot_Batch(o[:ns], d[:ns], counters=True)
+            gpu_cnt, gpu_shots = r["counters"], ns
+        gpu_bytes, gpu_avg = algorithmic_bytes(gpu_cnt, gpu_shots, cfg["part"])
+        if cpu is not None:
+            n = cpu["n"]
+            ref = cpu["result"]
+            if chain:
+                ok = np.array_equal(ref["nshots"], dev_res["nshots"][:n]) and np.array_equal(ref["o"], dev_res["o"][:n])
+            else:
+                got = {k: dev_res[k][:n].cpu().numpy() for k in ("poly_id", "t", "xyz", "uv")}
+                ok = all(np.array_equal(got[k], ref[k]) for k in (("poly_id", "t", "xyz") if cfg["part"] == "Voxel_Grid" else ("poly_id", "t", "xyz", "uv")))
+            assert ok, f"{cfg['name']}: GPU results differ from the oracle on the first {n} rays"
+            parity = {"rays_compared": n, "bit_exact": True, "fields": "poly_id, t, X_Point" + ("" if cfg["part"] == "Voxel_Grid" else ", u, v")}
+            ref_bytes, ref_avg = algorithmic_bytes(cpu["counters"], cpu["shots"], cfg["part"])
+            cpu_line = {"value": cpu["mrays"], "unit": "Mrays/s", "cores": cores, "kind": "port",
+                        "sample": f"first {n} rays" + (f" x {order}-order chains" if chain else "") +
+                                  f" ({cpu['shots']} Shoots, {cpu['seconds']:.1f} s) of the {total_rays(cfg, x.world)}-ray workload; "
+                                  f"oracle partition build {cpu['build_seconds']:.1f} s not included"}
+        else:
+            ref_bytes, ref_avg = None, None
+        # contract figure (SURVEY 8(d)): reference-algorithm counts for Voxel_Grid / Octree, the pruned GPU count for KDTree
+        if cfg["part"] == "KDTree" or ref_bytes is None:
+            contract_bytes, contract_avg, contract_src = gpu_bytes, gpu_avg, "GPU walk counters (pruned)"
+        else:
+            contract_bytes, contract_avg, contract_src = ref_bytes, ref_avg, "oracle following the reference algorithm"
+        shots_per_launch = shots_rank / steps
+        achieved = shots_per_launch * contract_bytes / (kernel_ms * 1e-3) / 1e9
+        achieved_gpu = shots_per_launch * gpu_bytes / (kernel_ms * 1e-3) / 1e9
+        act = ncu_actual(cfg)
+        kname = {"Voxel_Grid": "vg_wave_kernel", "Octree": "oct_walk_kernel", "KDTree": "kd_walk_kernel"}[cfg["part"]]
+        roof = {"bound": (act or {}).get("bound", "issue/latency (see actual)"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_reference_bytes": achieved / peak,
+                "frac_flag": "exceeds 1: the culls legitimately skip most of the reference's fetches; read achieved_gpu_counted / actual instead" if achieved / peak > 1.0 else None,
+                "traffic": (act or {}).get("traffic_bytes_per_launch"), "peak_kind": peak_kind, "kernel": kname, "kernel_ms": kernel_ms, "kernel_ms_max_over_ranks": kernel_ms_max,
+                "bytes_per_shoot": contract_bytes, "per_shoot": contract_avg, "counted_by": contract_src,
+                "formula": f"56 + {EVENT_BYTES[cfg['part']]} + {HEADER_BYTES[cfg['part']]}*nodes_or_cells + 4*entries + 128*tests (SURVEY.md 8(d))",
+                "achieved_gpu_counted": achieved_gpu, "frac_gpu_counted": achieved_gpu / peak, "gpu_bytes_per_shoot": gpu_bytes, "gpu_per_shoot": gpu_avg,
+                "actual": (act or {}).get("actual"), "actual_source": (f"profiles/r2_ncu_{cfg['name']}.json" if act else None)}
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": x.world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(cfg, mesh, x.world, {"build_seconds_gpu": build_s}),
+                "roofline": roof, "cpu_baseline": cpu_line, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "shots_per_step": shots_all // steps, "parity": parity,
+                "result_delivery": None if x.world == 1 else ("peer stores from the traversal kernel into rank 0 (CUDA IPC over NVLink) + 4-byte NCCL fence" if peer is not None else "NCCL gather after the kernel")}
+    if peer is not None:
+        dev_res = None
+        peer.close()
+    del part, T
+    free_pins(x)
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_build_config(x, args, cfg, steps, warmup, do_cpu=True):
+    """C5: Voxel_Grid(Model, Domain) cell lists on the GPU vs the CPU hierarchical constructor (rank 0 only)."""
+    if x.rank != 0:
+        return None
+    torch, L, hb = x.torch, x.L, x.hb
+    mesh = get_mesh(cfg)
+    dom = cfg["args"][0]
+    T = hb.Topology.from_mesh(mesh)
+    g = None
+    for _ in range(max(1, warmup)):
+        g = hb.Voxel_Grid([T], dom)
+    torch.cuda.synchronize()
+    l0 = hb.launch_count()
+    walls = []
+    for _ in range(steps):
+        del g
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g = hb.Voxel_Grid([T], dom)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    launches = hb.launch_count() - l0
+    wall = float(np.median(walls))
+    kms = g.build_kernel_ms() if hasattr(g, "build_kernel_ms") else None
+    _, _, ct, K = g.info()
+    ncells = int(ct[0]) * int(ct[1]) * int(ct[2])
+    B = 2 * mesh.P * 128 + 12 * ncells + 4 * K
+    peak, peak_kind = peak_hbm()
+    cpu_line, parity = None, None
+    if do_cpu:
+        from oracle import hare_oracle as ho
+        cores = os.cpu_count() or 1
+        To = ho.Topology.from_mesh(mesh)
+        md = int(round(np.log2(dom)))
+        t0 = time.perf_counter()
+        og = ho.Voxel_Grid(To, md, mode="hier", avg_polys=0, nthreads=cores)
+        dt = time.perf_counter() - t0
+        off, pol = g.csr(); ooff, opol = og.csr()
+        assert np.array_equal(off, ooff) and np.array_equal(pol, opol), "C5: GPU cell lists differ from the oracle's hierarchical build"
+        parity = {"csr_equal": True, "cells": ncells, "pairs": int(K)}
+        cpu_line = {"value": mesh.P / dt / 1e6, "unit": "Mpolys/s", "cores": cores, "kind": "port",
+                    "sample": f"one full hierarchical build Voxel_Grid(Model, MaxDomain={md}, Avg_polys=0) of all {mesh.P} polygons, {dt:.1f} s"}
+    t_roof = (kms if kms else wall * 1e3) * 1e-3
+    line = {"metric": "Mpolys/s Voxel_Grid build", "value": mesh.P / wall / 1e6, "unit": "Mpolys/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+            "ms_per_step": wall * 1e3, "kernel_ms": kms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(cfg, mesh, 1, {"cells": ncells, "pairs": int(K)}),
+            "roofline": {"bound": "hbm", "achieved": B / t_roof / 1e9, "peak": peak, "unit": "GB/s", "frac": B / t_roof / 1e9 / peak, "traffic": None,
+                         "peak_kind": peak_kind, "kernel": "vg_bin_kernel (count + scatter), scan, vg_finish_cells", "bytes_per_build": B,
+                         "formula": "2*P*128 + 12*Ncells + 4*K (SURVEY.md 8(d))", "timed": "kernels (CUDA events inside the build)" if kms else "host wall time"},
+            "cpu_baseline": cpu_line, "e2e": {"value": mesh.P / wall / 1e6, "unit": "Mpolys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                                               "note": "hare_voxelgrid_build wall time; the Topology is already on the device, only the pair count returns"},
+            "gpu_launches": int(launches), "parity": parity, "wall_ms_all": [w * 1e3 for w in walls]}
+    del g, T
+    return line
+
+
+def run_c1(x, args, cfg):
+    """C1 parity configuration + the boundary's cliffs: single-ray Shoot latency, pageable vs page-locked batches."""
+    line = run_shoot_config(x, args, cfg, steps=5, warmup=3, cpu_seconds=3.0, do_e2e=True, do_cpu=True)
+    if x.rank != 0:
+        return None
+    hb = x.hb
+    from hare_b200.harness import rays_from_sources
+    mesh = get_mesh(cfg)
+    T = hb.Topology.from_mesh(mesh)
+    g = hb.Voxel_Grid([T], 10)
+    o, d = rays_from_sources(2000, get_sources(cfg), stream=1)
+    R = [hb.Ray(*o[i], *d[i], Ray_ID=i + 1) for i in range(len(o))]
+    for r in R[:200]:
+        g.Shoot(r, 0)
+    t0 = time.perf_counter()
+    for r in R:
+        g.Shoot(r, 0)
+    single_us = (time.perf_counter() - t0) / len(R) * 1e6
+    # pageable vs page-locked host arrays through hare_shoot_batch, 4 M rays
+    n = 4_000_000
+    op, dp = rays_from_sources(n, get_sources(cfg), stream=1)
+    t0 = time.perf_counter(); g.Shoot_Batch(op, dp); g.Shoot_Batch(op, dp); pageable = 2 * n / (time.perf_counter() - t0) / 1e6
+    line["boundary"] = {"single_ray_Shoot_us": single_us, "single_ray_Shoot_per_s": 1e6 / single_us,
+                        "note": "Spatial_Partition.Shoot(Ray) through the C ABI is a one-ray batch: H2D + launch + D2H + sync per call; use the batched overload",
+                        "shoot_batch_pageable_Mrays_s": pageable, "shoot_batch_pinned_Mrays_s": line["e2e"]["value"] if line.get("e2e") else None}
+    return line
+
+
+def run_b200(args):
+    x = make_ctx(args)
+    cfg = cfg_of(args)
+    do_cpu = not args.no_cpu_baseline
+    if cfg["kind"] == "build":
+        line = run_build_config(x, args, cfg, args.steps, args.warmup, do_cpu)
+    elif cfg["name"] == "C1":
+        line = run_c1(x, args, cfg)
+    else:
+        line = run_shoot_config(x, args, cfg, args.steps, args.warmup, args.cpu_seconds, do_e2e=not args.no_e2e, do_cpu=do_cpu, gather=args.gather)
+    if x.world == 1 and not args.no_extras and args.config == "C3" and line is not None:
+        # the other BASELINE configurations, short, so that every round's driver run has them side by side
+        others = {}
+        for name, st, wu, cs in (("C2", 3, 3, 4.0), ("C4vg", 3, 3, 4.0), ("C4kd", 3, 3, 4.0)):
+            c2 = cfg_of(args, name)
+            try:
+                others[name] = run_shoot_config(x, args, c2, st, wu, cs, do_e2e=(name == "C2"), do_cpu=do_cpu)
+            except AssertionError:
+                raise
+            except Exception as e:   # e.g. out of host memory on a small box: say so instead of hiding the main line
+                others[name] = {"error": repr(e)}
+        try:
+            others["C5"] = run_build_config(x, args, cfg_of(args, "C5"), 5, 2, do_cpu)
+        except AssertionError:
+            raise
+        except Exception as e:
+            others["C5"] = {"error": repr(e)}
+        try:
+            others["C1"] = run_c1(x, args, cfg_of(args, "C1"))
+        except AssertionError:
+            raise
+        except Exception as e:
+            others["C1"] = {"error": repr(e)}
+        line["other_configs"] = others
+    if x.rank == 0 and line is not None:
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if x.world > 1:
+        x.dist.barrier()
+        x.dist.destroy_process_group()
 
 
 def main():

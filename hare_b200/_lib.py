@@ -85,6 +85,18 @@ def lib():
     L.hare_reflect_chain.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
     L.hare_reflect_chain_device.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hare_launch_count.restype = u64
+    sz = C.c_size_t
+    L.hare_host_alloc.argtypes = [sz, pp]
+    L.hare_host_free.argtypes = [vp]
+    L.hare_host_register.argtypes = [vp, sz]
+    L.hare_host_unregister.argtypes = [vp]
+    L.hare_host_is_pinned.argtypes = [vp]
+    L.hare_device_alloc.argtypes = [i32, sz, pp]
+    L.hare_device_free.argtypes = [i32, vp]
+    L.hare_device_memcpy.argtypes = [vp, vp, sz, i32, i32]
+    L.hare_ipc_export.argtypes = [i32, vp, vp]
+    L.hare_ipc_open.argtypes = [i32, vp, pp]
+    L.hare_ipc_close.argtypes = [i32, vp]
     _lib = L
     return L
 

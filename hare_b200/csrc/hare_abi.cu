@@ -17,6 +17,8 @@
 
 #include "host_build.hpp"
 #include "kernels.cuh"
+#include "oct_wave.cuh"
+#include "pack.hpp"
 
 using namespace hare;
 
@@ -579,111 +581,23 @@ static int oct_to_device(hare_part_s* p) {
     const OctTree& t = p->oct;
     const size_t N = t.first_child.size();
     if (oct_depth(t) >= HARE_OCT_MAXLVL) return fail(HARE_ERR_UNSUPPORTED, "octree deeper than HARE_OCT_MAXLVL levels");
-    std::vector<OctNode> nodes(N);
-    for (size_t i = 0; i < N; ++i) {
-        OctNode& n = nodes[i];
-        n.mnx = t.box[6 * i]; n.mny = t.box[6 * i + 1]; n.mnz = t.box[6 * i + 2]; n.mxx = t.box[6 * i + 3]; n.mxy = t.box[6 * i + 4]; n.mxz = t.box[6 * i + 5];
-        n.first_child = t.first_child[i]; n.list_off = t.list_off[i]; n.list_cnt = t.list_cnt[i]; n.pad = 0;
-    }
-    // pad = bit c set when the subtree of child c holds at least one polygon: the kernel never enters the others
-    // (entering a polygon-free subtree has no effect on the result).  Children have larger indices than parents.
-    {
-        std::vector<uint8_t> has(N, 0);
-        for (size_t i = N; i-- > 0;) {
-            if (t.first_child[i] < 0) has[i] = t.list_cnt[i] > 0;
-            else {
-                uint32_t m = 0;
-                for (int c = 0; c < 8; ++c) if (has[(size_t)t.first_child[i] + c]) m |= 1u << c;
-                nodes[i].pad = m; has[i] = m != 0;
-            }
-        }
-    }
-    // Chunk spheres: every run of HARE_OCT_CHUNK consecutive entries of a leaf list gets a sphere enclosing its
-    // members' padded spheres; a ray whose line misses it misses all of them (leaf.pad = index of the leaf's first chunk).
-    std::vector<float> csph;
-    {
-        const std::vector<float>& ps = p->topo->sph;
-        for (size_t i = 0; i < N; ++i) {
-            if (t.first_child[i] >= 0) continue;
-            while ((csph.size() / 4) % 8) { const float z[4] = { 0.f, 0.f, 0.f, 0.f }; csph.insert(csph.end(), z, z + 4); }   // a leaf's chunks start a group of 8
-            nodes[i].pad = (uint32_t)(csph.size() / 4);
-            for (uint32_t b = 0; b < t.list_cnt[i]; b += HARE_OCT_CHUNK) {
-                const uint32_t e = std::min<uint32_t>(b + HARE_OCT_CHUNK, t.list_cnt[i]);
-                double c[3] = { 0, 0, 0 };
-                for (uint32_t k = b; k < e; ++k) { const float* s = &ps[4 * (size_t)t.polys[t.list_off[i] + k]]; c[0] += s[0]; c[1] += s[1]; c[2] += s[2]; }
-                for (int a2 = 0; a2 < 3; ++a2) c[a2] /= (double)(e - b);
-                float cf[3] = { (float)c[0], (float)c[1], (float)c[2] };
-                double r = 0;
-                for (uint32_t k = b; k < e; ++k) {
-                    const float* s = &ps[4 * (size_t)t.polys[t.list_off[i] + k]];
-                    const double dx = (double)s[0] - cf[0], dy = (double)s[1] - cf[1], dz = (double)s[2] - cf[2];
-                    r = std::max(r, std::sqrt(dx * dx + dy * dy + dz * dz) + (double)s[3]);
-                }
-                r = r * (1.0 + 1e-6) + 1e-6;
-                float rf = (float)r;
-                while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
-                csph.push_back(cf[0]); csph.push_back(cf[1]); csph.push_back(cf[2]); csph.push_back(rf);
-            }
-        }
-    }
-    // The same runs' boxes (union of the members' padded boxes), and one (box, polygon id) record per list entry.
-    // Chunks are numbered as for csph (every leaf starts a multiple of 8); gbox[g] encloses chunks 8g .. 8g+7.
-    std::vector<float> cbox, gbox;
-    const float kEmptyBox[8] = { INFINITY, INFINITY, INFINITY, 0.f, -INFINITY, -INFINITY, -INFINITY, 0.f };
-    for (size_t i = 0; i < N; ++i) {
-        if (t.first_child[i] >= 0) continue;
-        while ((cbox.size() / 8) % 8) cbox.insert(cbox.end(), kEmptyBox, kEmptyBox + 8);
-        for (uint32_t b = 0; b < t.list_cnt[i]; b += HARE_OCT_CHUNK) {
-            const uint32_t e = std::min<uint32_t>(b + HARE_OCT_CHUNK, t.list_cnt[i]);
-            float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-            for (uint32_t k = b; k < e; ++k) {
-                const float* q = &p->topo->pbox[6 * (size_t)t.polys[t.list_off[i] + k]];
-                for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], q[a2]); hi[a2] = std::max(hi[a2], q[3 + a2]); }
-            }
-            const float rec[8] = { lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f };
-            cbox.insert(cbox.end(), rec, rec + 8);
-        }
-    }
-    for (size_t g = 0; g * 64 < cbox.size(); ++g) {
-        float rec[8] = { INFINITY, INFINITY, INFINITY, 0.f, -INFINITY, -INFINITY, -INFINITY, 0.f };
-        for (size_t c = 8 * g; c < 8 * g + 8 && c * 8 < cbox.size(); ++c)
-            for (int a2 = 0; a2 < 3; ++a2) { rec[a2] = std::min(rec[a2], cbox[8 * c + a2]); rec[4 + a2] = std::max(rec[4 + a2], cbox[8 * c + 4 + a2]); }
-        gbox.insert(gbox.end(), rec, rec + 8);
-    }
-    // Node content boxes: union of the padded boxes of every polygon listed below the node (children have larger indices).
-    std::vector<float> nbox(N * 8);
-    for (size_t i = N; i-- > 0;) {
-        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-        if (t.first_child[i] < 0) {
-            for (uint32_t k = 0; k < t.list_cnt[i]; ++k) {
-                const float* q = &p->topo->pbox[6 * (size_t)t.polys[t.list_off[i] + k]];
-                for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], q[a2]); hi[a2] = std::max(hi[a2], q[3 + a2]); }
-            }
-        } else {
-            for (int c = 0; c < 8; ++c) {
-                const float* q = &nbox[8 * ((size_t)t.first_child[i] + c)];
-                for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], q[a2]); hi[a2] = std::max(hi[a2], q[4 + a2]); }
-            }
-        }
-        const float rec[8] = { lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f };
-        std::memcpy(&nbox[8 * i], rec, sizeof rec);
-    }
+    // node records (content masks, chunk indices), chunk / group boxes and node content boxes: pack.hpp (shared with tests/emu)
+    PackedOct pk;
+    pack_octree(t, p->topo->pbox.data(), pk);
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         OctNode* dn = nullptr;
         CK(dmalloc(&dn, N)); d.nodes = dn;
-        CK(dmalloc(&d.lists, t.polys.size()));
-        CK(dmalloc(&d.csph, csph.size() / 4));
-        if (!csph.empty()) CK(cudaMemcpy(d.csph, csph.data(), csph.size() * 4, cudaMemcpyHostToDevice));
-        CK(dmalloc(&d.cbox, cbox.size() / 4)); CK(dmalloc(&d.nbox, nbox.size() / 4));
-        CK(cudaMemcpy(d.nbox, nbox.data(), nbox.size() * 4, cudaMemcpyHostToDevice));
-        if (!cbox.empty()) CK(cudaMemcpy(d.cbox, cbox.data(), cbox.size() * 4, cudaMemcpyHostToDevice));
-        CK(dmalloc(&d.gbox, gbox.size() / 4));
-        if (!gbox.empty()) CK(cudaMemcpy(d.gbox, gbox.data(), gbox.size() * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dn, nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
+        CK(dmalloc(&d.lists, t.polys.size() + 8));
+        CK(dmalloc(&d.cbox, pk.cbox.size() / 4 + 16)); CK(dmalloc(&d.nbox, pk.nbox.size() / 4));
+        CK(cudaMemcpy(d.nbox, pk.nbox.data(), pk.nbox.size() * 4, cudaMemcpyHostToDevice));
+        if (!pk.cbox.empty()) CK(cudaMemcpy(d.cbox, pk.cbox.data(), pk.cbox.size() * 4, cudaMemcpyHostToDevice));
+        CK(dmalloc(&d.gbox, pk.gbox.size() / 4 + 2));
+        if (!pk.gbox.empty()) CK(cudaMemcpy(d.gbox, pk.gbox.data(), pk.gbox.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dn, pk.nodes.data(), N * sizeof(OctNode), cudaMemcpyHostToDevice));
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
-        { int r = tree_entry_boxes(d, t.polys.size(), p->topo->host.P, HARE_OCT_ENTRY_PBOX != 0); if (r) return r; }
-        d.bytes = N * sizeof(OctNode) + t.polys.size() * (HARE_OCT_ENTRY_PBOX ? 4 : 36) + (HARE_OCT_ENTRY_PBOX ? (size_t)p->topo->host.P * 32 : 0) + cbox.size() * 4 + csph.size() * 4;
+        { int r = tree_entry_boxes(d, t.polys.size(), p->topo->host.P, true); if (r) return r; }
+        d.bytes = N * sizeof(OctNode) + t.polys.size() * 4 + (size_t)p->topo->host.P * 32 + (pk.cbox.size() + pk.gbox.size() + pk.nbox.size()) * 4;
     }
     return HARE_OK;
 }
@@ -1251,31 +1165,45 @@ static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, con
     return launch_vg_walk2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, w, 0, st);
 }
 
-#ifndef HARE_OCT_SBATCH
-#define HARE_OCT_SBATCH 6
+#ifndef HARE_OCTW_SLOTS
+#define HARE_OCTW_SLOTS 64
 #endif
-#ifndef HARE_OCT_NMAX
-#define HARE_OCT_NMAX 6
+#ifndef HARE_OCTW_NMAX
+#define HARE_OCTW_NMAX 4
 #endif
-#ifndef HARE_OCT_NBATCH
-#define HARE_OCT_NBATCH 8
-#endif
-#ifndef HARE_OCT_TBATCH
-#define HARE_OCT_TBATCH 6
-#endif
-static bool use_oct_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_OCT_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
 
-// Octree: phased persistent kernel (oct_walk.cuh), one 512-thread CTA per SM
+// Octree: per-warp wavefront scheduler over shared-memory ray pools (oct_wave.cuh), one CTA of HARE_OCTW_WARPS warps per SM.
+// The spilled traversal frames live in a scratch area allocated stream-ordered for this launch (24 bytes per slot and level).
+template <bool CHAIN, bool COUNT>
+static int launch_oct_wave2(const OctDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
+                            int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+    auto k = oct_wave_kernel<CHAIN, COUNT, HARE_OCTW_SLOTS, HARE_OCTW_NMAX>;
+    const size_t smem = (size_t)HARE_OCTW_WARPS * OctPool<HARE_OCTW_SLOTS>::STRIDE;
+    static_assert((size_t)HARE_OCTW_WARPS * OctPool<HARE_OCTW_SLOTS>::STRIDE <= 227 * 1024, "ray pools exceed the shared memory of an SM");
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = HARE_OCTW_WARPS * 32;
+    const int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms);
+    OctFrames F;
+    F.depth = t.depth + 1;
+    const size_t nfr = (size_t)blocks * HARE_OCTW_WARPS * HARE_OCTW_SLOTS * (size_t)F.depth;
+    void* scratch = nullptr;
+    CK(cudaMallocAsync(&scratch, nfr * (sizeof(double2) + sizeof(uint2)), st));
+    F.ab = reinterpret_cast<double2*>(scratch); F.cq = reinterpret_cast<uint2*>(F.ab + nfr);
+    k<<<(unsigned)blocks, threads, smem, st>>>(t, F, d.polys, o, dd, o1, o2, N, order, w);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    CK(e);
+    return HARE_OK;
+}
+
 template <bool CHAIN>
 static int launch_oct_walk(const OctDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
                            int64_t N, int order, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
-    int64_t blocks = std::min<int64_t>((N + HARE_OCT_THREADS - 1) / HARE_OCT_THREADS, (int64_t)d.sms);
-    if (w.counters) oct_walk_kernel<CHAIN, true, HARE_OCT_SBATCH, HARE_OCT_NMAX, HARE_OCT_NBATCH, HARE_OCT_TBATCH><<<(unsigned)blocks, HARE_OCT_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, N, order, w);
-    else oct_walk_kernel<CHAIN, false, HARE_OCT_SBATCH, HARE_OCT_NMAX, HARE_OCT_NBATCH, HARE_OCT_TBATCH><<<(unsigned)blocks, HARE_OCT_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, N, order, w);
-    ++g_launches;
-    CK(cudaGetLastError());
-    return HARE_OK;
+    if (N >= (1LL << 32) || order >= 65536) return fail(HARE_ERR_INVALID, "Octree Shoot: at most 2^32-1 rays and 65535 bounces per call");
+    if (w.counters) return launch_oct_wave2<CHAIN, true>(t, d, o, dd, o1, o2, N, order, w, st);
+    return launch_oct_wave2<CHAIN, false>(t, d, o, dd, o1, o2, N, order, w, st);
 }
 
 static bool use_kd_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_KD_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
@@ -1489,3 +1417,64 @@ extern "C" int hare_reflect_chain_device(hare_part_t p, const double* o, const d
     ChainArgs a = { o, d, N, order, ev_poly_id, ev_t, fin_o, fin_d, nshots, (unsigned long long*)total_shots_device, (unsigned long long*)counters_device };
     return launch_chain(p, dv, a, cuda_stream ? (cudaStream_t)cuda_stream : dv.stream[0]);
 }
+
+// ---------------------------------------------------------------------------------------
+// host / device buffers, IPC export of result buffers (include/hare_b200.h)
+// ---------------------------------------------------------------------------------------
+extern "C" int hare_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(HARE_ERR_INVALID, "hare_host_alloc: null argument");
+    int rc = ensure_init(); if (rc) return rc;
+    if (g_host_only) return fail(HARE_ERR_CUDA, "hare_host_alloc: host-only mode, no CUDA device");
+    *out = nullptr;
+    CK(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable));
+    return HARE_OK;
+}
+extern "C" int hare_host_free(void* p) { if (p) CK(cudaFreeHost(p)); return HARE_OK; }
+extern "C" int hare_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return fail(HARE_ERR_INVALID, "hare_host_register: null argument");
+    int rc = ensure_init(); if (rc) return rc;
+    if (g_host_only) return fail(HARE_ERR_CUDA, "hare_host_register: host-only mode, no CUDA device");
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return HARE_OK;
+}
+extern "C" int hare_host_unregister(void* p) { if (p) CK(cudaHostUnregister(p)); return HARE_OK; }
+extern "C" int hare_host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
+extern "C" int hare_device_alloc(int device, size_t bytes, void** out) {
+    if (!out) return fail(HARE_ERR_INVALID, "hare_device_alloc: null argument");
+    *out = nullptr;
+    CK(cudaSetDevice(device));
+    CK(cudaMalloc(out, std::max<size_t>(bytes, 1)));
+    return HARE_OK;
+}
+extern "C" int hare_device_free(int device, void* p) { if (p) { CK(cudaSetDevice(device)); CK(cudaFree(p)); } return HARE_OK; }
+extern "C" int hare_device_memcpy(void* dst, const void* src, size_t bytes, int kind, int device) {
+    if (!dst || !src) return fail(HARE_ERR_INVALID, "hare_device_memcpy: null argument");
+    if (kind < 1 || kind > 3) return fail(HARE_ERR_INVALID, "hare_device_memcpy: kind must be 1 (H2D), 2 (D2H) or 3 (D2D)");
+    CK(cudaSetDevice(device));
+    CK(cudaMemcpy(dst, src, bytes, kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice)));
+    return HARE_OK;
+}
+extern "C" int hare_ipc_export(int device, void* dev_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!dev_ptr || !handle) return fail(HARE_ERR_INVALID, "hare_ipc_export: null argument");
+    CK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, dev_ptr));
+    std::memcpy(handle, &h, 64);
+    return HARE_OK;
+}
+extern "C" int hare_ipc_open(int device, const unsigned char handle[64], void** out) {
+    if (!handle || !out) return fail(HARE_ERR_INVALID, "hare_ipc_open: null argument");
+    *out = nullptr;
+    CK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return HARE_OK;
+}
+extern "C" int hare_ipc_close(int device, void* p) { if (p) { CK(cudaSetDevice(device)); CK(cudaIpcCloseMemHandle(p)); } return HARE_OK; }

@@ -125,6 +125,34 @@ HD bool ray_x_tri_fast1(const Ray3& R, double ax, double ay, double az, double b
     return true;
 }
 
+// The slow path (ray_x_tri<true>: Polygon.RayXtri(Ray, Point x3, ref t, ref u, ref v), Hare_Geometry_Polygons.cs:385-435) as one
+// code path for a converged warp: cross products through Hare_math.Cross (y = -(ax*bz - az*bx), Hare_Geometry_Math.cs:66-69),
+// u and v scaled by 1/det (:430-432).  Values are bit-identical to ray_x_tri<true>; u, v are written only on success.
+HD bool ray_x_tri_slow1(const Ray3& R, double ax, double ay, double az, double bx, double by, double bz,
+                        double cx, double cy, double cz, double& t, double& u, double& v) {
+    const double e1x = bx - ax, e1y = by - ay, e1z = bz - az;
+    const double e2x = cx - ax, e2y = cy - ay, e2z = cz - az;
+    const double px = R.dy * e2z - R.dz * e2y;
+    const double py = -(R.dx * e2z - R.dz * e2x);
+    const double pz = R.dx * e2y - R.dy * e2x;
+    const double det = dot3(e1x, e1y, e1z, px, py, pz);
+    const bool pos = det > 0.000001, neg = det < -0.000001;
+    if (!(pos || neg)) return false;
+    const double tx = R.x - ax, ty = R.y - ay, tz = R.z - az;
+    const double uu = dot3(tx, ty, tz, px, py, pz);
+    if (pos ? (uu < 0.0 || uu > det) : (uu > 0.0 || uu < det)) return false;
+    const double qx = ty * e1z - tz * e1y;
+    const double qy = -(tx * e1z - tz * e1x);
+    const double qz = tx * e1y - ty * e1x;
+    const double vv = dot3(R.dx, R.dy, R.dz, qx, qy, qz);
+    const double uv = uu + vv;
+    if (pos ? (vv < 0.0 || uv > det) : (vv > 0.0 || uv < det)) return false;
+    const double invdet = 1.0 / det;
+    t = dot3(e2x, e2y, e2z, qx, qy, qz) * invdet;
+    u = uu * invdet; v = vv * invdet;
+    return true;
+}
+
 // Triangle.Intersect / Quadrilateral.Intersect  (Hare_Geometry_Polygons.cs:637-688, 731-823) with
 // Polygon.Ray_Side (:601-606) choosing the winding.  P = the 16 doubles of a PolyRec.
 // On success writes t (and u, v for SLOW); the caller forms X_Point = o + d*t.

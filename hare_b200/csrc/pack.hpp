@@ -1,0 +1,112 @@
+// pack.hpp -- host-side packing of a built partition into the arrays the traversal kernels read (device layout, DESIGN.md
+// section 4).  Header-only so that tests/emu can build exactly the same arrays for the CPU replay of the kernels.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "host_build.hpp"
+#include "shoot.cuh"
+
+namespace hare {
+
+// padded FP32 bounding box of one polygon (cull_box): exact box -/+ hare_box_pad, rounded outwards.  out = lo xyz, hi xyz
+inline void poly_pad_box(const double* verts12, int vcount, float out[6]) {
+    for (int a = 0; a < 3; ++a) {
+        double lo = verts12[a], hi = lo;
+        for (int k = 1; k < vcount; ++k) { lo = std::min(lo, verts12[3 * k + a]); hi = std::max(hi, verts12[3 * k + a]); }
+        const double pad = hare_box_pad(lo, hi);
+        float bl = (float)(lo - pad), bh = (float)(hi + pad);
+        while ((double)bl > lo - pad) bl = std::nextafter(bl, -INFINITY);
+        while ((double)bh < hi + pad) bh = std::nextafter(bh, INFINITY);
+        out[a] = bl; out[3 + a] = bh;
+    }
+}
+
+struct PackedOct {
+    std::vector<OctNode> nodes;   // box, first_child, list range; pad = content mask of the 8 children (internal) / first chunk index (leaf)
+    std::vector<float> cbox;      // per run of HARE_OCT_CHUNK leaf-list entries: union of the members' padded boxes (lo.xyz, 0, hi.xyz, 0)
+    std::vector<float> gbox;      // per group of 8 runs (a leaf's first run is a multiple of 8)
+    std::vector<float> nbox;      // per node: union of the padded boxes of every polygon listed below it
+};
+
+// pbox6: P x 6 padded polygon boxes (poly_pad_box).  Children have larger indices than their parents (checked at upload).
+inline void pack_octree(const OctTree& t, const float* pbox6, PackedOct& out) {
+    const size_t N = t.first_child.size();
+    out.nodes.resize(N);
+    for (size_t i = 0; i < N; ++i) {
+        OctNode& n = out.nodes[i];
+        n.mnx = t.box[6 * i]; n.mny = t.box[6 * i + 1]; n.mnz = t.box[6 * i + 2]; n.mxx = t.box[6 * i + 3]; n.mxy = t.box[6 * i + 4]; n.mxz = t.box[6 * i + 5];
+        n.first_child = t.first_child[i]; n.list_off = t.list_off[i]; n.list_cnt = t.list_cnt[i]; n.pad = 0;
+    }
+    // internal node: pad = bit c set when the subtree of child c holds at least one polygon: the kernel never enters the others
+    // (entering a polygon-free subtree has no effect on the result)
+    {
+        std::vector<uint8_t> has(N, 0);
+        for (size_t i = N; i-- > 0;) {
+            if (t.first_child[i] < 0) has[i] = t.list_cnt[i] > 0;
+            else {
+                uint32_t m = 0;
+                for (int c = 0; c < 8; ++c) if (has[(size_t)t.first_child[i] + c]) m |= 1u << c;
+                out.nodes[i].pad = m; has[i] = m != 0;
+            }
+        }
+    }
+    // chunk boxes; every leaf starts a multiple of 8 chunks (leaf.pad = its first chunk), gbox[g] encloses chunks 8g .. 8g+7
+    const float kEmptyBox[8] = { INFINITY, INFINITY, INFINITY, 0.f, -INFINITY, -INFINITY, -INFINITY, 0.f };
+    out.cbox.clear(); out.gbox.clear();
+    for (size_t i = 0; i < N; ++i) {
+        if (t.first_child[i] >= 0) continue;
+        while ((out.cbox.size() / 8) % 8) out.cbox.insert(out.cbox.end(), kEmptyBox, kEmptyBox + 8);
+        out.nodes[i].pad = (uint32_t)(out.cbox.size() / 8);
+        for (uint32_t b = 0; b < t.list_cnt[i]; b += HARE_OCT_CHUNK) {
+            const uint32_t e = std::min<uint32_t>(b + HARE_OCT_CHUNK, t.list_cnt[i]);
+            float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+            for (uint32_t k = b; k < e; ++k) {
+                const float* q = pbox6 + 6 * (size_t)t.polys[t.list_off[i] + k];
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[3 + a]); }
+            }
+            const float rec[8] = { lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f };
+            out.cbox.insert(out.cbox.end(), rec, rec + 8);
+        }
+    }
+    for (size_t g = 0; g * 64 < out.cbox.size(); ++g) {
+        float rec[8] = { INFINITY, INFINITY, INFINITY, 0.f, -INFINITY, -INFINITY, -INFINITY, 0.f };
+        for (size_t c = 8 * g; c < 8 * g + 8 && c * 8 < out.cbox.size(); ++c)
+            for (int a = 0; a < 3; ++a) { rec[a] = std::min(rec[a], out.cbox[8 * c + a]); rec[4 + a] = std::max(rec[4 + a], out.cbox[8 * c + 4 + a]); }
+        out.gbox.insert(out.gbox.end(), rec, rec + 8);
+    }
+    // node content boxes, bottom up
+    out.nbox.assign(N * 8, 0.f);
+    for (size_t i = N; i-- > 0;) {
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        if (t.first_child[i] < 0) {
+            for (uint32_t k = 0; k < t.list_cnt[i]; ++k) {
+                const float* q = pbox6 + 6 * (size_t)t.polys[t.list_off[i] + k];
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[3 + a]); }
+            }
+        } else {
+            for (int c = 0; c < 8; ++c) {
+                const float* q = &out.nbox[8 * ((size_t)t.first_child[i] + c)];
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[4 + a]); }
+            }
+        }
+        const float rec[8] = { lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f };
+        std::memcpy(&out.nbox[8 * i], rec, sizeof rec);
+    }
+}
+
+// deepest level of an octree / kd-tree whose children have larger indices than their parents (root = 0)
+inline int oct_depth_of(const OctTree& t) {
+    const size_t N = t.first_child.size();
+    std::vector<int> dep(N, 0);
+    int best = 0;
+    for (size_t i = 0; i < N; ++i) {
+        best = std::max(best, dep[i]);
+        if (t.first_child[i] >= 0) for (int c = 0; c < 8; ++c) dep[(size_t)t.first_child[i] + c] = dep[i] + 1;
+    }
+    return best;
+}
+
+}  // namespace hare

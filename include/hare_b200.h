@@ -19,6 +19,7 @@
 #ifndef HARE_B200_H
 #define HARE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -178,6 +179,31 @@ int hare_reflect_chain(hare_part_t part, const double* o, const double* d, int64
 int hare_reflect_chain_device(hare_part_t part, const double* o, const double* d, int64_t N, int order,
                               int32_t* ev_poly_id, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots,
                               uint64_t* total_shots_device, uint64_t* counters_device, void* cuda_stream);
+
+/* ---- host and device buffers for the batched calls --------------------------------- */
+/* Page-locked host memory.  The reference's callers hold managed arrays; C# `fixed` / GCHandle only pins an array for the
+ * garbage collector -- it does NOT page-lock it for CUDA, and cudaMemcpyAsync from pageable memory is staged and
+ * synchronous, so the two-stream copy/compute pipeline of hare_shoot_batch / hare_reflect_chain degenerates to serial
+ * copies.  Either allocate the ray / event arrays here (hare_host_alloc; wrap the pointer in a Span<T> / Memory<T>), or
+ * page-lock an existing pinned array for the lifetime of the batches (hare_host_register, after GCHandle.Alloc(Pinned)).
+ * hare_host_is_pinned reports how the library sees a pointer (1 page-locked, 0 pageable). */
+int hare_host_alloc(size_t bytes, void** out);
+int hare_host_free(void* p);
+int hare_host_register(void* p, size_t bytes);
+int hare_host_unregister(void* p);
+int hare_host_is_pinned(const void* p);
+
+/* Raw device buffers for the *_device entry points (cudaMalloc on `device`), and their export to the other ranks of a
+ * one-process-per-GPU job: a rank that opened rank 0's result buffers passes those pointers (offset by its first ray) as the
+ * outputs of hare_shoot_batch_device, and the traversal kernel's finish phase stores its X_Event rows straight into rank 0's
+ * memory over NVLink -- the path's only cross-GPU step, fused into the kernel instead of a gather after it.
+ * handle = the 64 bytes of a cudaIpcMemHandle_t. */
+int hare_device_alloc(int device, size_t bytes, void** out);
+int hare_device_free(int device, void* p);
+int hare_device_memcpy(void* dst, const void* src, size_t bytes, int kind /* 1 H2D, 2 D2H, 3 D2D */, int device);
+int hare_ipc_export(int device, void* dev_ptr, unsigned char handle[64]);
+int hare_ipc_open(int device, const unsigned char handle[64], void** out);
+int hare_ipc_close(int device, void* p);
 
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t hare_launch_count(void);
