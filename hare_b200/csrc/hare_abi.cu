@@ -18,6 +18,7 @@
 #include "host_build.hpp"
 #include "kernels.cuh"
 #include "oct_wave.cuh"
+#include "kd_wave.cuh"
 #include "pack.hpp"
 
 using namespace hare;
@@ -82,7 +83,6 @@ struct hare_topo_s {
     HostTopo host;
     std::vector<int> devs;
     std::vector<PolyRec*> d_polys;   // one replica per device
-    std::vector<float> sph;          // host copy of the padded bounding spheres (P x 4)
     std::vector<float> pbox;         // host copy of the padded FP32 bounding boxes (P x 6: lo xyz, hi xyz), see cull_box()
 };
 
@@ -94,8 +94,8 @@ struct PartDev {
     uint2* cells = nullptr; uint32_t* cell_poly = nullptr; uint32_t* occ = nullptr; uint32_t* occp = nullptr; uint32_t* cell_offset = nullptr;
     float4* list_box = nullptr;   // per list entry: padded FP32 bounding box + polygon id (VGrid::lbox; vg_wave.cuh's cull)
     // trees
-    void* nodes = nullptr; uint32_t* lists = nullptr; float4* csph = nullptr;   // csph: octree chunk spheres
-    float4* cbox = nullptr; float4* gbox = nullptr; float4* tbox = nullptr; float4* nbox = nullptr; float4* pbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id); octree node content boxes
+    void* nodes = nullptr; uint32_t* lists = nullptr;
+    double* ref_box = nullptr; float4* cbox = nullptr; float4* gbox = nullptr; float4* tbox = nullptr; float4* nbox = nullptr; float4* pbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id); octree node content boxes
     // staging (per stream), sized for `cap` rays
     int64_t cap = 0;
     double *s_o[2] = {}, *s_d[2] = {}, *s_t[2] = {}, *s_xyz[2] = {}, *s_uv[2] = {}, *s_om[2] = {};
@@ -115,7 +115,7 @@ struct hare_part_s {
     // voxel grid
     double obox[6] = {}, vd[3] = {}; int ct[3] = {}; int64_t npairs = 0;
     // trees (host copies, for *_download and *_info)
-    OctTree oct; KdTree kd;
+    OctTree oct; KdTree kd; bool oct_regular = false;
 };
 
 static void free_partdev(PartDev& d) {
@@ -126,7 +126,7 @@ static void free_partdev(PartDev& d) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occp); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.csph); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.pbox); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occp); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.pbox); cudaFree(d.ref_box); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
@@ -259,7 +259,6 @@ extern "C" int hare_topology_create(const double* verts, const double* normals, 
     std::memcpy(t->host.minmax, minmax, 6 * sizeof(double));
     for (int a = 0; a < 3; ++a) { t->host.vmin[a] = INFINITY; t->host.vmax[a] = -INFINITY; }
     std::vector<PolyRec> recs((size_t)P);
-    std::vector<float> sph((size_t)P * 4);
     t->pbox.resize((size_t)P * 6);
     double part_min[16][3], part_max[16][3];
     for (int k = 0; k < 16; ++k) for (int a = 0; a < 3; ++a) { part_min[k][a] = INFINITY; part_max[k][a] = -INFINITY; }
@@ -275,39 +274,18 @@ extern "C" int hare_topology_create(const double* verts, const double* normals, 
             for (int k = 1; k < vcount[i]; ++k)
                 for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], verts[12 * i + 3 * k + a]); hi[a] = std::max(hi[a], verts[12 * i + 3 * k + a]); }
             for (int a = 0; a < 3; ++a) { if (lo[a] < vmn[a]) vmn[a] = lo[a]; if (hi[a] > vmx[a]) vmx[a] = hi[a]; }
-            // padded bounding sphere in FP32 (centre of the vertex box, radius to the farthest vertex, padded by 1e-3 + 1e-5
-            // relative, which covers the FP32 evaluation in cull_sphere()): a conservative reject, stored right after the records
-            float cf[3]; double r2 = 0;
-            for (int a = 0; a < 3; ++a) cf[a] = (float)(0.5 * (lo[a] + hi[a]));
-            for (int k = 0; k < vcount[i]; ++k) {
-                double q = 0;
-                for (int a = 0; a < 3; ++a) { double dlt = verts[12 * i + 3 * k + a] - (double)cf[a]; q += dlt * dlt; }
-                r2 = std::max(r2, q);
-            }
-            const double r = std::sqrt(r2) * (1.0 + 1e-5) + 1e-3;
-            float rf = (float)r;
-            while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
-            sph[4 * i] = cf[0]; sph[4 * i + 1] = cf[1]; sph[4 * i + 2] = cf[2]; sph[4 * i + 3] = rf;
-            // padded FP32 bounding box (second conservative reject, cull_box): exact box -/+ hare_box_pad, rounded outwards
-            for (int a = 0; a < 3; ++a) {
-                const double pad = hare_box_pad(lo[a], hi[a]);
-                float bl = (float)(lo[a] - pad), bh = (float)(hi[a] + pad);
-                while ((double)bl > lo[a] - pad) bl = std::nextafter(bl, -INFINITY);
-                while ((double)bh < hi[a] + pad) bh = std::nextafter(bh, INFINITY);
-                t->pbox[6 * i + a] = bl; t->pbox[6 * i + 3 + a] = bh;
-            }
+            // padded FP32 bounding box (the conservative reject cull_box): exact box -/+ hare_box_pad, rounded outwards
+            poly_pad_box(verts + 12 * i, vcount[i], &t->pbox[6 * i]);
         }
     });
     for (int k = 0; k < 16; ++k)
         for (int a = 0; a < 3; ++a) { t->host.vmin[a] = std::min(t->host.vmin[a], part_min[k][a]); t->host.vmax[a] = std::max(t->host.vmax[a], part_max[k][a]); }
-    t->sph = sph;
     { std::lock_guard<std::mutex> lk(g_mu); t->devs = g_devices; }
     for (int dev : t->devs) {
         PolyRec* d = nullptr;
         cudaError_t e = cudaSetDevice(dev);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d, (size_t)P * (sizeof(PolyRec) + 16));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d, (size_t)P * sizeof(PolyRec));
         if (e == cudaSuccess) e = cudaMemcpy(d, recs.data(), (size_t)P * sizeof(PolyRec), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d + P, sph.data(), (size_t)P * 16, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             for (size_t k = 0; k < t->d_polys.size(); ++k) { cudaSetDevice(t->devs[k]); cudaFree(t->d_polys[k]); }
             cudaFree(d); delete t;
@@ -349,7 +327,6 @@ static VGrid make_vgrid(const hare_part_s* p, const PartDev& d) {
     g.vdx = p->vd[0]; g.vdy = p->vd[1]; g.vdz = p->vd[2];
     g.nx = p->ct[0]; g.ny = p->ct[1]; g.nz = p->ct[2];
     g.cells = d.cells; g.cell_poly = d.cell_poly; g.occ = d.occ; g.occp = d.occp;
-    g.sph = reinterpret_cast<const float4*>(d.polys + p->topo->host.P);   // spheres follow the records
     g.lbox = d.list_box;
     return g;
 }
@@ -375,9 +352,6 @@ static int vg_set_dims(hare_part_s* p, const double obox[6], const int32_t ct[3]
     return HARE_OK;
 }
 
-// HARE_VG_LBOX=0 leaves the per-entry boxes out (A/B measurements; 32 bytes per list entry); the cull then uses the spheres
-static bool use_lbox() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_LBOX"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
-
 static int vg_make_list_box(PartDev& d, uint32_t total, cudaStream_t st, const int ct[3]) {
     {   // the wavefront kernel's border-padded occupancy bitmap
         const int64_t padded = ((int64_t)ct[0] + 2) * ((int64_t)ct[1] + 2) * ((int64_t)ct[2] + 2);
@@ -388,7 +362,7 @@ static int vg_make_list_box(PartDev& d, uint32_t total, cudaStream_t st, const i
             CK(cudaGetLastError());
         }
     }
-    if (!use_lbox() || total == 0) return HARE_OK;
+    if (total == 0) return HARE_OK;
     CK(dmalloc(&d.list_box, 2 * (size_t)total));
     vg_gather_list_box<<<(unsigned)(((int64_t)total + 255) / 256), 256, 0, st>>>(d.cell_poly, d.polys, total, d.list_box);
     ++g_launches;
@@ -446,7 +420,7 @@ extern "C" int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* o
             if (r) return r;
             CK(cudaStreamSynchronize(st));
             cudaFree(count); cudaFree(cursor); cudaFree(tiles);
-            d.bytes = (size_t)ncells * 12 + (size_t)total * (d.list_box ? 36 : 4) + (size_t)ncells / 8;
+            d.bytes = (size_t)ncells * 12 + (size_t)total * 36 + (size_t)ncells / 8;
             return HARE_OK;
         };
         rc = body();
@@ -516,7 +490,7 @@ extern "C" int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], con
             int r = vg_make_list_box(d, total, st, ct);
             if (r) return r;
             CK(cudaStreamSynchronize(st));
-            d.bytes = (size_t)ncells * 12 + (size_t)total * (d.list_box ? 36 : 4) + (size_t)ncells / 8;
+            d.bytes = (size_t)ncells * 12 + (size_t)total * 36 + (size_t)ncells / 8;
             return HARE_OK;
         };
         rc = body();
@@ -584,6 +558,7 @@ static int oct_to_device(hare_part_s* p) {
     // node records (content masks, chunk indices), chunk / group boxes and node content boxes: pack.hpp (shared with tests/emu)
     PackedOct pk;
     pack_octree(t, p->topo->pbox.data(), pk);
+    p->oct_regular = pk.regular;
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         OctNode* dn = nullptr;
@@ -825,60 +800,23 @@ static int kd_depth(const KdTree& t) {
     return best;
 }
 
-// HARE_KD_TIGHT=0 keeps the reference's node boxes on the device (A/B measurements)
-static bool use_kd_tight() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_KD_TIGHT"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
-
 static int kd_to_device(hare_part_s* p) {
     const KdTree& t = p->kd;
     const size_t N = t.axis.size();
     if (kd_depth(t) + 2 > HARE_KD_MAXSTACK) return fail(HARE_ERR_UNSUPPORTED, "kd-tree deeper than HARE_KD_MAXSTACK allows");
-    // Device node boxes = the reference's node box (KDTree.cs:68-83, 107-121) INTERSECTED with the bounding box of the polygons
-    // listed below the node.  The walk only uses a node box to decide that no polygon of the subtree can be hit at
-    // t <= closest inside it (kd_box_reachable); a hit point inside the node box lies on a listed polygon, hence inside
-    // that polygon's bounding box too, so the intersection prunes the same way -- it is just far tighter for the many
-    // leaves that hold a sliver of a wall in a box of air.  hare_kdtree_download still returns the reference's boxes.
-    std::vector<double> tight(t.box);
-    if (use_kd_tight()) {
-        const HostTopo& M = p->topo->host;
-        std::vector<double> content(6 * N);
-        std::vector<std::pair<int, int>> st; st.push_back({ 0, 0 });   // (node, 0 = enter / 1 = leave)
-        while (!st.empty()) {
-            auto [n, leave] = st.back(); st.pop_back();
-            double* cb = &content[6 * (size_t)n];
-            if (t.left[n] < 0) {
-                for (int a = 0; a < 3; ++a) { cb[a] = INFINITY; cb[3 + a] = -INFINITY; }
-                for (uint32_t k = 0; k < t.list_cnt[n]; ++k) {
-                    const int64_t q = t.polys[t.list_off[n] + k];
-                    for (int v = 0; v < M.vcount[q]; ++v)
-                        for (int a = 0; a < 3; ++a) { const double c = M.verts[12 * q + 3 * v + a]; cb[a] = std::min(cb[a], c); cb[3 + a] = std::max(cb[3 + a], c); }
-                }
-            } else if (!leave) {
-                st.push_back({ n, 1 }); st.push_back({ t.left[n], 0 }); st.push_back({ t.left[n] + 1, 0 });
-                continue;
-            } else {
-                const double *l = &content[6 * (size_t)t.left[n]], *r = l + 6;
-                for (int a = 0; a < 3; ++a) { cb[a] = std::min(l[a], r[a]); cb[3 + a] = std::max(l[3 + a], r[3 + a]); }
-            }
-            for (int a = 0; a < 3; ++a) { tight[6 * (size_t)n + a] = std::max(tight[6 * (size_t)n + a], cb[a]); tight[6 * (size_t)n + 3 + a] = std::min(tight[6 * (size_t)n + 3 + a], cb[3 + a]); }
-        }
-    }
-    std::vector<KdNode> nodes(N);
-    for (size_t i = 0; i < N; ++i) {
-        KdNode& n = nodes[i];
-        n.mnx = tight[6 * i]; n.mny = tight[6 * i + 1]; n.mnz = tight[6 * i + 2]; n.mxx = tight[6 * i + 3]; n.mxy = tight[6 * i + 4]; n.mxz = tight[6 * i + 5];
-        n.left = t.left[i]; n.axis = t.left[i] >= 0 ? t.axis[i] : 0;
-        if (t.left[i] >= 0) n.split = t.split[i];
-        else { uint64_t bits = (uint64_t)t.list_off[i] | ((uint64_t)t.list_cnt[i] << 32); std::memcpy(&n.split, &bits, 8); }
-    }
+    std::vector<KdNode> nodes;
+    pack_kdtree(t, p->topo->host, nodes);   // content-tightened node boxes (pack.hpp)
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         KdNode* dn = nullptr;
         CK(dmalloc(&dn, N)); d.nodes = dn;
-        CK(dmalloc(&d.lists, t.polys.size()));
+        CK(dmalloc(&d.lists, t.polys.size() + 8));
+        CK(dmalloc(&d.ref_box, 6 * N));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(KdNode), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d.ref_box, t.box.data(), 6 * N * sizeof(double), cudaMemcpyHostToDevice));   // the reference's boxes: tie rule only
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
-        { int r = tree_entry_boxes(d, t.polys.size(), p->topo->host.P, HARE_KD_ENTRY_PBOX != 0); if (r) return r; }
-        d.bytes = N * sizeof(KdNode) + t.polys.size() * (HARE_KD_ENTRY_PBOX ? 4 : 36) + (HARE_KD_ENTRY_PBOX ? (size_t)p->topo->host.P * 32 : 0);
+        { int r = tree_entry_boxes(d, t.polys.size(), p->topo->host.P, false); if (r) return r; }
+        d.bytes = N * (sizeof(KdNode) + 48) + t.polys.size() * 36;
     }
     return HARE_OK;
 }
@@ -1062,53 +1000,13 @@ struct ShootArgs {
     double *t, *xyz; int32_t* pid; double *uv, *om; unsigned long long* counters;
 };
 
-template <class PART>
-static int launch_shoot_t(const PART& part, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
-    if (a.N <= 0) return HARE_OK;
-    const int threads = 128;
-    int64_t blocks = std::min<int64_t>((a.N + threads - 1) / threads, (int64_t)d.sms * 16);
-    if (a.counters)
-        shoot_kernel<PART, true><<<(unsigned)blocks, threads, 0, st>>>(part, d.polys, a.o, a.d, a.o1, a.o2, a.rid, a.N, a.t, a.xyz, a.pid, a.uv, a.om, a.counters);
-    else
-        shoot_kernel<PART, false><<<(unsigned)blocks, threads, 0, st>>>(part, d.polys, a.o, a.d, a.o1, a.o2, a.rid, a.N, a.t, a.xyz, a.pid, a.uv, a.om, nullptr);
-    ++g_launches;
-    CK(cudaGetLastError());
-    return HARE_OK;
-}
-
-#ifndef HARE_VG_SBATCH
-#define HARE_VG_SBATCH 6
-#endif
-#ifndef HARE_VG_WMAX
-#define HARE_VG_WMAX 4
-#endif
-static bool use_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
-
-// Voxel_Grid: phased persistent kernel (vg_walk.cuh); one launch covers Shoot batches and chains.
-// One 512-thread CTA per SM; the occupancy bitmap rides in shared memory when it fits (<= 200 KB,
-// i.e. up to ~117^3 voxels), otherwise it is read through L1.
-template <bool CHAIN, bool COUNT, bool OCC_SMEM>
-static int launch_vg_walk2(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
-                           const int32_t* rid, int64_t N, int order, const WalkOut& w, size_t smem, cudaStream_t st) {
-    auto k = vg_walk_kernel<CHAIN, COUNT, OCC_SMEM, HARE_VG_SBATCH, HARE_VG_WMAX>;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = std::min<int64_t>((N + HARE_VG_THREADS - 1) / HARE_VG_THREADS, (int64_t)d.sms);
-    k<<<(unsigned)blocks, HARE_VG_THREADS, smem, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
-    ++g_launches;
-    CK(cudaGetLastError());
-    return HARE_OK;
-}
-
 #ifndef HARE_WAVE_SLOTS
 #define HARE_WAVE_SLOTS 64
 #endif
 #ifndef HARE_WAVE_WMAX
 #define HARE_WAVE_WMAX 8
 #endif
-// HARE_VG_WAVE=0 selects the first-generation kernel (vg_walk.cuh) for A/B measurements
-static bool use_wave() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_VG_WAVE"); v = (e && *e == '0') ? 0 : 1; } return v == 1; }
-
-// Voxel_Grid, second generation: per-warp wavefront scheduler over shared-memory ray pools (vg_wave.cuh).
+// Voxel_Grid: per-warp wavefront scheduler over shared-memory ray pools (vg_wave.cuh).
 // One CTA of HARE_WAVE_WARPS warps per SM; dynamic shared memory = occupancy bitmap (when it fits) + the pools.
 template <bool CHAIN, bool COUNT, bool OCC_SMEM>
 static int launch_vg_wave2(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
@@ -1124,11 +1022,6 @@ static int launch_vg_wave2(const VGrid& g, const PartDev& d, const double* o, co
 }
 
 static const size_t kSmemMax = 227 * 1024;
-
-// the wavefront kernel needs the padded bitmap (grids below 2^32 padded voxels), packs ray numbers into 32 bits and the bounce into 16
-static bool wave_eligible(const VGrid& g, int64_t N, int order) {
-    return use_wave() && g.occp && N < (1LL << 32) && order < 65536;
-}
 
 template <bool CHAIN>
 static int launch_vg_wave(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
@@ -1154,15 +1047,10 @@ template <bool CHAIN>
 static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
                           const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
-    if (wave_eligible(g, N, order)) return launch_vg_wave<CHAIN>(g, d, o, dd, o1, o2, rid, N, order, w, st);
-    const size_t occ_bytes = (((size_t)g.nx * g.ny * g.nz + 31) / 32) * 4;
-    const bool in_smem = occ_bytes <= 200 * 1024;
-    if (w.counters) {
-        if (in_smem) return launch_vg_walk2<CHAIN, true, true>(g, d, o, dd, o1, o2, rid, N, order, w, occ_bytes, st);
-        return launch_vg_walk2<CHAIN, true, false>(g, d, o, dd, o1, o2, rid, N, order, w, 0, st);
-    }
-    if (in_smem) return launch_vg_walk2<CHAIN, false, true>(g, d, o, dd, o1, o2, rid, N, order, w, occ_bytes, st);
-    return launch_vg_walk2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, w, 0, st);
+    // the kernel packs ray numbers into 32 bits and the bounce into 16, and walks the border-padded bitmap (grids below 2^32 padded voxels)
+    if (N >= (1LL << 32) || order >= 65536) return fail(HARE_ERR_INVALID, "Voxel_Grid Shoot: at most 2^32-1 rays and 65535 bounces per call");
+    if (!g.occp) return fail(HARE_ERR_UNSUPPORTED, "Voxel_Grid Shoot: grid with 2^32 or more padded voxels");
+    return launch_vg_wave<CHAIN>(g, d, o, dd, o1, o2, rid, N, order, w, st);
 }
 
 #ifndef HARE_OCTW_SLOTS
@@ -1206,37 +1094,60 @@ static int launch_oct_walk(const OctDev& t, const PartDev& d, const double* o, c
     return launch_oct_wave2<CHAIN, false>(t, d, o, dd, o1, o2, N, order, w, st);
 }
 
-static bool use_kd_v1() { static int v = -1; if (v < 0) { const char* e = getenv("HARE_KD_V1"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
+#ifndef HARE_KDW_SLOTS
+#define HARE_KDW_SLOTS 64
+#endif
+#ifndef HARE_KDW_NMAX
+#define HARE_KDW_NMAX 4
+#endif
 
-// KDTree: phased persistent kernel (kd_walk.cuh)
+// KDTree: per-warp wavefront scheduler over shared-memory ray pools (kd_wave.cuh); the stacks of pending far children live in a
+// scratch area allocated stream-ordered for this launch (4 bytes per slot and level)
+template <bool CHAIN, bool COUNT>
+static int launch_kd_wave2(const KdDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2, const int32_t* rid,
+                           int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+    auto k = kd_wave_kernel<CHAIN, COUNT, HARE_KDW_SLOTS, HARE_KDW_NMAX>;
+    const size_t smem = (size_t)HARE_KDW_WARPS * KdPool<HARE_KDW_SLOTS>::STRIDE;
+    static_assert((size_t)HARE_KDW_WARPS * KdPool<HARE_KDW_SLOTS>::STRIDE <= 227 * 1024, "ray pools exceed the shared memory of an SM");
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = HARE_KDW_WARPS * 32;
+    const int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms);
+    KdStacks S;
+    S.depth = t.depth + 2;
+    const size_t n = (size_t)blocks * HARE_KDW_WARPS * HARE_KDW_SLOTS * (size_t)S.depth;
+    void* scratch = nullptr;
+    CK(cudaMallocAsync(&scratch, n * sizeof(uint32_t), st));
+    S.st = reinterpret_cast<uint32_t*>(scratch);
+    k<<<(unsigned)blocks, threads, smem, st>>>(t, S, d.polys, o, dd, o1, o2, rid, N, order, w);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    CK(e);
+    return HARE_OK;
+}
+
 template <bool CHAIN>
 static int launch_kd_walk(const KdDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2, const int32_t* rid,
                           int64_t N, int order, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
-    int64_t blocks = std::min<int64_t>((N + HARE_KD_THREADS - 1) / HARE_KD_THREADS, (int64_t)d.sms);
-    if (w.counters) kd_walk_kernel<CHAIN, true, HARE_OCT_SBATCH, HARE_OCT_NMAX, HARE_OCT_NBATCH, HARE_OCT_TBATCH><<<(unsigned)blocks, HARE_KD_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, rid, N, order, w);
-    else kd_walk_kernel<CHAIN, false, HARE_OCT_SBATCH, HARE_OCT_NMAX, HARE_OCT_NBATCH, HARE_OCT_TBATCH><<<(unsigned)blocks, HARE_KD_THREADS, 0, st>>>(t, d.polys, o, dd, o1, o2, rid, N, order, w);
-    ++g_launches;
-    CK(cudaGetLastError());
-    return HARE_OK;
+    if (N >= (1LL << 32) || order >= 65536) return fail(HARE_ERR_INVALID, "KDTree Shoot: at most 2^32-1 rays and 65535 bounces per call");
+    if (w.counters) return launch_kd_wave2<CHAIN, true>(t, d, o, dd, o1, o2, rid, N, order, w, st);
+    return launch_kd_wave2<CHAIN, false>(t, d, o, dd, o1, o2, rid, N, order, w, st);
 }
 
 static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
     switch (p->kind) {
         case HARE_VOXEL_GRID: {
-            if (use_v1()) return launch_shoot_t(make_vgrid(p, d), d, a, st);
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.gbox, d.tbox, d.pbox, d.nbox, p->oct.depth };
-            if (use_oct_v1()) return launch_shoot_t(t, d, a, st);
+            OctDev t = { (const OctNode*)d.nodes, d.lists, d.cbox, d.gbox, d.pbox, d.nbox, p->oct.depth, p->oct_regular ? 1 : 0 };
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
         }
         case HARE_KDTREE: {
-            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.tbox, d.pbox, p->kd.depth };
-            if (use_kd_v1()) return launch_shoot_t(t, d, a, st);
+            KdDev t = { (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
             WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
             return launch_kd_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
         }
@@ -1250,36 +1161,19 @@ struct ChainArgs {
     unsigned long long *total, *counters;
 };
 
-template <class PART>
-static int launch_chain_t(const PART& part, const PartDev& d, const ChainArgs& a, cudaStream_t st) {
-    if (a.N <= 0) return HARE_OK;
-    const int threads = 128;
-    int64_t blocks = std::min<int64_t>((a.N + threads - 1) / threads, (int64_t)d.sms * 16);
-    if (a.counters)
-        chain_kernel<PART, true><<<(unsigned)blocks, threads, 0, st>>>(part, d.polys, a.o, a.d, a.N, a.order, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters);
-    else
-        chain_kernel<PART, false><<<(unsigned)blocks, threads, 0, st>>>(part, d.polys, a.o, a.d, a.N, a.order, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, nullptr);
-    ++g_launches;
-    CK(cudaGetLastError());
-    return HARE_OK;
-}
-
 static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cudaStream_t st) {
     switch (p->kind) {
         case HARE_VOXEL_GRID: {
-            if (use_v1()) return launch_chain_t(make_vgrid(p, d), d, a, st);
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_OCTREE: {
-            OctDev t = { (const OctNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.csph, d.cbox, d.gbox, d.tbox, d.pbox, d.nbox, p->oct.depth };
-            if (use_oct_v1()) return launch_chain_t(t, d, a, st);
+            OctDev t = { (const OctNode*)d.nodes, d.lists, d.cbox, d.gbox, d.pbox, d.nbox, p->oct.depth, p->oct_regular ? 1 : 0 };
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);
         }
         case HARE_KDTREE: {
-            KdDev t = { (const KdNode*)d.nodes, d.lists, reinterpret_cast<const float4*>(d.polys + p->topo->host.P), d.tbox, d.pbox, p->kd.depth };
-            if (use_kd_v1()) return launch_chain_t(t, d, a, st);
+            KdDev t = { (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_kd_walk<true>(t, d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
         }

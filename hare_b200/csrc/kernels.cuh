@@ -1,8 +1,7 @@
-// kernels.cuh -- __global__ entry points (sm_100a).
-//
-//   shoot_kernel<PART>    K1/K3/K4: batched Shoot, one ray per thread, persistent grid-stride loop
-//   chain_kernel<PART>    K5: specular reflection chains kept on the device
+// kernels.cuh -- __global__ entry points of the build path (sm_100a); the traversal kernels live in vg_wave.cuh / oct_wave.cuh /
+// kd_wave.cuh.
 //   vg_* kernels          K2: Voxel_Grid cell-list build (count -> scan -> scatter -> per-cell sort)
+//   oct_* kernels         GPU Octree build (level-synchronous SAT masks, scan, order-preserving scatter)
 #pragma once
 #include <cstdint>
 #include "hare_math.cuh"
@@ -10,92 +9,6 @@
 #include "shoot.cuh"
 
 namespace hare {
-
-template <bool COUNT>
-__device__ __forceinline__ void flush_counters(const CntT<COUNT>& c, unsigned long long* __restrict__ counters) {
-    if (!COUNT) return;
-    unsigned int v[4] = { c.cells, c.entries, c.tests, c.hits };
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        unsigned int s = v[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if ((threadIdx.x & 31) == 0 && s) atomicAdd(counters + k, (unsigned long long)s);
-    }
-}
-
-}  // namespace hare
-#include "vg_walk.cuh"
-#include "vg_wave.cuh"
-#include "oct_walk.cuh"
-#include "kd_walk.cuh"
-namespace hare {
-
-template <class PART, bool COUNT>
-__global__ void __launch_bounds__(128)
-shoot_kernel(const PART part, const PolyRec* __restrict__ polys,
-             const double* __restrict__ o, const double* __restrict__ d,
-             const int32_t* __restrict__ o1, const int32_t* __restrict__ o2, const int32_t* __restrict__ rid,
-             long long N, double* __restrict__ t, double* __restrict__ xyz, int32_t* __restrict__ pid,
-             double* __restrict__ uv, double* __restrict__ omoved, unsigned long long* __restrict__ counters) {
-    CntT<COUNT> c;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        Ray3 R = { o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2] };
-        Event ev;
-        const bool blind = rid ? (rid[i] == 0) : false;
-        shoot_one<COUNT>(part, polys, R, o1 ? o1[i] : -1, o2 ? o2[i] : -1, blind, ev, c);
-        pid[i] = ev.pid;
-        if (t) t[i] = ev.t;
-        if (xyz) { xyz[3 * i] = ev.x; xyz[3 * i + 1] = ev.y; xyz[3 * i + 2] = ev.z; }
-        if (uv) { uv[2 * i] = ev.u; uv[2 * i + 1] = ev.v; }
-        if (omoved) { omoved[3 * i] = R.x; omoved[3 * i + 1] = R.y; omoved[3 * i + 2] = R.z; }
-    }
-    flush_counters<COUNT>(c, counters);
-}
-
-// Reflection chain (harness-defined): after a hit on polygon p with unit normal n,
-//   k = 2*((dx*nx)+(dy*ny)+(dz*nz)); d' = (dx - k*nx, dy - k*ny, dz - k*nz); o' = X_Point; poly_origin1 = p.
-template <class PART, bool COUNT>
-__global__ void __launch_bounds__(128)
-chain_kernel(const PART part, const PolyRec* __restrict__ polys,
-             const double* __restrict__ o, const double* __restrict__ d, long long N, int order,
-             int32_t* __restrict__ ev_pid, double* __restrict__ ev_t,
-             double* __restrict__ fin_o, double* __restrict__ fin_d, int32_t* __restrict__ nshots,
-             unsigned long long* __restrict__ total_shots, unsigned long long* __restrict__ counters) {
-    CntT<COUNT> c;
-    unsigned int shots = 0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        Ray3 R = { o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2] };
-        int origin = -1, b = 0;
-        for (; b < order; ++b) {
-            Event ev;
-            const int st = shoot_one<COUNT>(part, polys, R, origin, -1, false, ev, c);
-            if (ev_pid) ev_pid[i * order + b] = ev.pid;
-            if (ev_t) ev_t[i * order + b] = ev.t;
-            if (st != 1) { ++b; break; }
-            const double* P = polys[ev.pid].v;
-            const double nx = __ldg(P + 12), ny = __ldg(P + 13), nz = __ldg(P + 14);
-            const double k = 2 * ((R.dx * nx) + (R.dy * ny) + (R.dz * nz));
-            R.dx = R.dx - k * nx; R.dy = R.dy - k * ny; R.dz = R.dz - k * nz;
-            R.x = ev.x; R.y = ev.y; R.z = ev.z;
-            origin = ev.pid;
-        }
-        shots += (unsigned int)b;
-        for (int q = b; q < order; ++q) {
-            if (ev_pid) ev_pid[i * order + q] = -3;
-            if (ev_t) ev_t[i * order + q] = 0;
-        }
-        if (fin_o) { fin_o[3 * i] = R.x; fin_o[3 * i + 1] = R.y; fin_o[3 * i + 2] = R.z; }
-        if (fin_d) { fin_d[3 * i] = R.dx; fin_d[3 * i + 1] = R.dy; fin_d[3 * i + 2] = R.dz; }
-        if (nshots) nshots[i] = b;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) shots += __shfl_xor_sync(0xffffffffu, shots, off);
-    if ((threadIdx.x & 31) == 0 && shots) atomicAdd(total_shots, (unsigned long long)shots);
-    flush_counters<COUNT>(c, counters);
-}
 
 // ---------------------------------------------------------------------------------------
 // K2: Voxel_Grid build.  Voxel_Grid(Model, Domain) tests every voxel against every polygon

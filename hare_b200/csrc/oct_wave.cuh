@@ -37,9 +37,11 @@ enum : uint32_t {
     OFL_NORAY = 1u, OFL_FIN_SHIFT = 1, OFL_FIN_MASK = 3u << 1, OFL_HIT = 8u,
     OFL_SGN_SHIFT = 4, OFL_SGN_MASK = 7u << 4, OFL_SP_SHIFT = 7, OFL_SP_MASK = 31u << 7, OFL_BOUNCE_SHIFT = 16
 };
-// OU_MASKS: qmask (octants of the top frame still to pop) | emask << 8 (surviving chunks of the current group) | bmask << 16 (surviving entries of the current chunk)
+// OU_MASKS: qmask (octants of the top frame still to pop) | emask << 8 (surviving chunks of the current group) | bmask << 16 (surviving entries of the
+// current chunk) | kc << 24 (which chunk of the group that is) | OM_PEND (OU_PEND holds the id of the lowest surviving entry)
+enum : uint32_t { OM_KC_SHIFT = 24, OM_KC_MASK = 7u << 24, OM_PEND = 1u << 27 };
 enum { OD_OX, OD_OY, OD_OZ, OD_DX, OD_DY, OD_DZ, OD_IX, OD_IY, OD_IZ, OD_CLOSEST, OD_EU, OD_EV, OD_CA, OD_FA, OD_FB, OD_COUNT };
-enum { OU_FLAGS, OU_RAY, OU_PID, OU_OR1, OU_OR2, OU_LAST, OU_LPOS, OU_LEND, OU_CIDX, OU_CPOS, OU_CBASE, OU_FCHILD, OU_MASKS, OU_COUNT };
+enum { OU_FLAGS, OU_RAY, OU_PID, OU_OR1, OU_OR2, OU_LAST, OU_LPOS, OU_LEND, OU_CIDX, OU_CPOS, OU_PEND, OU_FCHILD, OU_MASKS, OU_COUNT };
 enum { OF_PX, OF_PY, OF_PZ, OF_COUNT };   // cull_box frame point, already divided by d (FP32)
 
 template <int SLOTS>
@@ -95,12 +97,33 @@ HD int oct_pick(const int n[OP_COUNT]) {
     return bn > 0 ? best : -1;
 }
 
+// 16-byte read-only loads of a node record, issued where they are written: the compiler must not sink the rarely used words
+// (first_child / list range) below the culls, that would cost the entering lanes a second L2 round trip
+HD double2 oct_ld_d2(const double2* q) {
+#if defined(__CUDA_ARCH__)
+    double2 r; asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(q)); return r;
+#else
+    return *q;
+#endif
+}
+HD uint4 oct_ld_u4(const uint4* q) {
+#if defined(__CUDA_ARCH__)
+    uint4 r; asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(q)); return r;
+#else
+    return *q;
+#endif
+}
+HD float4 oct_ld_f4(const float4* q) {
+#if defined(__CUDA_ARCH__)
+    float4 r; asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(q)); return r;
+#else
+    return *q;
+#endif
+}
+
 // child interval of a ray with finite components ("Octree - alt.cs":252-266; see oct_interval_finite in shoot.cuh)
-HD void oct_interval_hd(const OctNode* __restrict__ n, double ox, double oy, double oz, double ix, double iy, double iz, double& lo, double& hi, uint4& meta) {
-    const double2* q = reinterpret_cast<const double2*>(n);
-    const double2 a = hare_ldg(q), b = hare_ldg(q + 1), cc = hare_ldg(q + 2);   // mnx,mny | mnz,mxx | mxy,mxz
-    meta = hare_ldg(reinterpret_cast<const uint4*>(n) + 3);                      // first_child, list_off, list_cnt, pad
-    double tx0 = (a.x - ox) * ix, tx1 = (b.y - ox) * ix;
+HD void oct_interval_of(const double2 a, const double2 b, const double2 cc, double ox, double oy, double oz, double ix, double iy, double iz, double& lo, double& hi) {
+    double tx0 = (a.x - ox) * ix, tx1 = (b.y - ox) * ix;      // a = mnx,mny | b = mnz,mxx | cc = mxy,mxz
     double ty0 = (a.y - oy) * iy, ty1 = (cc.x - oy) * iy;
     double tz0 = (b.x - oz) * iz, tz1 = (cc.y - oz) * iz;
     if (ix < 0) { double s = tx0; tx0 = tx1; tx1 = s; }
@@ -112,10 +135,52 @@ HD void oct_interval_hd(const OctNode* __restrict__ n, double ox, double oy, dou
 
 // near->far permutation of a node's content mask: bit q = octant (q ^ sgn) holds polygons
 HD uint32_t oct_perm_mask(uint32_t content, int sgn) {
-    uint32_t pm = 0;
+    // q -> q ^ sgn permutes the bits by up to three swaps: neighbours (sgn & 1), pairs (sgn & 2), nibbles (sgn & 4)
+    uint32_t m = content & 0xffu;
+    m = (sgn & 1) ? (((m & 0xaau) >> 1) | ((m & 0x55u) << 1)) : m;
+    m = (sgn & 2) ? (((m & 0xccu) >> 2) | ((m & 0x33u) << 2)) : m;
+    m = (sgn & 4) ? (((m & 0xf0u) >> 4) | ((m & 0x0fu) << 4)) : m;
+    return m;
+}
+
+// Push-time filter of all eight children at once ("Octree - alt.cs":252-268), from the PARENT's box: BuildOctree derives a child's
+// box from its parent's (:99-114: centre = (Max + Min) / 2; Min = (bit ? centre : Min) - 0.1, Max = (bit ? Max : centre) + 0.1), so per
+// axis there are only four planes and the eight child intervals share twelve slab parameters.  The expressions are the builder's and
+// the interval code's, so every value equals what oct_interval_of() gets from the child's stored box (OctDev::regular: checked
+// against the stored boxes when the tree is uploaded; an irregular tree skips this filter and relies on the per-child one).
+// Returns the mask in near->far order: bit q = child (q ^ sgn) passes.
+HD uint32_t oct_child_filter(const double2 a, const double2 b, const double2 cc, double ox, double oy, double oz, double ix, double iy, double iz,
+                             double fa, double fb, int sgn) {
+    const double mn[3] = { a.x, a.y, b.x }, mx[3] = { b.y, cc.x, cc.y }, o[3] = { ox, oy, oz }, inv[3] = { ix, iy, iz };
+    double p[3][2], q[3][2];   // [axis][half]: entry / exit parameter of the lower (0) and upper (1) half's slab
 #pragma unroll
-    for (int q = 0; q < 8; ++q) pm |= ((content >> (q ^ sgn)) & 1u) << q;
-    return pm;
+    for (int k = 0; k < 3; ++k) {
+        const double mid = (mx[k] + mn[k]) / 2;
+        const double l0 = mn[k] - 0.1, h0 = mid + 0.1, l1 = mid - 0.1, h1 = mx[k] + 0.1;
+        double p0 = (l0 - o[k]) * inv[k], q0 = (h0 - o[k]) * inv[k], p1 = (l1 - o[k]) * inv[k], q1 = (h1 - o[k]) * inv[k];
+        if (inv[k] < 0) { double t = p0; p0 = q0; q0 = t; t = p1; p1 = q1; q1 = t; }
+        p[k][0] = p0; q[k][0] = q0; p[k][1] = p1; q[k][1] = q1;
+    }
+    // A child is skipped when hi < lo || hi < 0 || lo > b || hi < a with lo = max of its three entries p, hi = min of its three exits q
+    // (all finite): that is, when some exit lies below some entry of another axis, below 0 or below a, or some entry above b.  Each of
+    // these comparisons is shared by the two or four children on that side, so the eight verdicts take 42 comparisons and no min/max.
+    const uint32_t side[3][2] = { { 0x0fu, 0xf0u }, { 0x33u, 0xccu }, { 0x55u, 0xaau } };   // children in the lower / upper half of x, y, z
+    uint32_t m = 0xffu;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            m &= (q[k][h] < 0 || q[k][h] < fa || p[k][h] > fb) ? ~side[k][h] : 0xffu;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int j = (k + 1) % 3;
+#pragma unroll
+        for (int hk = 0; hk < 2; ++hk)
+#pragma unroll
+            for (int hj = 0; hj < 2; ++hj)
+                m &= (q[k][hk] < p[j][hj] || q[j][hj] < p[k][hk]) ? ~(side[k][hk] & side[j][hj]) : 0xffu;
+    }
+    return oct_perm_mask(m, sgn);
 }
 
 // ---- SF, part 1: the Shoot in slot s is over -> write its event; a chain reflects and goes on, or ends
@@ -196,9 +261,11 @@ HD uint32_t octw_setup(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COU
     p.D(OD_IX, s) = ix; p.D(OD_IY, s) = iy; p.D(OD_IZ, s) = iz;
     double ca, cb;
     uint4 m;
+    double2 ra, rb, rc;
     {   // root interval with .NET Math.Max / Math.Min (NaN-propagating): the ray may hold anything here
         const double2* q = reinterpret_cast<const double2*>(T.nodes);
         const double2 a = hare_ldg(q), b = hare_ldg(q + 1), cc = hare_ldg(q + 2);
+        ra = a; rb = b; rc = cc;
         m = hare_ldg(reinterpret_cast<const uint4*>(T.nodes) + 3);
         double tx0 = (a.x - R.x) * ix, tx1 = (b.y - R.x) * ix;
         double ty0 = (a.y - R.y) * iy, ty1 = (cc.x - R.y) * iy;
@@ -236,6 +303,7 @@ HD uint32_t octw_setup(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COU
         } else {
             p.U(OU_FCHILD, s) = m.x;
             masks = oct_perm_mask(m.w, sgn);
+            if (T.regular) masks &= oct_child_filter(ra, rb, rc, R.x, R.y, R.z, ix, iy, iz, ca, cb, sgn);
             p.D(OD_FA, s) = ca; p.D(OD_FB, s) = cb;
         }
     }
@@ -276,25 +344,37 @@ HD uint32_t octw_node(const OctDev& T, const OctFrames& F, size_t gslot, const O
         // the candidate's content box and its node record are fetched together (one round trip); the ray's line missing everything
         // listed below the child means entering it could change nothing (only a successful test updates closestT or returns)
         const float4* e = T.nbox + 2 * (size_t)child;
-        const float4 nlo = hare_ldg(e), nhi = hare_ldg(e + 1);
-        double lo, hi; uint4 m;
-        oct_interval_hd(T.nodes + child, ox, oy, oz, ix, iy, iz, lo, hi, m);
-        if (cull_box(nlo, nhi, fpx, fpy, fpz, fix, fiy, fiz)) continue;
-        if (hi < lo || hi < 0 || lo > fb || hi < fa) continue;               // push-time filter :268
+        const double2* nq = reinterpret_cast<const double2*>(T.nodes + child);
+        const float4 nlo = oct_ld_f4(e), nhi = oct_ld_f4(e + 1);
+        const double2 na = oct_ld_d2(nq), nb = oct_ld_d2(nq + 1), nc = oct_ld_d2(nq + 2);
+        const uint4 m = oct_ld_u4(reinterpret_cast<const uint4*>(nq) + 3);      // first_child, list_off, list_cnt, pad
+        // this was the frame's last octant: unless the child opens a level of its own, the next thing needed is the parent's frame --
+        // fetch it in the same round trip
+        const bool last_q = qmask == 0 && sp > 0;
+        double2 pab = make_double2(0.0, 0.0); uint2 pcq = make_uint2(0u, 0u);
+        if (last_q) { pab = fab[sp - 1]; pcq = fcq[sp - 1]; }
+        double lo, hi;
+        oct_interval_of(na, nb, nc, ox, oy, oz, ix, iy, iz, lo, hi);
         const double ca = fmax(lo, fa), cb = fmin(hi, fb);
-        if (cb < ca || cb < 0) continue;                                     // pop-time prunes :207-211
-        if (hit && closest <= ca) continue;
-        c.cell();
-        if ((int)m.x < 0) {
-            if (m.z == 0) continue;                                          // empty leaf
+        const bool enter = !cull_box(nlo, nhi, fpx, fpy, fpz, fix, fiy, fiz) &&
+                           !(hi < lo || hi < 0 || lo > fb || hi < fa) &&         // push-time filter :268
+                           !(cb < ca || cb < 0) && !(hit && closest <= ca) &&    // pop-time prunes :207-211
+                           !((int)m.x < 0 && m.z == 0);                          // (an empty leaf changes nothing)
+        if (enter && (int)m.x >= 0) {
+            // an internal node opens a level; the current top goes to the spill area -- unless it is exhausted: nothing would ever
+            // be read from it again
+            c.cell();
+            if (qmask != 0) { fab[sp] = make_double2(fa, fb); fcq[sp] = make_uint2(fchild, qmask); ++sp; }
+            fchild = m.x; qmask = oct_perm_mask(m.w, sgn); fa = ca; fb = cb;
+            if (T.regular) qmask &= oct_child_filter(na, nb, nc, ox, oy, oz, ix, iy, iz, fa, fb, sgn);
+            continue;
+        }
+        if (last_q) { --sp; fa = pab.x; fb = pab.y; fchild = pcq.x; qmask = pcq.y; }
+        if (enter) {                                                         // a leaf with a list
+            c.cell();
             lpos = m.y; lend = m.y + m.z;
             p.U(OU_CIDX, s) = m.w; p.D(OD_CA, s) = ca;
             break;
-        }
-        if (sp + 1 < F.depth + 1) {                                          // push a level: the current top goes to the spill area
-            fab[sp] = make_double2(fa, fb); fcq[sp] = make_uint2(fchild, qmask);
-            ++sp;
-            fchild = m.x; qmask = oct_perm_mask(m.w, sgn); fa = ca; fb = cb;
         }
     }
     fl = (fl & ~(OFL_SP_MASK | OFL_FIN_MASK)) | ((uint32_t)sp << OFL_SP_SHIFT) | (fin << OFL_FIN_SHIFT);
@@ -317,19 +397,29 @@ HD uint32_t octw_group(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COU
     const float fpx = p.F(OF_PX, s), fpy = p.F(OF_PY, s), fpz = p.F(OF_PZ, s);
     const uint32_t left = lend - lpos, nch = (left + 7u) / 8u < 8u ? (left + 7u) / 8u : 8u;
     uint32_t em = 0;
+    // the group box and the first four chunk boxes are fetched together (one round trip); most groups of a long leaf list are
+    // nowhere near the ray and end here
     const float4* ge = T.gbox + 2 * (size_t)(cidx >> 3);
-    if (!cull_box(hare_ldg(ge), hare_ldg(ge + 1), fpx, fpy, fpz, fix, fiy, fiz)) {
+    const float4 glo = oct_ld_f4(ge), ghi = oct_ld_f4(ge + 1);
+    float4 lo[4], hi[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float4 lo[4], hi[4];
+    for (int j = 0; j < 4; ++j) {
+        const float4* e = T.cbox + 2 * (size_t)(cidx + (j < (int)nch ? j : 0));
+        lo[j] = oct_ld_f4(e); hi[j] = oct_ld_f4(e + 1);
+    }
+    if (!cull_box(glo, ghi, fpx, fpy, fpz, fix, fiy, fiz)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            em |= (j < (int)nch && !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz)) ? (1u << j) : 0u;
+        if (nch > 4u) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4* e = T.cbox + 2 * (size_t)(cidx + (4 * h + j < (int)nch ? 4 * h + j : 0));
-                lo[j] = hare_ldg(e); hi[j] = hare_ldg(e + 1);
+                const float4* e = T.cbox + 2 * (size_t)(cidx + (4 + j < (int)nch ? 4 + j : 0));
+                lo[j] = oct_ld_f4(e); hi[j] = oct_ld_f4(e + 1);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                em |= (4 * h + j < (int)nch && !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz)) ? (1u << (4 * h + j)) : 0u;
+                em |= (4 + j < (int)nch && !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz)) ? (1u << (4 + j)) : 0u;
         }
     }
     const uint32_t adv = left < 64u ? left : 64u;
@@ -357,7 +447,7 @@ HD uint32_t octw_cull(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COUN
     const float fpx = p.F(OF_PX, s), fpy = p.F(OF_PY, s), fpz = p.F(OF_PZ, s);
     const int or1 = (int)p.U(OU_OR1, s), or2 = (int)p.U(OU_OR2, s), pid = (int)p.U(OU_PID, s);
     const uint32_t last = p.U(OU_LAST, s);
-    uint32_t bm = 0;
+    uint32_t bm = 0, first_id = 0;
     // poly_origin skip (:218); a polygon already tested for this ray (it sits in several leaves) cannot change anything:
     // its t is not below closestT any more, so neither the update nor the early return fires
 #pragma unroll
@@ -366,17 +456,19 @@ HD uint32_t octw_cull(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COUN
 #pragma unroll
         for (int j = 0; j < 4; ++j) ids[j] = hare_ldg(T.lists + base + (4 * h + j < (int)n ? 4 * h + j : 0));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float4* e = T.pbox + 2 * (size_t)ids[j]; lo[j] = hare_ldg(e); hi[j] = hare_ldg(e + 1); }
+        for (int j = 0; j < 4; ++j) { const float4* e = T.pbox + 2 * (size_t)ids[j]; lo[j] = oct_ld_f4(e); hi[j] = oct_ld_f4(e + 1); }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t i = ids[j];
             const bool keep = (4 * h + j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
                               !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz);
+            first_id = (keep && bm == 0) ? i : first_id;
             bm |= keep ? (1u << (4 * h + j)) : 0u;
         }
     }
-    masks = (masks & 0xffu) | (emask << 8) | (bm << 16);
-    p.U(OU_MASKS, s) = masks; p.U(OU_CBASE, s) = base;
+    // the lowest survivor's id rides in the slot, so that the test phase fetches its record without re-reading the list
+    masks = (masks & 0xffu) | (emask << 8) | (bm << 16) | ((uint32_t)kc << OM_KC_SHIFT) | (bm ? (uint32_t)OM_PEND : 0u);
+    p.U(OU_MASKS, s) = masks; p.U(OU_PEND, s) = first_id;
     return oct_tag(0, masks, p.U(OU_LPOS, s), lend);
 }
 
@@ -387,8 +479,9 @@ HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const 
     uint32_t bmask = (masks >> 16) & 0xffu;
     const int k = hare_ffs(bmask) - 1;                // lowest survivor first: stored list order
     bmask &= bmask - 1u;
-    masks = (masks & 0xffffu) | (bmask << 16);
-    const uint32_t pend = hare_ldg(T.lists + p.U(OU_CBASE, s) + (uint32_t)k);
+    const uint32_t kc = (masks & OM_KC_MASK) >> OM_KC_SHIFT;
+    const uint32_t pend = (masks & OM_PEND) ? p.U(OU_PEND, s) : hare_ldg(T.lists + p.U(OU_CPOS, s) + kc * 8u + (uint32_t)k);
+    masks = (masks & (0xffffu | OM_KC_MASK)) | (bmask << 16);
     c.test();
     const Ray3 R = { p.D(OD_OX, s), p.D(OD_OY, s), p.D(OD_OZ, s), p.D(OD_DX, s), p.D(OD_DY, s), p.D(OD_DZ, s) };
     double P[16], t = 0, u = 0, v = 0;

@@ -25,6 +25,7 @@ inline void poly_pad_box(const double* verts12, int vcount, float out[6]) {
 }
 
 struct PackedOct {
+    bool regular = true;          // every child box equals BuildOctree's function of its parent's box ("Octree - alt.cs":99-114), bit for bit
     std::vector<OctNode> nodes;   // box, first_child, list range; pad = content mask of the 8 children (internal) / first chunk index (leaf)
     std::vector<float> cbox;      // per run of HARE_OCT_CHUNK leaf-list entries: union of the members' padded boxes (lo.xyz, 0, hi.xyz, 0)
     std::vector<float> gbox;      // per group of 8 runs (a leaf's first run is a multiple of 8)
@@ -39,6 +40,19 @@ inline void pack_octree(const OctTree& t, const float* pbox6, PackedOct& out) {
         OctNode& n = out.nodes[i];
         n.mnx = t.box[6 * i]; n.mny = t.box[6 * i + 1]; n.mnz = t.box[6 * i + 2]; n.mxx = t.box[6 * i + 3]; n.mxy = t.box[6 * i + 4]; n.mxz = t.box[6 * i + 5];
         n.first_child = t.first_child[i]; n.list_off = t.list_off[i]; n.list_cnt = t.list_cnt[i]; n.pad = 0;
+    }
+    out.regular = true;
+    for (size_t i = 0; i < N && out.regular; ++i) {
+        if (t.first_child[i] < 0) continue;
+        for (int c = 0; c < 8 && out.regular; ++c) {
+            const double* cb = &t.box[6 * ((size_t)t.first_child[i] + c)];
+            for (int a = 0; a < 3; ++a) {
+                const double mn = t.box[6 * i + a], mx = t.box[6 * i + 3 + a], mid = (mx + mn) / 2;
+                const bool upper = (c & (4 >> a)) != 0;
+                const double cmn = (upper ? mid : mn) - 0.1, cmx = (upper ? mx : mid) + 0.1;
+                if (std::memcmp(&cmn, &cb[a], 8) != 0 || std::memcmp(&cmx, &cb[3 + a], 8) != 0) out.regular = false;
+            }
+        }
     }
     // internal node: pad = bit c set when the subtree of child c holds at least one polygon: the kernel never enters the others
     // (entering a polygon-free subtree has no effect on the result)
@@ -95,6 +109,55 @@ inline void pack_octree(const OctTree& t, const float* pbox6, PackedOct& out) {
         const float rec[8] = { lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f };
         std::memcpy(&out.nbox[8 * i], rec, sizeof rec);
     }
+}
+
+// Device node records of a kd-tree.  The node box is the reference's (KDTree.cs:68-83, 107-121) INTERSECTED with the bounding box of
+// the polygons listed below the node: the walk only uses a node box to decide that no polygon of the subtree can be hit at
+// t <= closest inside it (kd_box_reachable); a hit inside the node box lies on a listed polygon, hence inside that polygon's
+// bounding box too, so the intersection prunes as validly and far tighter -- the median splits leave most leaves holding a sliver
+// of wall in a box of air.  The reference's own boxes stay in KdTree::box (downloads, and the tie rule's side table).
+inline void pack_kdtree(const KdTree& t, const HostTopo& M, std::vector<KdNode>& nodes) {
+    const size_t N = t.axis.size();
+    std::vector<double> tight(t.box), content(6 * N);
+    std::vector<std::pair<int, int>> st; st.push_back({ 0, 0 });   // (node, 0 = enter / 1 = leave)
+    while (!st.empty()) {
+        auto [n, leave] = st.back(); st.pop_back();
+        double* cb = &content[6 * (size_t)n];
+        if (t.left[n] < 0) {
+            for (int a = 0; a < 3; ++a) { cb[a] = INFINITY; cb[3 + a] = -INFINITY; }
+            for (uint32_t k = 0; k < t.list_cnt[n]; ++k) {
+                const int64_t q = t.polys[t.list_off[n] + k];
+                for (int v = 0; v < M.vcount[q]; ++v)
+                    for (int a = 0; a < 3; ++a) { const double c = M.verts[12 * q + 3 * v + a]; cb[a] = std::min(cb[a], c); cb[3 + a] = std::max(cb[3 + a], c); }
+            }
+        } else if (!leave) {
+            st.push_back({ n, 1 }); st.push_back({ t.left[n], 0 }); st.push_back({ t.left[n] + 1, 0 });
+            continue;
+        } else {
+            const double *l = &content[6 * (size_t)t.left[n]], *r = l + 6;
+            for (int a = 0; a < 3; ++a) { cb[a] = std::min(l[a], r[a]); cb[3 + a] = std::max(l[3 + a], r[3 + a]); }
+        }
+        for (int a = 0; a < 3; ++a) { tight[6 * (size_t)n + a] = std::max(tight[6 * (size_t)n + a], cb[a]); tight[6 * (size_t)n + 3 + a] = std::min(tight[6 * (size_t)n + 3 + a], cb[3 + a]); }
+    }
+    nodes.resize(N);
+    for (size_t i = 0; i < N; ++i) {
+        KdNode& n = nodes[i];
+        n.mnx = tight[6 * i]; n.mny = tight[6 * i + 1]; n.mnz = tight[6 * i + 2]; n.mxx = tight[6 * i + 3]; n.mxy = tight[6 * i + 4]; n.mxz = tight[6 * i + 5];
+        n.left = t.left[i]; n.axis = t.left[i] >= 0 ? t.axis[i] : 0;
+        if (t.left[i] >= 0) n.split = t.split[i];
+        else { uint64_t bits = (uint64_t)t.list_off[i] | ((uint64_t)t.list_cnt[i] << 32); std::memcpy(&n.split, &bits, 8); }
+    }
+}
+
+inline int kd_depth_of(const KdTree& t) {
+    const size_t N = t.axis.size();
+    std::vector<int> dep(N, 0);
+    int best = 0;
+    for (size_t i = 0; i < N; ++i) {
+        best = std::max(best, dep[i]);
+        if (t.left[i] >= 0) { dep[(size_t)t.left[i]] = dep[i] + 1; dep[(size_t)t.left[i] + 1] = dep[i] + 1; }
+    }
+    return best;
 }
 
 // deepest level of an octree / kd-tree whose children have larger indices than their parents (root = 0)

@@ -1,8 +1,8 @@
 // vg_wave.cuh -- K1/K5 for Voxel_Grid, second generation: a per-warp WAVEFRONT scheduler.
 //
-// vg_walk.cuh ties one ray to one thread; every trip round its loop the warp runs the S, W, C, F and T
-// phases one after the other, each with the subset of lanes whose ray happens to be in that phase: ncu
-// shows ~10 of 32 lanes active per issued instruction (profiles/r1_ncu_bench_summary.txt).
+// The first generation tied one ray to one thread; every trip round its loop the warp ran the S, W, C, F and T
+// phases one after the other, each with the subset of lanes whose ray happened to be in that phase: ncu
+// showed ~10 of 32 lanes active per issued instruction (profiles/r1_ncu_v7_summary.txt).
 //
 // Here the ray state lives in SHARED MEMORY instead of registers.  Every warp owns a private pool of SLOTS
 // (> 32) ray slots, stored structure-of-arrays so that any lane can work on any slot.  Each slot carries a
@@ -13,18 +13,16 @@
 //   4. runs that ONE phase converged on (up to) 32 different rays, and writes the state and new tags back.
 // No inter-warp communication exists (only __syncwarp), so there is nothing to deadlock on.
 //
-// Phases (the arithmetic of each is the same, operation for operation, as in vg_walk.cuh / shoot_one, i.e.
-// Voxel_Grid.Shoot, Voxel_Grid.cs:351-552):
+// Phases (the arithmetic of each is Voxel_Grid.Shoot's, operation for operation; Voxel_Grid.cs:351-552):
 //   SF  finish a Shoot (write the event, reflect), fetch a new ray if the slot is empty, DDA set-up
 //   W   up to W_MAX voxel steps on the border-padded occupancy bitmap in shared memory (no coordinates, no bounds checks)
-//   C   next <= 4 list entries: ids + bounding spheres, FP32 conservative sphere cull
+//   C   next <= 4 list entries: (padded box, id) records in list order, FP32 conservative box cull
 //   T   one exact FP64 polygon test (128-byte record, Ray_Side, Moller-Trumbore)
 //
 // Every per-slot function below is `HD`: tests/emu/ compiles the same functions for the host and replays
 // the scheduler on the CPU against the oracle (logic check without a GPU, and lane-utilisation statistics).
 #pragma once
 #include "shoot.cuh"
-#include "vg_walk.cuh"
 
 namespace hare {
 
@@ -42,16 +40,7 @@ enum : uint32_t { FIN_RUN = 0, FIN_HIT = 1, FIN_MISS = 2, FIN_FAULT = 3 };
 
 // field indices of the structure-of-arrays pool
 enum { D_OX, D_OY, D_OZ, D_DX, D_DY, D_DZ, D_TMX, D_TMY, D_TMZ, D_TDX, D_TDY, D_TDZ, D_TMIN, D_TSTART, D_COUNT };
-// HARE_WAVE_BIDS = 1 keeps the ids of a culled batch's survivors in the slot (16 bytes); 0 re-reads them from the
-// cell list in T (the list position stays on the batch until its survivors are consumed)
-#ifndef HARE_WAVE_BIDS
-#define HARE_WAVE_BIDS 0
-#endif
-#if HARE_WAVE_BIDS
-enum { U_XYZ /* padded voxel index cp */, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_BID0, U_BID1, U_BID2, U_BID3, U_COUNT };
-#else
 enum { U_XYZ /* padded voxel index cp */, U_FLAGS, U_LPOS, U_LEND, U_PID, U_OR1, U_OR2, U_LAST, U_RAY, U_COUNT };
-#endif
 
 template <int SLOTS>
 struct WavePool {
@@ -234,6 +223,13 @@ HD uint32_t wave_setup(const VGrid& g, const uint32_t* occ, bool occ_smem, const
     return wave_tag(fl, lpos, lend);
 }
 
+// Which axis the 3D-DDA steps along (Voxel_Grid.cs:504-550, quirk Q4): X only if tMaxX is STRICTLY below both others, Y only if
+// tMaxY < tMaxZ (given that X lost), otherwise Z -- so an exact tie goes to the later axis.  Branch-free for a converged warp.
+HD int dda_axis(double tMaxX, double tMaxY, double tMaxZ) {
+    const bool xy = tMaxX < tMaxY, xz = tMaxX < tMaxZ, yz = tMaxY < tMaxZ;
+    return (xy & xz) ? 0 : (((!xy) & yz) ? 1 : 2);
+}
+
 // ---- W: the slot's list is exhausted -> accept the carried candidate or step the 3D-DDA (<= W_MAX voxels)
 template <bool COUNT, int SLOTS, int W_MAX>
 HD uint32_t wave_walk(const VGrid& g, const WaveGeom& w, const uint32_t* occ, bool occ_smem, const WavePool<SLOTS>& p, int s, CntT<COUNT>& c) {
@@ -260,9 +256,8 @@ HD uint32_t wave_walk(const VGrid& g, const WaveGeom& w, const uint32_t* occ, bo
         }
         // next voxel   Voxel_Grid.cs:504-550: X only if strictly below both, Y only if below Z, else Z
         {
-            const bool xy = tMaxX < tMaxY, xz = tMaxX < tMaxZ, yz = tMaxY < tMaxZ;
-            const bool goX = xy & xz, goY = (!xy) & yz;
-            const bool goZ = !(goX | goY);
+            const int ax = dda_axis(tMaxX, tMaxY, tMaxZ);
+            const bool goX = ax == 0, goY = ax == 1, goZ = ax == 2;
             const double nX = tMaxX + tDeltaX, nY = tMaxY + tDeltaY, nZ = tMaxZ + tDeltaZ;
             tMaxX = goX ? nX : tMaxX; tMaxY = goY ? nY : tMaxY; tMaxZ = goZ ? nZ : tMaxZ;
             cp += (uint32_t)(goX ? sX : (goY ? sY : sZ));
@@ -306,8 +301,8 @@ HD uint32_t wave_cull(const VGrid& g, const WavePool<SLOTS>& p, int s, CntT<COUN
     const uint32_t lend = p.U(U_LEND, s);
     const uint32_t n = (lend - lpos) < 4u ? (lend - lpos) : 4u;
     if (COUNT) c.entries += n;
-    // the culls work in FP32 in a frame local to the voxel: their ray point is where the ray LEAVES the current voxel,
-    // min(tMax) -- like the entry point vg_walk.cuh uses, at most a voxel diagonal from anything listed here
+    // the cull works in FP32 in a frame local to the voxel: its ray point is where the ray LEAVES the current voxel,
+    // min(tMax), at most a voxel diagonal from anything listed here
     const double dx = p.D(D_DX, s), dy = p.D(D_DY, s), dz = p.D(D_DZ, s);
     const double te = fmin(fmin(p.D(D_TMX, s), p.D(D_TMY, s)), p.D(D_TMZ, s));
     const float fpx = (float)fma(dx, te, p.D(D_OX, s)), fpy = (float)fma(dy, te, p.D(D_OY, s)), fpz = (float)fma(dz, te, p.D(D_OZ, s));
@@ -316,46 +311,22 @@ HD uint32_t wave_cull(const VGrid& g, const WavePool<SLOTS>& p, int s, CntT<COUN
     const uint32_t last = p.U(U_LAST, s);
     // poly_origin skip (Voxel_Grid.cs:477); a polygon already tested for this ray cannot change the result
     auto fresh = [&](uint32_t i) { return !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid); };
-    uint32_t bid0, bid1, bid2, bid3, bmask;
-    if (g.lbox) {
-        // list entries carry their polygon's padded bounding box and its id: one contiguous 32 bytes per entry
-        const float4* e = g.lbox + 2 * (size_t)lpos;
-        const float4 l0 = hare_ldg(e), h0 = hare_ldg(e + 1);
-        const float4 l1 = (n > 1) ? hare_ldg(e + 2) : l0, h1 = (n > 1) ? hare_ldg(e + 3) : h0;
-        const float4 l2 = (n > 2) ? hare_ldg(e + 4) : l0, h2 = (n > 2) ? hare_ldg(e + 5) : h0;
-        const float4 l3 = (n > 3) ? hare_ldg(e + 6) : l0, h3 = (n > 3) ? hare_ldg(e + 7) : h0;
-        bid0 = hare_f2u(l0.w); bid1 = hare_f2u(l1.w); bid2 = hare_f2u(l2.w); bid3 = hare_f2u(l3.w);
-        const float ix = cull_rcp(fdx), iy = cull_rcp(fdy), iz = cull_rcp(fdz);
-        const float pxi = fpx * ix, pyi = fpy * iy, pzi = fpz * iz;
-        bmask = ((fresh(bid0) && !cull_box(l0, h0, pxi, pyi, pzi, ix, iy, iz)) ? 1u : 0u) |
-                ((n > 1 && fresh(bid1) && !cull_box(l1, h1, pxi, pyi, pzi, ix, iy, iz)) ? 2u : 0u) |
-                ((n > 2 && fresh(bid2) && !cull_box(l2, h2, pxi, pyi, pzi, ix, iy, iz)) ? 4u : 0u) |
-                ((n > 3 && fresh(bid3) && !cull_box(l3, h3, pxi, pyi, pzi, ix, iy, iz)) ? 8u : 0u);
-    } else {
-        bid0 = hare_ldg(g.cell_poly + lpos);
-        bid1 = (n > 1) ? hare_ldg(g.cell_poly + lpos + 1) : bid0;
-        bid2 = (n > 2) ? hare_ldg(g.cell_poly + lpos + 2) : bid0;
-        bid3 = (n > 3) ? hare_ldg(g.cell_poly + lpos + 3) : bid0;
-        const float4 s0 = hare_ldg(g.sph + bid0), s1 = hare_ldg(g.sph + bid1), s2 = hare_ldg(g.sph + bid2), s3 = hare_ldg(g.sph + bid3);
-        const float fdd = fmaf(fdx, fdx, fmaf(fdy, fdy, fdz * fdz));
-        bmask = ((fresh(bid0) && !cull_sphere(s0, fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? 1u : 0u) |
-                ((n > 1 && fresh(bid1) && !cull_sphere(s1, fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? 2u : 0u) |
-                ((n > 2 && fresh(bid2) && !cull_sphere(s2, fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? 4u : 0u) |
-                ((n > 3 && fresh(bid3) && !cull_sphere(s3, fpx, fpy, fpz, fdx, fdy, fdz, fdd)) ? 8u : 0u);
-    }
-#if HARE_WAVE_BIDS
-    lpos += n;
-    p.U(U_LPOS, s) = lpos;
-    if (bmask) {
-        p.U(U_BID0, s) = bid0; p.U(U_BID1, s) = bid1; p.U(U_BID2, s) = bid2; p.U(U_BID3, s) = bid3;
-        p.U(U_FLAGS, s) |= bmask << WF_BMASK_SHIFT;
-        return PH_T;
-    }
-#else
+    // list entries carry their polygon's padded bounding box and its id: one contiguous 32 bytes per entry, no id -> box dependent load
+    const float4* e = g.lbox + 2 * (size_t)lpos;
+    const float4 l0 = hare_ldg(e), h0 = hare_ldg(e + 1);
+    const float4 l1 = (n > 1) ? hare_ldg(e + 2) : l0, h1 = (n > 1) ? hare_ldg(e + 3) : h0;
+    const float4 l2 = (n > 2) ? hare_ldg(e + 4) : l0, h2 = (n > 2) ? hare_ldg(e + 5) : h0;
+    const float4 l3 = (n > 3) ? hare_ldg(e + 6) : l0, h3 = (n > 3) ? hare_ldg(e + 7) : h0;
+    const uint32_t bid0 = hare_f2u(l0.w), bid1 = hare_f2u(l1.w), bid2 = hare_f2u(l2.w), bid3 = hare_f2u(l3.w);
+    const float ix = cull_rcp(fdx), iy = cull_rcp(fdy), iz = cull_rcp(fdz);
+    const float pxi = fpx * ix, pyi = fpy * iy, pzi = fpz * iz;
+    const uint32_t bmask = ((fresh(bid0) && !cull_box(l0, h0, pxi, pyi, pzi, ix, iy, iz)) ? 1u : 0u) |
+                           ((n > 1 && fresh(bid1) && !cull_box(l1, h1, pxi, pyi, pzi, ix, iy, iz)) ? 2u : 0u) |
+                           ((n > 2 && fresh(bid2) && !cull_box(l2, h2, pxi, pyi, pzi, ix, iy, iz)) ? 4u : 0u) |
+                           ((n > 3 && fresh(bid3) && !cull_box(l3, h3, pxi, pyi, pzi, ix, iy, iz)) ? 8u : 0u);
     if (bmask) { p.U(U_FLAGS, s) |= bmask << WF_BMASK_SHIFT; return PH_T; }   // lpos stays on the batch until T has consumed it
     lpos += n;
     p.U(U_LPOS, s) = lpos;
-#endif
     return lpos < lend ? PH_C : PH_W;
 }
 
@@ -367,14 +338,9 @@ HD uint32_t wave_test(const VGrid& g, const PolyRec* __restrict__ polys, const W
     const int k = (bmask & 1u) ? 0 : ((bmask & 2u) ? 1 : ((bmask & 4u) ? 2 : 3));   // lowest survivor first
     uint32_t lpos = p.U(U_LPOS, s);
     const uint32_t lend = p.U(U_LEND, s);
-#if HARE_WAVE_BIDS
-    const uint32_t pend = p.U(U_BID0 + k, s);
-    fl &= ~((1u << k) << WF_BMASK_SHIFT);
-#else
     const uint32_t pend = hare_ldg(g.cell_poly + lpos + k);
     fl &= ~((1u << k) << WF_BMASK_SHIFT);
     if (!(fl & WF_BMASK_MASK)) { lpos += (lend - lpos) < 4u ? (lend - lpos) : 4u; p.U(U_LPOS, s) = lpos; }
-#endif
     c.test();
     const Ray3 R = { p.D(D_OX, s), p.D(D_OY, s), p.D(D_OZ, s), p.D(D_DX, s), p.D(D_DY, s), p.D(D_DZ, s) };
     double P[16], t = 0;

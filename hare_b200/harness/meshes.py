@@ -189,3 +189,10 @@ def sources(n):
     base = np.array([[15.0, 6.0, 5.0], [11.0, 14.0, 8.0], [19.0, 22.0, 10.5], [15.0, 30.0, 11.5],
                      [13.0, 9.0, 6.5], [17.0, 17.0, 9.5], [9.5, 26.0, 11.0], [20.5, 11.0, 7.5]])
     return base[:n].copy()
+
+
+def lattice_room(n=32, size=16.0, height=8.0):
+    """Closed box room whose floor, ceiling and walls are n x n lattices of mixed triangles / quads with DYADIC coordinates
+    (size / n a power of two): rays with small-integer origins and directions hit shared edges and vertices at bit-identical t
+    for every adjacent polygon -- the exact-t ties of the KDTree / Octree tie rules."""
+    return _finish(_box_polys((0.0, 0.0, 0.0), (size, size, height), (n, n, max(1, n // 2))), "lattice-room")

@@ -1,4 +1,4 @@
-"""ctypes driver of tests/emu/liboct_emu.so: the CPU replay of oct_wave.cuh's wavefront scheduler (test infrastructure)."""
+"""ctypes driver of tests/emu/libkd_emu.so: the CPU replay of kd_wave.cuh's wavefront scheduler (test infrastructure)."""
 import ctypes as C
 import os
 import subprocess
@@ -6,15 +6,15 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "liboct_emu.so")
+_SO = os.path.join(_HERE, "libkd_emu.so")
 _lib = None
-PHASES = "SF N G C T".split()
+PHASES = "SF N C T".split()
 
 
 def lib():
     global _lib
     if _lib is None:
-        subprocess.check_call(["make", "-C", _HERE, "-s", "liboct_emu.so"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libkd_emu.so"])
         _lib = C.CDLL(_SO)
     return _lib
 
@@ -23,12 +23,15 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, chain=False, order=1, slots=64, nmax=4, n_warps=4, regular=True):
-    """topo_arrays = oracle Topology.arrays(); tree_arrays = oracle Octree.arrays() = (box, first_child, list_off, list_cnt, polys)."""
+def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, ray_id=None, chain=False, order=1, slots=64, nmax=4, n_warps=4, tie_rule_on_tight_boxes=False):
+    """topo_arrays = oracle Topology.arrays(); tree_arrays = oracle KDTree.arrays() = (box, split, axis, left, right, list_off, list_cnt, polys)."""
     verts, normals, vcount, _ = topo_arrays
-    box, fc, lo, lc, pol = tree_arrays
+    box, sp, ax, le, ri, lo, lc, pol = tree_arrays
+    internal = le >= 0
+    assert np.array_equal(ri[internal], le[internal] + 1), "the flattened kd-tree keeps Right = Left + 1"
     verts = np.ascontiguousarray(verts, np.float64); normals = np.ascontiguousarray(normals, np.float64); vcount = np.ascontiguousarray(vcount, np.int32)
-    box = np.ascontiguousarray(box, np.float64); fc = np.ascontiguousarray(fc, np.int32)
+    box = np.ascontiguousarray(box, np.float64); sp = np.ascontiguousarray(sp, np.float64)
+    ax = np.ascontiguousarray(ax, np.int32); le = np.ascontiguousarray(le, np.int32)
     lo = np.ascontiguousarray(lo, np.uint32); lc = np.ascontiguousarray(lc, np.uint32)
     npol = len(pol)
     pol = np.ascontiguousarray(pol if npol else np.zeros(1), np.uint32)
@@ -36,6 +39,7 @@ def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, chain=False,
     N = o.shape[0]
     o1 = None if origin1 is None else np.ascontiguousarray(origin1, np.int32)
     o2 = None if origin2 is None else np.ascontiguousarray(origin2, np.int32)
+    rid = None if ray_id is None else np.ascontiguousarray(ray_id, np.int32)
     stats = np.zeros(16); counters = np.zeros(4, np.uint64)
     if chain:
         ev_pid = np.zeros((N, order), np.int32); ev_t = np.zeros((N, order)); fo = np.zeros((N, 3)); fd = np.zeros((N, 3))
@@ -46,11 +50,11 @@ def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, chain=False,
         t = np.zeros(N); xyz = np.zeros((N, 3)); pid = np.zeros(N, np.int32); uv = np.ones((N, 2)); om = np.zeros((N, 3))
         args = [_p(t), _p(xyz), _p(pid), _p(uv), _p(om)] + [None] * 6
         res = dict(t=t, xyz=xyz, poly_id=pid, uv=uv, o=om)
-    rc = lib().oct_emu(_p(verts), _p(normals), _p(vcount), C.c_int64(len(vcount)), _p(box), _p(fc), _p(lo), _p(lc), _p(pol),
-                       C.c_int64(len(fc)), C.c_int64(npol), _p(o), _p(d), _p(o1), _p(o2), C.c_int64(N), int(chain), int(order),
-                       *args, int(slots), int(nmax), int(n_warps), int(regular), _p(stats), _p(counters))
+    rc = lib().kd_emu(_p(verts), _p(normals), _p(vcount), C.c_int64(len(vcount)), _p(box), _p(sp), _p(ax), _p(le), _p(lo), _p(lc), _p(pol),
+                      C.c_int64(len(le)), C.c_int64(npol), _p(o), _p(d), _p(o1), _p(o2), _p(rid), C.c_int64(N), int(chain), int(order),
+                      *args, int(slots), int(nmax), int(n_warps), int(tie_rule_on_tight_boxes), _p(stats), _p(counters))
     if rc != 0:
-        raise ValueError("oct_emu: unsupported (slots, nmax)")
-    res["stats"] = dict(exec=dict(zip(PHASES, stats[0:5])), lanes=dict(zip(PHASES, stats[5:10])), trips=stats[10])
+        raise ValueError("kd_emu: unsupported (slots, nmax)")
+    res["stats"] = dict(exec=dict(zip(PHASES, stats[0:4])), lanes=dict(zip(PHASES, stats[4:8])), trips=stats[8])
     res["counters"] = counters
     return res

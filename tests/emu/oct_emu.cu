@@ -81,7 +81,7 @@ extern "C" int oct_emu(const double* verts, const double* normals, const int32_t
                        const double* o, const double* d, const int32_t* o1, const int32_t* o2, int64_t N, int chain, int order,
                        double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
                        int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
-                       int slots, int nmax, int n_warps, double* stats, unsigned long long* counters) {
+                       int slots, int nmax, int n_warps, int regular_ok, double* stats, unsigned long long* counters) {
     std::vector<PolyRec> recs((size_t)P);
     std::vector<float> pbox6((size_t)P * 6);
     for (int64_t i = 0; i < P; ++i) {
@@ -108,7 +108,7 @@ extern "C" int oct_emu(const double* verts, const double* normals, const int32_t
     T.nodes = pk.nodes.data(); T.lists = tr.polys.data();
     T.cbox = reinterpret_cast<const float4*>(pk.cbox.data()); T.gbox = reinterpret_cast<const float4*>(pk.gbox.data());
     T.pbox = pbox.data(); T.nbox = reinterpret_cast<const float4*>(pk.nbox.data());
-    T.depth = depth;
+    T.depth = depth; T.regular = (pk.regular && regular_ok) ? 1 : 0;
     WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
     Stats st;
 #define RUN(S, M) if (slots == S && nmax == M) { if (chain) run<true, S, M>(T, depth, recs.data(), o, d, o1, o2, N, order, out, n_warps, st, counters); \

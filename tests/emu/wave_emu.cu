@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../hare_b200/csrc/kernels.cuh"
 #include "../../hare_b200/csrc/vg_wave.cuh"
+#include "../../hare_b200/csrc/pack.hpp"
 
 using namespace hare;
 
@@ -103,30 +104,13 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
                         int chain, int order,
                         double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
                         int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
-                        int slots, int wmax, int n_warps, int list_boxes, int wexit, double* stats, unsigned long long* counters) {
+                        int slots, int wmax, int n_warps, int wexit, double* stats, unsigned long long* counters) {
     std::vector<PolyRec> recs((size_t)P);
-    std::vector<float4> sph((size_t)P);
     for (int64_t i = 0; i < P; ++i) {
         for (int k = 0; k < 12; ++k) recs[i].v[k] = verts[12 * i + k];
         if (vcount[i] == 3) for (int a = 0; a < 3; ++a) recs[i].v[9 + a] = verts[12 * i + 6 + a];
         for (int a = 0; a < 3; ++a) recs[i].v[12 + a] = normals[3 * i + a];
         recs[i].v[15] = (double)vcount[i];
-        // padded FP32 bounding sphere, as hare_topology_create makes it
-        double lo[3], hi[3];
-        for (int a = 0; a < 3; ++a) lo[a] = hi[a] = verts[12 * i + a];
-        for (int k = 1; k < vcount[i]; ++k)
-            for (int a = 0; a < 3; ++a) { lo[a] = std::fmin(lo[a], verts[12 * i + 3 * k + a]); hi[a] = std::fmax(hi[a], verts[12 * i + 3 * k + a]); }
-        float cf[3]; double r2 = 0;
-        for (int a = 0; a < 3; ++a) cf[a] = (float)(0.5 * (lo[a] + hi[a]));
-        for (int k = 0; k < vcount[i]; ++k) {
-            double q = 0;
-            for (int a = 0; a < 3; ++a) { double dl = verts[12 * i + 3 * k + a] - (double)cf[a]; q += dl * dl; }
-            r2 = std::fmax(r2, q);
-        }
-        const double r = std::sqrt(r2) * (1.0 + 1e-5) + 1e-3;
-        float rf = (float)r;
-        while ((double)rf < r) rf = std::nextafter(rf, INFINITY);
-        sph[i] = make_float4(cf[0], cf[1], cf[2], rf);
     }
     const int64_t ncells = (int64_t)ct[0] * ct[1] * ct[2];
     std::vector<uint2> cells((size_t)ncells);
@@ -148,7 +132,7 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
         if (!bit) { const int64_t ci = ((xp - 1) * ct[1] + (yp - 1)) * ct[2] + (zp - 1); bit = cells[ci].y != 0; }
         if (bit) occp[cp >> 5] |= 1u << (cp & 31);
     }
-    g.cells = cells.data(); g.cell_poly = cell_poly; g.occ = occ.data(); g.occp = occp.data(); g.sph = sph.data();
+    g.cells = cells.data(); g.cell_poly = cell_poly; g.occ = occ.data(); g.occp = occp.data();
     // per-entry padded boxes with the id in lo.w, as vg_gather_list_box makes them
     std::vector<float4> lbox(2 * (size_t)cell_offset[ncells] + 2);
     for (uint32_t k = 0; k < cell_offset[ncells]; ++k) {
@@ -163,7 +147,7 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
         }
         lbox[2 * k] = make_float4(lo[0], lo[1], lo[2], hare_u2f((uint32_t)i)); lbox[2 * k + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
     }
-    g.lbox = list_boxes ? lbox.data() : nullptr;
+    g.lbox = lbox.data();
     WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
     Stats st;
 #define RUN(S, W) if (slots == S && wmax == W) { if (chain) run<true, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, wexit, st, counters); \
@@ -200,3 +184,6 @@ extern "C" void emu_cull_box(const double* verts, const int32_t* vcount, const d
         out[i] = cull_box(make_float4(lo[0], lo[1], lo[2], 0.f), make_float4(hi[0], hi[1], hi[2], 0.f), px * ix, py * iy, pz * iz, ix, iy, iz) ? 1 : 0;
     }
 }
+
+// ---- the DDA step selection exactly as the kernel uses it (quirk Q4 unit test) ----------
+extern "C" int emu_dda_axis(double tx, double ty, double tz) { return dda_axis(tx, ty, tz); }

@@ -22,7 +22,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run(topo_arrays, grid_info, csr, o, d, origin1=None, origin2=None, ray_id=None, chain=False, order=1, slots=64, wmax=4, n_warps=4, list_boxes=True, wexit=0):
+def run(topo_arrays, grid_info, csr, o, d, origin1=None, origin2=None, ray_id=None, chain=False, order=1, slots=64, wmax=4, n_warps=4, wexit=0):
     """topo_arrays = oracle Topology.arrays(); grid_info = oracle Voxel_Grid.info(); csr = Voxel_Grid.csr()."""
     verts, normals, vcount, _ = topo_arrays
     obox, _, ct, _ = grid_info
@@ -48,7 +48,7 @@ def run(topo_arrays, grid_info, csr, o, d, origin1=None, origin2=None, ray_id=No
         res = dict(t=t, xyz=xyz, poly_id=pid, uv=uv, o=om)
     rc = lib().wave_emu(_p(verts), _p(normals), _p(vcount), C.c_int64(len(vcount)), _p(np.ascontiguousarray(obox, np.float64)),
                         _p(np.ascontiguousarray(ct, np.int32)), _p(off), _p(pol), _p(o), _p(d), _p(o1), _p(o2), _p(rid), C.c_int64(N),
-                        int(chain), int(order), *args, int(slots), int(wmax), int(n_warps), int(list_boxes), int(wexit), _p(stats), _p(counters))
+                        int(chain), int(order), *args, int(slots), int(wmax), int(n_warps), int(wexit), _p(stats), _p(counters))
     if rc != 0:
         raise ValueError("wave_emu: unsupported (slots, wmax)")
     res["stats"] = dict(exec=dict(zip("SF W C T".split(), stats[0:4])), lanes=dict(zip("SF W C T".split(), stats[4:8])),
