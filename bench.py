@@ -591,7 +591,7 @@ def run_build_config(x, args, cfg, steps, warmup, do_cpu=True):
         walls.append(time.perf_counter() - t0)
     launches = hb.launch_count() - l0
     wall = float(np.median(walls))
-    kms = g.build_kernel_ms() if hasattr(g, "build_kernel_ms") else None
+    kms = g.build_ms()[0] or None
     _, _, ct, K = g.info()
     ncells = int(ct[0]) * int(ct[1]) * int(ct[2])
     B = 2 * mesh.P * 128 + 12 * ncells + 4 * K

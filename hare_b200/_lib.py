@@ -77,6 +77,7 @@ def lib():
     L.hare_part_save.argtypes = [vp, C.c_char_p]
     L.hare_part_load.argtypes = [vp, C.c_char_p, pp]
     L.hare_part_kind.argtypes = [vp]
+    L.hare_part_build_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.hare_part_device_bytes.restype = i64
     L.hare_part_device_bytes.argtypes = [vp]
     L.hare_part_destroy.argtypes = [vp]

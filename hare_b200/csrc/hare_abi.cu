@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -76,11 +77,35 @@ static DevInfo dev_info(int dev) {
 template <class T>
 static cudaError_t dmalloc(T** p, size_t n) { *p = nullptr; return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
+// Build-path memory comes from the device's stream-ordered pool (cudaMallocAsync): a rebuild reuses the blocks the previous one
+// returned instead of paying ~10 cudaMalloc / cudaFree round trips (which dominated and randomised the build's wall time).  The pool
+// keeps up to 8 GB of freed blocks.  Persistent arrays allocated this way are released with plain cudaFree in free_partdev.
+static void pool_keep(int dev) {
+    static std::mutex mu; static std::vector<int> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if (std::find(done.begin(), done.end(), dev) != done.end()) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { uint64_t keep = 8ull << 30; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+    done.push_back(dev);
+}
+template <class T>
+static cudaError_t pmalloc(T** p, size_t n, cudaStream_t st) { *p = nullptr; return cudaMallocAsync((void**)p, std::max<size_t>(n, 1) * sizeof(T), st); }
+// temporaries of one build step: returned to the pool (stream-ordered) when the guard leaves scope, on every path
+struct StreamTemps {
+    cudaStream_t st; std::vector<void*> v;
+    explicit StreamTemps(cudaStream_t s) : st(s) {}
+    template <class T> cudaError_t get(T** p, size_t n) { cudaError_t e = pmalloc(p, n, st); if (e == cudaSuccess) v.push_back(*p); return e; }
+    void keep(void* p) { v.erase(std::remove(v.begin(), v.end(), p), v.end()); }   // ownership moves to the caller
+    void drop(void* p) { if (!p) return; keep(p); cudaFreeAsync(p, st); }
+    ~StreamTemps() { for (void* p : v) cudaFreeAsync(p, st); }
+};
+
 // ---------------------------------------------------------------------------------------
 // handles
 // ---------------------------------------------------------------------------------------
 struct hare_topo_s {
     HostTopo host;
+    std::atomic<int> parts{ 0 };       // partitions built on this Topology that are still alive (they read its device records)
     std::vector<int> devs;
     std::vector<PolyRec*> d_polys;   // one replica per device
     std::vector<float> pbox;         // host copy of the padded FP32 bounding boxes (P x 6: lo xyz, hi xyz), see cull_box()
@@ -114,6 +139,7 @@ struct hare_part_s {
     std::mutex mu;
     // voxel grid
     double obox[6] = {}, vd[3] = {}; int ct[3] = {}; int64_t npairs = 0;
+    double build_kernel_ms = 0, build_wall_ms = 0;   // device time of the build kernels (CUDA events) / host wall time of the constructor
     // trees (host copies, for *_download and *_info)
     OctTree oct; KdTree kd; bool oct_regular = false;
 };
@@ -132,6 +158,7 @@ static void free_partdev(PartDev& d) {
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
     d.dev = dev; d.polys = polys; d.sms = dev_info(dev).sms;
     CK(cudaSetDevice(dev));
+    pool_keep(dev);
     for (int s = 0; s < 2; ++s) CK(cudaStreamCreateWithFlags(&d.stream[s], cudaStreamNonBlocking));
     CK(dmalloc(&d.counters, 8));
     CK(cudaMemset(d.counters, 0, 8 * sizeof(unsigned long long)));
@@ -301,6 +328,7 @@ extern "C" int64_t hare_topology_polygon_count(hare_topo_t t) { return t ? t->ho
 
 extern "C" int hare_topology_destroy(hare_topo_t t) {
     if (!t) return HARE_OK;
+    if (t->parts.load() > 0) return fail(HARE_ERR_INVALID, "hare_topology_destroy: partitions built on this Topology are still alive (destroy them first)");
     for (size_t k = 0; k < t->d_polys.size(); ++k) { cudaSetDevice(t->devs[k]); cudaFree(t->d_polys[k]); }
     delete t;
     return HARE_OK;
@@ -331,6 +359,8 @@ static VGrid make_vgrid(const hare_part_s* p, const PartDev& d) {
     return g;
 }
 
+static void drop_part(hare_part_s* p) { if (p->topo) --p->topo->parts; delete p; }
+
 static int new_part(hare_topo_t topo, int kind, hare_part_s** out) {
     hare_part_s* p = new hare_part_s();
     p->kind = kind; p->topo = topo;
@@ -339,6 +369,7 @@ static int new_part(hare_topo_t topo, int kind, hare_part_s** out) {
         int rc = init_partdev(p->dev[k], topo->devs[k], topo->d_polys[k]);
         if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
     }
+    ++topo->parts;
     *out = p;
     return HARE_OK;
 }
@@ -356,14 +387,14 @@ static int vg_make_list_box(PartDev& d, uint32_t total, cudaStream_t st, const i
     {   // the wavefront kernel's border-padded occupancy bitmap
         const int64_t padded = ((int64_t)ct[0] + 2) * ((int64_t)ct[1] + 2) * ((int64_t)ct[2] + 2);
         if (padded < (1LL << 32)) {
-            CK(dmalloc(&d.occp, (size_t)((padded + 31) / 32 + 1)));
+            CK(pmalloc(&d.occp, (size_t)((padded + 31) / 32 + 1), st));
             vg_pad_occupancy<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(d.occ, ct[0], ct[1], ct[2], d.occp);
             ++g_launches;
             CK(cudaGetLastError());
         }
     }
     if (total == 0) return HARE_OK;
-    CK(dmalloc(&d.list_box, 2 * (size_t)total));
+    CK(pmalloc(&d.list_box, 2 * (size_t)total, st));
     vg_gather_list_box<<<(unsigned)(((int64_t)total + 255) / 256), 256, 0, st>>>(d.cell_poly, d.polys, total, d.list_box);
     ++g_launches;
     CK(cudaGetLastError());
@@ -380,9 +411,30 @@ static int scan_u32(const uint32_t* in, int64_t n, uint32_t* out /* n + 1 */, ui
     return HARE_OK;
 }
 
+struct BuildTimer {   // device time between the first and the last kernel of a build (CUDA events on its stream)
+    cudaEvent_t e0 = nullptr, e1 = nullptr; cudaStream_t st;
+    explicit BuildTimer(cudaStream_t s) : st(s) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    double stop() { float ms = 0; cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1); return ms; }
+    ~BuildTimer() { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+};
+
+// headers, occupancy bits, ascending lists, padded bitmap and per-entry boxes of a grid whose cell_offset / cell_poly / counts exist
+static int vg_finalize(hare_part_s* p, PartDev& d, const uint32_t* count, uint32_t total, cudaStream_t st) {
+    const int64_t ncells = (int64_t)p->ct[0] * p->ct[1] * p->ct[2];
+    CK(pmalloc(&d.cells, ncells, st)); CK(pmalloc(&d.occ, (ncells + 31) / 32 + 1, st));
+    vg_finish_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(d.cell_offset, count, ncells, d.cell_poly, d.cells, d.occ);
+    ++g_launches;
+    CK(cudaGetLastError());
+    int r = vg_make_list_box(d, total, st, p->ct);
+    if (r) return r;
+    d.bytes = (size_t)ncells * 12 + (size_t)total * 36 + (size_t)ncells / 8;
+    return HARE_OK;
+}
+
 extern "C" int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* out) {
     if (!topo || !out || domain < 1 || domain > 1290) return fail(HARE_ERR_INVALID, "hare_voxelgrid_build: bad argument (1 <= Domain <= 1290)");
     if (topo->devs.empty()) return fail(HARE_ERR_CUDA, "hare_voxelgrid_build: host-only handle, no CUDA device (hare_b200 has no CPU fallback)");
+    const auto w0 = std::chrono::steady_clock::now();
     hare_part_s* p = nullptr;
     int rc = new_part(topo, HARE_VOXEL_GRID, &p);
     if (rc) return rc;
@@ -395,10 +447,12 @@ extern "C" int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* o
         auto body = [&]() -> int {
             CK(cudaSetDevice(d.dev));
             cudaStream_t st = d.stream[0];
+            StreamTemps tmp(st);
+            BuildTimer timer(st);
             uint32_t *count = nullptr, *cursor = nullptr, *tiles = nullptr;
-            CK(dmalloc(&count, ncells)); CK(dmalloc(&cursor, ncells));
-            CK(dmalloc(&tiles, (ncells + HARE_SCAN_TILE - 1) / HARE_SCAN_TILE + 1));
-            CK(dmalloc(&d.cell_offset, ncells + 1)); CK(dmalloc(&d.cells, ncells)); CK(dmalloc(&d.occ, (ncells + 31) / 32 + 1));
+            CK(tmp.get(&count, ncells)); CK(tmp.get(&cursor, ncells));
+            CK(tmp.get(&tiles, (ncells + HARE_SCAN_TILE - 1) / HARE_SCAN_TILE + 1));
+            CK(pmalloc(&d.cell_offset, ncells + 1, st));
             CK(cudaMemsetAsync(count, 0, ncells * 4, st)); CK(cudaMemsetAsync(cursor, 0, ncells * 4, st));
             VGBuild g = { obox[0], obox[1], obox[2], p->vd[0], p->vd[1], p->vd[2], domain, domain, domain };
             const int blocks = d.sms * 8;
@@ -411,53 +465,104 @@ extern "C" int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* o
             CK(cudaMemcpyAsync(&total, d.cell_offset + ncells, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             p->npairs = total;
-            CK(dmalloc(&d.cell_poly, (size_t)total));
+            CK(pmalloc(&d.cell_poly, (size_t)total, st));
             vg_bin_kernel<1><<<blocks, 256, 0, st>>>(g, d.polys, P, nullptr, d.cell_offset, cursor, d.cell_poly);
-            vg_finish_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, st>>>(d.cell_offset, count, ncells, d.cell_poly, d.cells, d.occ);
-            g_launches += 2;
+            ++g_launches;
             CK(cudaGetLastError());
-            r = vg_make_list_box(d, total, st, ct);
+            r = vg_finalize(p, d, count, total, st);
             if (r) return r;
-            CK(cudaStreamSynchronize(st));
-            cudaFree(count); cudaFree(cursor); cudaFree(tiles);
-            d.bytes = (size_t)ncells * 12 + (size_t)total * 36 + (size_t)ncells / 8;
+            p->build_kernel_ms = timer.stop();
             return HARE_OK;
         };
         rc = body();
-        if (rc) { for (auto& dd : p->dev) free_partdev(dd); delete p; return rc; }
+        if (rc) { for (auto& dd : p->dev) { cudaSetDevice(dd.dev); cudaStreamSynchronize(dd.stream[0]); free_partdev(dd); } drop_part(p); return rc; }
     }
+    p->build_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     *out = p;
     return HARE_OK;
 }
 
-// mean list length over the non-empty voxels, from the CSR offsets (host side: runs once per level)
-static int vg_mean_list_length(hare_part_s* p, double* avg) {
-    PartDev& d = p->dev[0];
-    const int64_t ncells = (int64_t)p->ct[0] * p->ct[1] * p->ct[2];
-    std::vector<uint32_t> off((size_t)ncells + 1);
-    CK(cudaSetDevice(d.dev));
-    CK(cudaMemcpy(off.data(), d.cell_offset, (size_t)(ncells + 1) * 4, cudaMemcpyDeviceToHost));
-    double sum = 0; int64_t ct = 0;
-    for (int64_t c = 0; c < ncells; ++c) { const uint32_t n = off[c + 1] - off[c]; if (n) { sum += n; ++ct; } }
-    *avg = ct ? sum / (double)ct : 0.0 / 0.0;   // C#: 0/0 -> NaN, and NaN < Avg_polys is false
+// new Voxel_Grid(Model, MaxDomain, Avg_polys)  (Voxel_Grid.cs:128-254), built the reference's way: level k + 1 tests each child voxel
+// only against its parent's list (:207-215), starting from the single voxel that lists every polygon, and stops after level k > 1 once
+// the mean list length of the non-empty voxels drops below Avg_polys (:252).  O(pairs) per level instead of a full flat rebuild, and
+// exactly the reference's semantics (no reliance on PolyBoxOverlap being monotone under box inclusion in floating point).
+extern "C" int hare_voxelgrid_build_adaptive(hare_topo_t topo, int max_domain_log2, int avg_polys, hare_part_t* out) {
+    if (!topo || !out || max_domain_log2 < 1 || max_domain_log2 > 10) return fail(HARE_ERR_INVALID, "hare_voxelgrid_build_adaptive: 1 <= MaxDomain <= 10");
+    if (topo->devs.empty()) return fail(HARE_ERR_CUDA, "hare_voxelgrid_build_adaptive: host-only handle, no CUDA device (hare_b200 has no CPU fallback)");
+    const auto w0 = std::chrono::steady_clock::now();
+    hare_part_s* p = nullptr;
+    int rc = new_part(topo, HARE_VOXEL_GRID, &p);
+    if (rc) return rc;
+    double obox[6]; vg_bounds(topo->host, obox);
+    const int64_t P = topo->host.P;
+    int final_level = -1;
+    for (PartDev& d : p->dev) {
+        auto body = [&]() -> int {
+            CK(cudaSetDevice(d.dev));
+            cudaStream_t st = d.stream[0];
+            StreamTemps tmp(st);
+            BuildTimer timer(st);
+            // level "-1": one voxel listing every polygon (:158-166)
+            uint32_t *poff = nullptr, *ppoly = nullptr, *count = nullptr;
+            unsigned long long* d_nonempty = nullptr;
+            CK(tmp.get(&poff, 2)); CK(tmp.get(&ppoly, (size_t)P)); CK(tmp.get(&d_nonempty, 1));
+            const uint32_t off0[2] = { 0u, (uint32_t)P };
+            CK(cudaMemcpyAsync(poff, off0, 8, cudaMemcpyHostToDevice, st));
+            fill_iota<<<d.sms * 4, 256, 0, st>>>(ppoly, P);
+            ++g_launches;
+            int64_t npairs = P, pcells = 1;
+            for (int k = 0; k < max_domain_log2; ++k) {        // :169-253
+                if (final_level >= 0 && k > final_level) break;  // further devices replay the level count the first one settled on
+                const int n = 1 << (k + 1);
+                const int32_t ct[3] = { n, n, n };
+                vg_set_dims(p, obox, ct);
+                const int64_t ncells = (int64_t)n * n * n;
+                VGBuild g = { obox[0], obox[1], obox[2], p->vd[0], p->vd[1], p->vd[2], n, n, n };
+                uint32_t *cnt = nullptr, *cursor = nullptr, *tiles = nullptr, *coff = nullptr, *cpoly = nullptr; uint8_t* mask = nullptr;
+                CK(tmp.get(&cnt, ncells)); CK(tmp.get(&cursor, ncells)); CK(tmp.get(&tiles, (ncells + HARE_SCAN_TILE - 1) / HARE_SCAN_TILE + 1));
+                CK(tmp.get(&coff, ncells + 1)); CK(tmp.get(&mask, (size_t)npairs));
+                CK(cudaMemsetAsync(cnt, 0, ncells * 4, st)); CK(cudaMemsetAsync(cursor, 0, ncells * 4, st)); CK(cudaMemsetAsync(d_nonempty, 0, 8, st));
+                const unsigned blocks = (unsigned)((npairs * 8 + 255) / 256);
+                if (npairs) vg_refine_kernel<0><<<blocks, 256, 0, st>>>(g, d.polys, poff, ppoly, npairs, pcells, mask, cnt, nullptr, nullptr, nullptr);
+                int r = scan_u32(cnt, ncells, coff, tiles, st);
+                if (r) return r;
+                vg_count_nonempty<<<d.sms * 4, 256, 0, st>>>(cnt, ncells, d_nonempty);
+                g_launches += 2;
+                uint32_t total = 0; unsigned long long nonempty = 0;
+                CK(cudaMemcpyAsync(&total, coff + ncells, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(&nonempty, d_nonempty, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                CK(tmp.get(&cpoly, (size_t)total));
+                if (npairs) vg_refine_kernel<1><<<blocks, 256, 0, st>>>(g, d.polys, poff, ppoly, npairs, pcells, mask, nullptr, coff, cursor, cpoly);
+                ++g_launches;
+                CK(cudaGetLastError());
+                tmp.drop(poff); tmp.drop(ppoly); tmp.drop(mask); tmp.drop(cursor); tmp.drop(tiles); tmp.drop(count);
+                poff = coff; ppoly = cpoly; count = cnt; npairs = total; pcells = ncells;
+                const double avg = nonempty ? (double)total / (double)nonempty : 0.0 / 0.0;   // C#: 0/0 -> NaN, and NaN < Avg_polys is false
+                const bool stop = (final_level >= 0) ? (k == final_level) : (k > 1 && avg < (double)avg_polys);   // :252
+                if (stop || k == max_domain_log2 - 1) { final_level = k; break; }
+            }
+            // the last level becomes the partition: sort the lists ascending, headers, bitmaps, per-entry boxes
+            tmp.keep(poff); tmp.keep(ppoly);
+            d.cell_offset = poff; d.cell_poly = ppoly;
+            p->npairs = npairs;
+            int r = vg_finalize(p, d, count, (uint32_t)npairs, st);
+            if (r) return r;
+            p->build_kernel_ms = timer.stop();
+            return HARE_OK;
+        };
+        rc = body();
+        if (rc) { for (auto& dd : p->dev) { cudaSetDevice(dd.dev); cudaStreamSynchronize(dd.stream[0]); free_partdev(dd); } drop_part(p); return rc; }
+    }
+    p->build_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    *out = p;
     return HARE_OK;
 }
 
-extern "C" int hare_voxelgrid_build_adaptive(hare_topo_t topo, int max_domain_log2, int avg_polys, hare_part_t* out) {
-    if (!topo || !out || max_domain_log2 < 1 || max_domain_log2 > 10) return fail(HARE_ERR_INVALID, "hare_voxelgrid_build_adaptive: 1 <= MaxDomain <= 10");
-    hare_part_t cur = nullptr;
-    for (int k = 0; k < max_domain_log2; ++k) {        // Voxel_Grid.cs:161-253
-        hare_part_t nxt = nullptr;
-        int rc = hare_voxelgrid_build(topo, 1 << (k + 1), &nxt);
-        if (rc) { if (cur) hare_part_destroy(cur); return rc; }
-        if (cur) hare_part_destroy(cur);
-        cur = nxt;
-        double avg = 0;
-        rc = vg_mean_list_length(cur, &avg);
-        if (rc) { hare_part_destroy(cur); return rc; }
-        if (k > 1 && avg < (double)avg_polys) break;   // :252
-    }
-    *out = cur;
+extern "C" int hare_part_build_ms(hare_part_t p, double* kernel_ms, double* wall_ms) {
+    if (!p) return fail(HARE_ERR_INVALID, "hare_part_build_ms: null handle");
+    if (kernel_ms) *kernel_ms = p->build_kernel_ms;
+    if (wall_ms) *wall_ms = p->build_wall_ms;
     return HARE_OK;
 }
 
@@ -469,6 +574,9 @@ extern "C" int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], con
     if (ncells > 0x7fffffffLL) return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: more than 2^31-1 cells");
     const uint32_t total = cell_offset[ncells];
     if (total && !cell_poly) return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: cell_poly is null");
+    if (cell_offset[0] != 0) return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: cell_offset[0] must be 0");
+    for (int64_t c = 0; c < ncells; ++c)
+        if (cell_offset[c] > cell_offset[c + 1]) return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: cell_offset must be non-decreasing");
     for (uint32_t k = 0; k < total; ++k)
         if ((int64_t)cell_poly[k] >= topo->host.P) return fail(HARE_ERR_INVALID, "hare_voxelgrid_upload: polygon index out of range");
     hare_part_s* p = nullptr;
@@ -494,7 +602,7 @@ extern "C" int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], con
             return HARE_OK;
         };
         rc = body();
-        if (rc) { for (auto& dd : p->dev) free_partdev(dd); delete p; return rc; }
+        if (rc) { for (auto& dd : p->dev) free_partdev(dd); drop_part(p); return rc; }
     }
     *out = p;
     return HARE_OK;
@@ -523,16 +631,7 @@ extern "C" int hare_voxelgrid_download(hare_part_t p, uint32_t* cell_offset, uin
 // ---------------------------------------------------------------------------------------
 // Octree
 // ---------------------------------------------------------------------------------------
-static int oct_depth(const OctTree& t) {
-    int best = 0;
-    std::vector<std::pair<int, int>> st; st.push_back({ 0, 0 });
-    while (!st.empty()) {
-        auto [n, dpt] = st.back(); st.pop_back();
-        best = std::max(best, dpt);
-        if (t.first_child[n] >= 0) for (int i = 0; i < 8; ++i) st.push_back({ t.first_child[n] + i, dpt + 1 });
-    }
-    return best;
-}
+static int oct_depth(const OctTree& t) { return oct_depth_of(t); }   // pack.hpp: index order, children follow their parents
 
 // per tree-list entry: the polygon's padded FP32 box with its id riding in lo.w -- gathered on the device from the records
 // (same kernel as the Voxel_Grid cell lists)
@@ -732,11 +831,11 @@ extern "C" int hare_octree_build(hare_topo_t topo, int maxDepth, int maxPolys, h
         if (p->dev.empty() || (e && *e == '1')) build_octree(topo->host, maxDepth, maxPolys, p->oct);   // host-only handles, or forced
         else {
             rc = build_octree_gpu(topo, p->dev[0].polys, p->dev[0].dev, p->dev[0].stream[0], maxDepth, maxPolys, p->oct);
-            if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+            if (rc) { for (auto& d : p->dev) free_partdev(d); drop_part(p); return rc; }
         }
     }
     rc = oct_to_device(p);
-    if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    if (rc) { for (auto& d : p->dev) free_partdev(d); drop_part(p); return rc; }
     *out = p;
     return HARE_OK;
 }
@@ -746,9 +845,25 @@ extern "C" int hare_octree_upload(hare_topo_t topo, const double* node_box, cons
                                   int64_t n_nodes, int64_t n_list, hare_part_t* out) {
     if (!topo || !node_box || !first_child || !list_off || !list_cnt || n_nodes < 1 || n_list < 0 || !out || (n_list && !polys))
         return fail(HARE_ERR_INVALID, "hare_octree_upload: bad argument");
-    for (int64_t i = 0; i < n_nodes; ++i) {
-        if (first_child[i] >= 0 && (int64_t)first_child[i] + 8 > n_nodes) return fail(HARE_ERR_INVALID, "hare_octree_upload: child index out of range");
-        if (first_child[i] < 0 && (int64_t)list_off[i] + list_cnt[i] > n_list) return fail(HARE_ERR_INVALID, "hare_octree_upload: list range out of bounds");
+    {   // a tree: children come after their parent (the packing passes and the kernels rely on it), every node but the root has
+        // exactly one parent, and the depth stays inside the kernels' frame budget -- cycles and shared subtrees are rejected here
+        std::vector<int32_t> level((size_t)n_nodes, -1);
+        level[0] = 0;
+        int64_t claimed = 1;
+        for (int64_t i = 0; i < n_nodes; ++i) {
+            if (first_child[i] >= 0) {
+                const int64_t fc = first_child[i];
+                if (fc <= i || fc + 8 > n_nodes) return fail(HARE_ERR_INVALID, "hare_octree_upload: children must follow their parent (i < first_child[i], first_child[i] + 8 <= n_nodes)");
+                if (level[i] < 0) return fail(HARE_ERR_INVALID, "hare_octree_upload: node is not reachable from the root");
+                if (level[i] + 1 >= HARE_OCT_MAXLVL) return fail(HARE_ERR_UNSUPPORTED, "hare_octree_upload: octree deeper than HARE_OCT_MAXLVL levels");
+                for (int c = 0; c < 8; ++c) {
+                    if (level[fc + c] >= 0) return fail(HARE_ERR_INVALID, "hare_octree_upload: a node has two parents");
+                    level[fc + c] = level[i] + 1;
+                }
+                claimed += 8;
+            } else if ((int64_t)list_off[i] + list_cnt[i] > n_list) return fail(HARE_ERR_INVALID, "hare_octree_upload: list range out of bounds");
+        }
+        if (claimed != n_nodes) return fail(HARE_ERR_INVALID, "hare_octree_upload: nodes that are not reachable from the root");
     }
     for (int64_t k = 0; k < n_list; ++k) if ((int64_t)polys[k] >= topo->host.P) return fail(HARE_ERR_INVALID, "hare_octree_upload: polygon index out of range");
     hare_part_s* p = nullptr;
@@ -761,7 +876,7 @@ extern "C" int hare_octree_upload(hare_topo_t topo, const double* node_box, cons
     if (n_list) p->oct.polys.assign(polys, polys + n_list);
     p->oct.depth = oct_depth(p->oct);
     rc = oct_to_device(p);
-    if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    if (rc) { for (auto& d : p->dev) free_partdev(d); drop_part(p); return rc; }
     *out = p;
     return HARE_OK;
 }
@@ -789,16 +904,7 @@ extern "C" int hare_octree_download(hare_part_t p, double* node_box, int32_t* fi
 // ---------------------------------------------------------------------------------------
 // KDTree
 // ---------------------------------------------------------------------------------------
-static int kd_depth(const KdTree& t) {
-    int best = 0;
-    std::vector<std::pair<int, int>> st; st.push_back({ 0, 0 });
-    while (!st.empty()) {
-        auto [n, dpt] = st.back(); st.pop_back();
-        best = std::max(best, dpt);
-        if (t.left[n] >= 0) { st.push_back({ t.left[n], dpt + 1 }); st.push_back({ t.left[n] + 1, dpt + 1 }); }
-    }
-    return best;
-}
+static int kd_depth(const KdTree& t) { return kd_depth_of(t); }
 
 static int kd_to_device(hare_part_s* p) {
     const KdTree& t = p->kd;
@@ -832,11 +938,11 @@ extern "C" int hare_kdtree_build(hare_topo_t topo, int maxDepth, int maxPolys, h
         else {
             std::string msg;
             rc = build_kdtree_gpu(topo->host, p->dev[0].polys, p->dev[0].dev, p->dev[0].stream[0], maxDepth, maxPolys, p->kd, msg);
-            if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return fail(HARE_ERR_CUDA, msg); }
+            if (rc) { for (auto& d : p->dev) free_partdev(d); drop_part(p); return fail(HARE_ERR_CUDA, msg); }
         }
     }
     rc = kd_to_device(p);
-    if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    if (rc) { for (auto& d : p->dev) free_partdev(d); drop_part(p); return rc; }
     *out = p;
     return HARE_OK;
 }
@@ -846,9 +952,22 @@ extern "C" int hare_kdtree_upload(hare_topo_t topo, const double* node_box, cons
                                   int64_t n_nodes, int64_t n_list, hare_part_t* out) {
     if (!topo || !node_box || !split || !axis || !left || !list_off || !list_cnt || n_nodes < 1 || n_list < 0 || !out || (n_list && !polys))
         return fail(HARE_ERR_INVALID, "hare_kdtree_upload: bad argument");
-    for (int64_t i = 0; i < n_nodes; ++i) {
-        if (left[i] >= 0 && ((int64_t)left[i] + 2 > n_nodes || axis[i] < 0 || axis[i] > 2)) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: bad internal node");
-        if (left[i] < 0 && (int64_t)list_off[i] + list_cnt[i] > n_list) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: list range out of bounds");
+    {   // same tree checks as hare_octree_upload
+        std::vector<int32_t> level((size_t)n_nodes, -1);
+        level[0] = 0;
+        int64_t claimed = 1;
+        for (int64_t i = 0; i < n_nodes; ++i) {
+            if (left[i] >= 0) {
+                const int64_t l = left[i];
+                if (l <= i || l + 2 > n_nodes || axis[i] < 0 || axis[i] > 2) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: bad internal node (i < left[i], left[i] + 2 <= n_nodes, axis in 0..2)");
+                if (level[i] < 0) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: node is not reachable from the root");
+                if (level[i] + 3 > HARE_KD_MAXSTACK) return fail(HARE_ERR_UNSUPPORTED, "hare_kdtree_upload: kd-tree deeper than HARE_KD_MAXSTACK allows");
+                if (level[l] >= 0 || level[l + 1] >= 0) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: a node has two parents");
+                level[l] = level[l + 1] = level[i] + 1;
+                claimed += 2;
+            } else if ((int64_t)list_off[i] + list_cnt[i] > n_list) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: list range out of bounds");
+        }
+        if (claimed != n_nodes) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: nodes that are not reachable from the root");
     }
     for (int64_t k = 0; k < n_list; ++k) if ((int64_t)polys[k] >= topo->host.P) return fail(HARE_ERR_INVALID, "hare_kdtree_upload: polygon index out of range");
     hare_part_s* p = nullptr;
@@ -863,7 +982,7 @@ extern "C" int hare_kdtree_upload(hare_topo_t topo, const double* node_box, cons
     if (n_list) p->kd.polys.assign(polys, polys + n_list);
     p->kd.depth = kd_depth(p->kd);
     rc = kd_to_device(p);
-    if (rc) { for (auto& d : p->dev) free_partdev(d); delete p; return rc; }
+    if (rc) { for (auto& d : p->dev) free_partdev(d); drop_part(p); return rc; }
     *out = p;
     return HARE_OK;
 }
@@ -988,7 +1107,7 @@ extern "C" int64_t hare_part_device_bytes(hare_part_t p) { return (p && !p->dev.
 extern "C" int hare_part_destroy(hare_part_t p) {
     if (!p) return HARE_OK;
     for (auto& d : p->dev) free_partdev(d);
-    delete p;
+    drop_part(p);
     return HARE_OK;
 }
 
@@ -1183,6 +1302,28 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
 
 static const int64_t kChunk = 1 << 20;   // rays per pipelined chunk of the host-buffer entry points
 
+// CUDA call inside a lambda that reports through an int status (the caller drains every stream before returning it)
+#define CKS(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(HARE_ERR_CUDA, b_);                                                        \
+        }                                                                                          \
+    } while (0)
+
+// Wait for both streams of every device: called on EVERY exit path of the host-buffer entry points, so that no asynchronous copy
+// into the caller's arrays is still in flight when the call returns (the caller may free them right after an error).
+static int drain_streams(hare_part_s* p) {
+    int rc = HARE_OK;
+    for (PartDev& dv : p->dev) {
+        if (cudaSetDevice(dv.dev) != cudaSuccess) { rc = HARE_ERR_CUDA; continue; }
+        for (int s = 0; s < 2; ++s) if (cudaStreamSynchronize(dv.stream[s]) != cudaSuccess) rc = HARE_ERR_CUDA;
+    }
+    return rc;
+}
+
 extern "C" int hare_shoot_batch(hare_part_t p, const double* o, const double* d,
                                 const int32_t* origin1, const int32_t* origin2, const int32_t* ray_id, int64_t N,
                                 double* t, double* xyz, int32_t* poly_id, double* uv, double* o_moved, uint64_t* counters) {
@@ -1192,42 +1333,47 @@ extern "C" int hare_shoot_batch(hare_part_t p, const double* o, const double* d,
     if (G == 0) return fail(HARE_ERR_CUDA, "hare_shoot_batch: host-only handle, no CUDA device (hare_b200 has no CPU fallback)");
     if (counters) std::memset(counters, 0, HARE_CNT_N * sizeof(uint64_t));
     // block-shard the batch over the devices; per device, pipeline chunks over two streams
-    for (int g = 0; g < G; ++g) {
-        PartDev& dv = p->dev[g];
-        const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
-        if (r1 <= r0) continue;
-        int rc = ensure_staging(dv, std::min<int64_t>(kChunk, r1 - r0));
-        if (rc) return rc;
-        CK(cudaSetDevice(dv.dev));
-        if (counters) CK(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
-        if (counters) CK(cudaStreamSynchronize(dv.stream[0]));
-        int s = 0;
-        for (int64_t c0 = r0; c0 < r1; c0 += kChunk, s ^= 1) {
-            const int64_t n = std::min<int64_t>(kChunk, r1 - c0);
-            cudaStream_t st = dv.stream[s];
-            CK(cudaMemcpyAsync(dv.s_o[s], o + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(dv.s_d[s], d + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
-            if (origin1) CK(cudaMemcpyAsync(dv.s_o1[s], origin1 + c0, n * 4, cudaMemcpyHostToDevice, st));
-            if (origin2) CK(cudaMemcpyAsync(dv.s_o2[s], origin2 + c0, n * 4, cudaMemcpyHostToDevice, st));
-            if (ray_id) CK(cudaMemcpyAsync(dv.s_rid[s], ray_id + c0, n * 4, cudaMemcpyHostToDevice, st));
-            ShootArgs a = { dv.s_o[s], dv.s_d[s], origin1 ? dv.s_o1[s] : nullptr, origin2 ? dv.s_o2[s] : nullptr, ray_id ? dv.s_rid[s] : nullptr, n,
-                            t ? dv.s_t[s] : nullptr, xyz ? dv.s_xyz[s] : nullptr, dv.s_pid[s], uv ? dv.s_uv[s] : nullptr,
-                            o_moved ? dv.s_om[s] : nullptr, counters ? dv.counters : nullptr };
-            int rc2 = launch_shoot(p, dv, a, st);
-            if (rc2) return rc2;
-            CK(cudaMemcpyAsync(poly_id + c0, dv.s_pid[s], n * 4, cudaMemcpyDeviceToHost, st));
-            if (t) CK(cudaMemcpyAsync(t + c0, dv.s_t[s], n * 8, cudaMemcpyDeviceToHost, st));
-            if (xyz) CK(cudaMemcpyAsync(xyz + 3 * c0, dv.s_xyz[s], n * 24, cudaMemcpyDeviceToHost, st));
-            if (uv) CK(cudaMemcpyAsync(uv + 2 * c0, dv.s_uv[s], n * 16, cudaMemcpyDeviceToHost, st));
-            if (o_moved) CK(cudaMemcpyAsync(o_moved + 3 * c0, dv.s_om[s], n * 24, cudaMemcpyDeviceToHost, st));
+    auto enqueue = [&]() -> int {
+        for (int g = 0; g < G; ++g) {
+            PartDev& dv = p->dev[g];
+            const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
+            if (r1 <= r0) continue;
+            int rc = ensure_staging(dv, std::min<int64_t>(kChunk, r1 - r0));
+            if (rc) return rc;
+            CKS(cudaSetDevice(dv.dev));
+            if (counters) CKS(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
+            if (counters) CKS(cudaStreamSynchronize(dv.stream[0]));
+            int s = 0;
+            for (int64_t c0 = r0; c0 < r1; c0 += kChunk, s ^= 1) {
+                const int64_t n = std::min<int64_t>(kChunk, r1 - c0);
+                cudaStream_t st = dv.stream[s];
+                CKS(cudaMemcpyAsync(dv.s_o[s], o + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
+                CKS(cudaMemcpyAsync(dv.s_d[s], d + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
+                if (origin1) CKS(cudaMemcpyAsync(dv.s_o1[s], origin1 + c0, n * 4, cudaMemcpyHostToDevice, st));
+                if (origin2) CKS(cudaMemcpyAsync(dv.s_o2[s], origin2 + c0, n * 4, cudaMemcpyHostToDevice, st));
+                if (ray_id) CKS(cudaMemcpyAsync(dv.s_rid[s], ray_id + c0, n * 4, cudaMemcpyHostToDevice, st));
+                ShootArgs a = { dv.s_o[s], dv.s_d[s], origin1 ? dv.s_o1[s] : nullptr, origin2 ? dv.s_o2[s] : nullptr, ray_id ? dv.s_rid[s] : nullptr, n,
+                                t ? dv.s_t[s] : nullptr, xyz ? dv.s_xyz[s] : nullptr, dv.s_pid[s], uv ? dv.s_uv[s] : nullptr,
+                                o_moved ? dv.s_om[s] : nullptr, counters ? dv.counters : nullptr };
+                int rc2 = launch_shoot(p, dv, a, st);
+                if (rc2) return rc2;
+                CKS(cudaMemcpyAsync(poly_id + c0, dv.s_pid[s], n * 4, cudaMemcpyDeviceToHost, st));
+                if (t) CKS(cudaMemcpyAsync(t + c0, dv.s_t[s], n * 8, cudaMemcpyDeviceToHost, st));
+                if (xyz) CKS(cudaMemcpyAsync(xyz + 3 * c0, dv.s_xyz[s], n * 24, cudaMemcpyDeviceToHost, st));
+                if (uv) CKS(cudaMemcpyAsync(uv + 2 * c0, dv.s_uv[s], n * 16, cudaMemcpyDeviceToHost, st));
+                if (o_moved) CKS(cudaMemcpyAsync(o_moved + 3 * c0, dv.s_om[s], n * 24, cudaMemcpyDeviceToHost, st));
+            }
         }
-    }
-    for (int g = 0; g < G; ++g) {
-        PartDev& dv = p->dev[g];
-        CK(cudaSetDevice(dv.dev));
-        CK(cudaStreamSynchronize(dv.stream[0]));
-        CK(cudaStreamSynchronize(dv.stream[1]));
-        if (counters) {
+        return HARE_OK;
+    };
+    const int rc = enqueue();
+    const int rs = drain_streams(p);
+    if (rc) return rc;
+    if (rs) return fail(HARE_ERR_CUDA, std::string("hare_shoot_batch: ") + cudaGetErrorString(cudaGetLastError()));
+    if (counters) {
+        for (int g = 0; g < G; ++g) {
+            PartDev& dv = p->dev[g];
+            CK(cudaSetDevice(dv.dev));
             unsigned long long h[4];
             CK(cudaMemcpy(h, dv.counters, sizeof h, cudaMemcpyDeviceToHost));
             for (int k = 0; k < 4; ++k) counters[k] += h[k];
@@ -1259,40 +1405,45 @@ extern "C" int hare_reflect_chain(hare_part_t p, const double* o, const double* 
     const int64_t chunk = events ? std::max<int64_t>(1024, kChunk / order) : kChunk;
     if (counters) std::memset(counters, 0, HARE_CNT_N * sizeof(uint64_t));
     if (total_shots) *total_shots = 0;
-    for (int g = 0; g < G; ++g) {
-        PartDev& dv = p->dev[g];
-        const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
-        if (r1 <= r0) continue;
-        int rc = ensure_staging(dv, std::min<int64_t>(chunk, r1 - r0));
-        if (rc) return rc;
-        if (events) { rc = ensure_chain_staging(dv, std::min<int64_t>(chunk, r1 - r0), order); if (rc) return rc; }
-        else if (nshots) { rc = ensure_chain_staging(dv, std::min<int64_t>(chunk, r1 - r0), 1); if (rc) return rc; }
-        CK(cudaSetDevice(dv.dev));
-        CK(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
-        CK(cudaStreamSynchronize(dv.stream[0]));
-        int s = 0;
-        for (int64_t c0 = r0; c0 < r1; c0 += chunk, s ^= 1) {
-            const int64_t n = std::min<int64_t>(chunk, r1 - c0);
-            cudaStream_t st = dv.stream[s];
-            CK(cudaMemcpyAsync(dv.s_o[s], o + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(dv.s_d[s], d + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
-            ChainArgs a = { dv.s_o[s], dv.s_d[s], n, order, ev_poly_id ? dv.c_evpid[s] : nullptr, ev_t ? dv.c_evt[s] : nullptr,
-                            fin_o ? dv.s_xyz[s] : nullptr, fin_d ? dv.s_om[s] : nullptr, nshots ? dv.c_ns[s] : nullptr,
-                            dv.counters + 4, counters ? dv.counters : nullptr };
-            int rc2 = launch_chain(p, dv, a, st);
-            if (rc2) return rc2;
-            if (ev_poly_id) CK(cudaMemcpyAsync(ev_poly_id + c0 * order, dv.c_evpid[s], (size_t)n * order * 4, cudaMemcpyDeviceToHost, st));
-            if (ev_t) CK(cudaMemcpyAsync(ev_t + c0 * order, dv.c_evt[s], (size_t)n * order * 8, cudaMemcpyDeviceToHost, st));
-            if (fin_o) CK(cudaMemcpyAsync(fin_o + 3 * c0, dv.s_xyz[s], n * 24, cudaMemcpyDeviceToHost, st));
-            if (fin_d) CK(cudaMemcpyAsync(fin_d + 3 * c0, dv.s_om[s], n * 24, cudaMemcpyDeviceToHost, st));
-            if (nshots) CK(cudaMemcpyAsync(nshots + c0, dv.c_ns[s], n * 4, cudaMemcpyDeviceToHost, st));
+    auto enqueue = [&]() -> int {
+        for (int g = 0; g < G; ++g) {
+            PartDev& dv = p->dev[g];
+            const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
+            if (r1 <= r0) continue;
+            int rc = ensure_staging(dv, std::min<int64_t>(chunk, r1 - r0));
+            if (rc) return rc;
+            if (events) { rc = ensure_chain_staging(dv, std::min<int64_t>(chunk, r1 - r0), order); if (rc) return rc; }
+            else if (nshots) { rc = ensure_chain_staging(dv, std::min<int64_t>(chunk, r1 - r0), 1); if (rc) return rc; }
+            CKS(cudaSetDevice(dv.dev));
+            CKS(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
+            CKS(cudaStreamSynchronize(dv.stream[0]));
+            int s = 0;
+            for (int64_t c0 = r0; c0 < r1; c0 += chunk, s ^= 1) {
+                const int64_t n = std::min<int64_t>(chunk, r1 - c0);
+                cudaStream_t st = dv.stream[s];
+                CKS(cudaMemcpyAsync(dv.s_o[s], o + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
+                CKS(cudaMemcpyAsync(dv.s_d[s], d + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
+                ChainArgs a = { dv.s_o[s], dv.s_d[s], n, order, ev_poly_id ? dv.c_evpid[s] : nullptr, ev_t ? dv.c_evt[s] : nullptr,
+                                fin_o ? dv.s_xyz[s] : nullptr, fin_d ? dv.s_om[s] : nullptr, nshots ? dv.c_ns[s] : nullptr,
+                                dv.counters + 4, counters ? dv.counters : nullptr };
+                int rc2 = launch_chain(p, dv, a, st);
+                if (rc2) return rc2;
+                if (ev_poly_id) CKS(cudaMemcpyAsync(ev_poly_id + c0 * order, dv.c_evpid[s], (size_t)n * order * 4, cudaMemcpyDeviceToHost, st));
+                if (ev_t) CKS(cudaMemcpyAsync(ev_t + c0 * order, dv.c_evt[s], (size_t)n * order * 8, cudaMemcpyDeviceToHost, st));
+                if (fin_o) CKS(cudaMemcpyAsync(fin_o + 3 * c0, dv.s_xyz[s], n * 24, cudaMemcpyDeviceToHost, st));
+                if (fin_d) CKS(cudaMemcpyAsync(fin_d + 3 * c0, dv.s_om[s], n * 24, cudaMemcpyDeviceToHost, st));
+                if (nshots) CKS(cudaMemcpyAsync(nshots + c0, dv.c_ns[s], n * 4, cudaMemcpyDeviceToHost, st));
+            }
         }
-    }
+        return HARE_OK;
+    };
+    const int rc = enqueue();
+    const int rs = drain_streams(p);
+    if (rc) return rc;
+    if (rs) return fail(HARE_ERR_CUDA, std::string("hare_reflect_chain: ") + cudaGetErrorString(cudaGetLastError()));
     for (int g = 0; g < G; ++g) {
         PartDev& dv = p->dev[g];
         CK(cudaSetDevice(dv.dev));
-        CK(cudaStreamSynchronize(dv.stream[0]));
-        CK(cudaStreamSynchronize(dv.stream[1]));
         unsigned long long h[5];
         CK(cudaMemcpy(h, dv.counters, sizeof h, cudaMemcpyDeviceToHost));
         if (counters) for (int k = 0; k < 4; ++k) counters[k] += h[k];

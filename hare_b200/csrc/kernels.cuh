@@ -80,6 +80,67 @@ vg_bin_kernel(const VGBuild g, const PolyRec* __restrict__ polys, long long P,
     }
 }
 
+// Level step of the hierarchical constructor Voxel_Grid(Model, MaxDomain, Avg_polys) (Voxel_Grid.cs:161-253): a child voxel tests only
+// the polygons of its parent's list (:207-215), so every (parent voxel, polygon) pair of the previous level runs PolyBoxOverlap on
+// the parent's eight children -- one thread per (pair, child), the eight lanes of a pair share the parent look-up and the record.
+//   PASS 0: SAT -> one mask byte per pair + the child voxels' list lengths.   PASS 1: scatter from the stored masks.
+// g = the CHILD grid (counts 2x the parent's); lists come out unordered and are sorted by vg_finish_cells like the flat build's.
+template <int PASS>
+__global__ void __launch_bounds__(256)
+vg_refine_kernel(const VGBuild g, const PolyRec* __restrict__ polys, const uint32_t* __restrict__ parent_offset,
+                 const uint32_t* __restrict__ parent_poly, long long npairs, long long ncells_parent, uint8_t* __restrict__ mask,
+                 uint32_t* __restrict__ cell_count, const uint32_t* __restrict__ cell_offset, uint32_t* __restrict__ cursor,
+                 uint32_t* __restrict__ cell_poly) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pair = tid >> 3;
+    const int ch = (int)(tid & 7), lane = threadIdx.x & 31, lead = lane & ~7;
+    const bool valid = pair < npairs;
+    long long cell = 0;
+    if (valid && lane == lead) {       // parent voxel of this pair: the last c with parent_offset[c] <= pair
+        long long lo = 0, hi = ncells_parent;          // invariant: parent_offset[lo] <= pair < parent_offset[hi]
+        while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if ((long long)parent_offset[mid] <= pair) lo = mid; else hi = mid; }
+        cell = lo;
+    }
+    cell = __shfl_sync(0xffffffffu, cell, lead);
+    const int pnz = g.nz >> 1, pny = g.ny >> 1;
+    const int Z = (int)(cell % pnz), Y = (int)((cell / pnz) % pny), X = (int)(cell / ((long long)pnz * pny));
+    const int x = 2 * X + ((ch >> 2) & 1), y = 2 * Y + ((ch >> 1) & 1), z = 2 * Z + (ch & 1);
+    const uint32_t ci = ((uint32_t)x * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nz + (uint32_t)z;
+    const uint32_t poly = valid ? parent_poly[pair] : 0u;
+    if (PASS == 0) {
+        bool hit = false;
+        if (valid) {
+            double V[16];
+            load_poly(polys, poly, V);
+            const int n = (V[15] == 4.0) ? 4 : 3;
+            // voxel box exactly as the constructor builds it (Voxel_Grid.cs:198-201): (x * VoxelDims - Epsilon) + OBox.Min ...
+            const Box3 B = make_box(((double)x * g.vdx - HARE_EPS) + g.ominx, ((double)y * g.vdy - HARE_EPS) + g.ominy,
+                                    ((double)z * g.vdz - HARE_EPS) + g.ominz,
+                                    ((double)(x + 1) * g.vdx + HARE_EPS) + g.ominx, ((double)(y + 1) * g.vdy + HARE_EPS) + g.ominy,
+                                    ((double)(z + 1) * g.vdz + HARE_EPS) + g.ominz);
+            hit = poly_box_overlap(B, V, n);
+            if (hit) atomicAdd(cell_count + ci, 1u);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (valid && lane == lead) mask[pair] = (uint8_t)((b >> lead) & 0xffu);
+    } else {
+        if (valid && ((mask[pair] >> ch) & 1u)) cell_poly[cell_offset[ci] + atomicAdd(cursor + ci, 1u)] = poly;
+    }
+}
+
+// number of non-empty voxels (the stop rule's denominator, Voxel_Grid.cs:251-252)
+__global__ void __launch_bounds__(256) vg_count_nonempty(const uint32_t* __restrict__ cell_count, long long ncells, unsigned long long* __restrict__ out) {
+    unsigned int s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (long long)gridDim.x * blockDim.x) s += cell_count[i] ? 1u : 0u;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, (unsigned long long)s);
+}
+
+__global__ void __launch_bounds__(256) fill_iota(uint32_t* __restrict__ a, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] = (uint32_t)i;
+}
+
 // Exclusive scan of n uint32 in three passes (tile sums, scan of tile sums, tile scan + offset).
 #define HARE_SCAN_TILE 4096   /* 1024 threads x 4 items */
 

@@ -508,7 +508,7 @@ HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const 
 #if defined(__CUDACC__)
 
 #ifndef HARE_OCTW_WARPS
-#define HARE_OCTW_WARPS 19
+#define HARE_OCTW_WARPS 16   /* 16 x 11.9 KB pools = 190 KB: the 196 KB shared-memory carve-out, leaving ~60 KB of L1 for the tree's upper levels (19 warps / 28 KB L1: 461 vs 595 Mrays/s on C3) */
 #endif
 
 template <bool CHAIN, bool COUNT, int SLOTS, int N_MAX>

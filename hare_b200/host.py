@@ -100,7 +100,9 @@ class Topology:
         self.Min, self.Max, self.Vertex_Count = mm[:3].copy(), mm[3:].copy(), nv.value
         self._mm = mm
         if self._h:
-            L.hare_topology_destroy(self._h)
+            # partitions built on the previous flattening still read its device records: the library refuses to free it
+            check(L.hare_topology_destroy(self._h), "Finish_Topology (re-finishing a Topology that still has live partitions)")
+            self._h = None
         h = C.c_void_p()
         check(L.hare_topology_create(ptr(verts), ptr(normals), ptr(cnt), P, ptr(mm), C.byref(h)), "hare_topology_create")
         self._h = h
@@ -252,6 +254,12 @@ class Voxel_Grid(Spatial_Partition):
         obox = np.empty(6); vd = np.empty(3); ct = np.empty(3, np.int32); n = C.c_int64()
         check(_lib.lib().hare_voxelgrid_info(self._h, ptr(obox), ptr(vd), ptr(ct), C.byref(n)), "hare_voxelgrid_info")
         return obox, vd, ct, n.value
+
+    def build_ms(self):
+        """(device time of the build kernels, host wall time of the constructor) in ms."""
+        k, w = C.c_double(), C.c_double()
+        check(_lib.lib().hare_part_build_ms(self._h, C.byref(k), C.byref(w)), "hare_part_build_ms")
+        return k.value, w.value
 
     def csr(self):
         _, _, ct, n = self.info()

@@ -77,6 +77,8 @@ int hare_topology_ingest(const double* raw_verts, const int32_t* vcount, int64_t
 int hare_topology_create(const double* verts, const double* normals, const int32_t* vcount, int64_t P,
                          const double minmax[6], hare_topo_t* out);
 int64_t hare_topology_polygon_count(hare_topo_t topo);
+/* Lifetime: a partition reads its Topology's device records for as long as it lives.  Destroy partitions first;
+ * hare_topology_destroy fails with HARE_ERR_INVALID (and frees nothing) while any partition built on the handle is alive. */
 int hare_topology_destroy(hare_topo_t topo);
 
 /* ---- Voxel_Grid -------------------------------------------------------- */
@@ -86,13 +88,13 @@ int hare_topology_destroy(hare_topo_t topo);
 int hare_voxelgrid_build(hare_topo_t topo, int domain, hare_part_t* out);
 /* new Voxel_Grid(Model, MaxDomain, Avg_polys)  (Voxel_Grid.cs:128-254): the grid is refined 2x per axis per
  * level, up to 2^MaxDomain voxels per axis, stopping after level k > 1 once the mean list length of the
- * non-empty voxels drops below Avg_polys (:252).  The reference filters each child voxel's list through its
- * parent's; a child box lies inside its parent box (their shared faces are bit-identical), so the lists are
- * those of the flat constructor at the final resolution -- which is what is built here, level by level, on
- * the GPU (CSR equality with the reference-order hierarchical build is tested up to 256^3 / 2M polygons). */
+ * non-empty voxels drops below Avg_polys (:252).  Built the reference's way on the GPU: a child voxel tests
+ * only the polygons of its parent's list (:207-215), level by level from the single voxel that lists every
+ * polygon (CSR equality with the oracle's hierarchical build is tested up to 256^3 / 2M polygons). */
 int hare_voxelgrid_build_adaptive(hare_topo_t topo, int max_domain_log2, int avg_polys, hare_part_t* out);
 /* Upload a grid built by the host (e.g. Hare's hierarchical ctor, Voxel_Grid.cs:128-254):
- * obox = OBox.Min xyz, OBox.Max xyz; ct = VoxelCtX/Y/Z; CSR lists, cell index ((x*Ny+y)*Nz+z). */
+ * obox = OBox.Min xyz, OBox.Max xyz; ct = VoxelCtX/Y/Z; CSR lists, cell index ((x*Ny+y)*Nz+z).
+ * Checked: cell_offset[0] == 0, non-decreasing offsets, polygon indices < P (HARE_ERR_INVALID otherwise). */
 int hare_voxelgrid_upload(hare_topo_t topo, const double obox[6], const int32_t ct[3],
                           const uint32_t* cell_offset, const uint32_t* cell_poly, hare_part_t* out);
 int hare_voxelgrid_info(hare_part_t part, double obox[6], double voxeldims[3], int32_t ct[3], int64_t* npairs);
@@ -102,7 +104,9 @@ int hare_voxelgrid_download(hare_part_t part, uint32_t* cell_offset, uint32_t* c
 /* new Octree(Model, maxDepth, maxPolygonsPerNode)  (:45-138). */
 int hare_octree_build(hare_topo_t topo, int maxDepth, int maxPolygonsPerNode, hare_part_t* out);
 /* Upload a host-built tree: node_box N x 6 (Min xyz, Max xyz); first_child[i] = index of child 0
- * (children are 8 consecutive nodes) or -1 for a leaf; leaf lists are polys[list_off, +list_cnt). */
+ * (children are 8 consecutive nodes) or -1 for a leaf; leaf lists are polys[list_off, +list_cnt).
+ * Checked (also for files read by hare_part_load): children follow their parent (i < first_child[i]), every node but the root has
+ * exactly one parent (no cycles, no shared subtrees, no orphans), depth < 20, list ranges and polygon indices in bounds. */
 int hare_octree_upload(hare_topo_t topo, const double* node_box, const int32_t* first_child,
                        const uint32_t* list_off, const uint32_t* list_cnt, const uint32_t* polys,
                        int64_t n_nodes, int64_t n_list, hare_part_t* out);
@@ -127,6 +131,8 @@ int hare_kdtree_download(hare_part_t part, double* node_box, double* split, int3
 int hare_part_save(hare_part_t part, const char* path);
 int hare_part_load(hare_topo_t topo, const char* path, hare_part_t* out);
 
+/* Device time of the build's kernels (CUDA events) and host wall time of the constructor call, in ms (Voxel_Grid builds; 0 otherwise). */
+int hare_part_build_ms(hare_part_t part, double* kernel_ms, double* wall_ms);
 int hare_part_kind(hare_part_t part);
 int64_t hare_part_device_bytes(hare_part_t part);
 int hare_part_destroy(hare_part_t part);

@@ -454,3 +454,132 @@ def test_rays_from_far_outside_the_model(gpu):
             ref = getattr(ho, kind)(To, *oargs).Shoot(of[:n], d[:n], nthreads=8)
             assert_events_equal(got, ref, uv=kind != "Voxel_Grid", what=f"{kind} from {back:g} m")
             assert (ref["poly_id"] >= 0).mean() > 0.9
+
+
+# ---------------------------------------------------------------- constructed quirk cases (Q4, Q11, Q14; CPU side: tests/test_quirks.py)
+def test_q4_dda_tie_rule(gpu):
+    """Voxel_Grid.cs:504-550: X only if strictly below both, Y only if below Z, else Z.  Cubic room => bit-identical tMax values."""
+    from tests import quirk_cases as qc
+    mesh = qc.cube_room()
+    T, To = _pair(gpu, mesh)
+    o, d = qc.dda_tie_rays()
+    og = ho.Voxel_Grid(To, 8, mode="flat")
+    ref = og.Shoot(o, d)
+    got = gpu.Voxel_Grid([T], 8).Shoot_Batch(o, d, counters=True)
+    assert_events_equal(got, ref, uv=False, what="Q4")
+    assert int(got["counters"][0]) == int(ref["counters"][0])      # voxels entered: the same path through every tie
+
+
+def test_q11_octree_early_return_is_not_the_closest_hit(gpu):
+    """"Octree - alt.cs":233-237: far-first pops + early return.  The table is closer, the Octree reports the floor; and the hall rays
+    contain such cases too (octree.poly_id != the KDTree's global closest hit), all reproduced."""
+    from tests import quirk_cases as qc
+    mesh = qc.table_room()
+    T, To = _pair(gpu, mesh)
+    o, d = qc.table_rays()
+    ref = ho.Octree(To, 4, 1).Shoot(o, d)
+    got = gpu.Octree([T], 4, 1).Shoot_Batch(o, d)
+    assert_events_equal(got, ref, what="Q11 table")
+    kd = gpu.KDTree([T], 6, 1).Shoot_Batch(o, d)
+    assert (kd["poly_id"] == 6).all() and (got["poly_id"] == 0).sum() >= 50
+    mesh = meshes.hall("10k")
+    T, To = _pair(gpu, mesh)
+    o, d = rays_from_sources(50_000, meshes.sources(8), stream=3)
+    oc = gpu.Octree([T], 6, 16).Shoot_Batch(o, d)
+    kd = gpu.KDTree([T], 18, 16).Shoot_Batch(o, d)
+    farther = oc["t"] > kd["t"]
+    assert farther.sum() >= 100 and (oc["poly_id"] != kd["poly_id"])[farther].all()
+    ref = ho.Octree(To, 6, 16).Shoot(o[farther], d[farther], nthreads=8)
+    assert_events_equal({k: oc[k][farther] for k in ("poly_id", "t", "xyz", "uv")}, ref, what="Q11 hall")
+
+
+def test_q14_absolute_determinant_threshold(gpu):
+    """Hare_Geometry_Polygons.cs:483, 494: |det| <= 1e-6 is absolute, so a short direction vector makes a small triangle invisible."""
+    from tests import quirk_cases as qc
+    mesh = qc.sliver_room()
+    T, To = _pair(gpu, mesh)
+    o, d = qc.sliver_rays()
+    for kind, args, oargs in (("Voxel_Grid", (10,), (10, "flat")), ("Octree", (3, 2), (3, 2)), ("KDTree", (4, 1), (4, 1))):
+        got = getattr(gpu, kind)([T], *args).Shoot_Batch(o, d)
+        ref = getattr(ho, kind)(To, *oargs).Shoot(o, d)
+        assert_events_equal(got, ref, uv=kind != "Voxel_Grid", what="Q14 " + kind)
+        assert list(got["poly_id"]) == [6, 3, 6, 3]
+
+
+def test_kdtree_exact_ties_oblique_rays(gpu):
+    """Exact-t ties on oblique rays through shared edges / vertices: the tie rule reads the reference's node boxes, not the
+    content-tightened device boxes (tests/test_tree_emu.py shows that the tightened ones fail this test)."""
+    from tests.test_tree_emu import lattice_tie_rays
+    mesh = meshes.lattice_room()
+    T, To = _pair(gpu, mesh)
+    o, d = lattice_tie_rays()
+    for args in ((20, 2), (12, 8)):
+        kd = ho.KDTree(To, *args)
+        ref = kd.Shoot(o, d, nthreads=8)
+        second = kd.Shoot(o, d, origin1=ref["poly_id"], nthreads=8)
+        assert ((second["t"] == ref["t"]) & (ref["poly_id"] >= 0) & (second["poly_id"] >= 0)).sum() >= 100
+        got = gpu.KDTree([T], *args).Shoot_Batch(o, d)
+        assert_events_equal(got, ref, what=f"KDTree{args} oblique ties")
+
+
+# ---------------------------------------------------------------- the BASELINE sizes (C3 / C4 / C5)
+@pytest.fixture(scope="module")
+def hall500k(gpu):
+    mesh = meshes.hall("500k")
+    return mesh, gpu.Topology.from_mesh(mesh), ho.Topology.from_mesh(mesh)
+
+
+@pytest.fixture(scope="module")
+def hall2m(gpu):
+    mesh = meshes.hall("2m")
+    return mesh, gpu.Topology.from_mesh(mesh), ho.Topology.from_mesh(mesh)
+
+
+def test_c3_octree_500k(gpu, hall500k):
+    """BASELINE config 3 at size: hall-500k, Octree(Model, 7, 32): tree structure and 100 k Shoots bit-equal to the oracle."""
+    from tests.util import canon_octree
+    mesh, T, To = hall500k
+    o, d = rays_from_sources(100_000, meshes.sources(8), stream=3)
+    g = gpu.Octree([T], 7, 32); og = ho.Octree(To, 7, 32)
+    i = g.info(); n, l, lost = og.info()
+    assert (i["nodes"], i["list_entries"], i["lost"]) == (n, l, lost)
+    assert canon_octree(*g.arrays()) == canon_octree(*og.arrays())      # same boxes, same children, same list order (numbering-independent form)
+    assert_events_equal(g.Shoot_Batch(o, d), og.Shoot(o, d, nthreads=16), what="C3 Octree(7,32)")
+
+
+def test_c3_voxelgrid_and_kdtree_500k(gpu, hall500k):
+    mesh, T, To = hall500k
+    o, d = rays_from_sources(100_000, meshes.sources(8), stream=3)
+    g = gpu.Voxel_Grid([T], 128); og = ho.Voxel_Grid(To, 128, mode="fast", nthreads=16)
+    a, b = g.csr(), og.csr()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert_events_equal(g.Shoot_Batch(o, d), og.Shoot(o, d, nthreads=16), uv=False, what="hall-500k Voxel_Grid 128")
+    k = gpu.KDTree([T], 24, 16); ok = ho.KDTree(To, 24, 16)
+    assert_events_equal(k.Shoot_Batch(o[:1500], d[:1500]), ok.Shoot(o[:1500], d[:1500], nthreads=16), what="hall-500k KDTree(24,16)")
+
+
+def test_c4_kdtree_2m(gpu, hall2m):
+    """BASELINE config 4 at size: hall-2m, KDTree(Model, 24, 16), 2 k rays against the exhaustive oracle (O(P) per ray)."""
+    mesh, T, To = hall2m
+    o, d = rays_from_sources(2_000, meshes.sources(8), stream=4)
+    k = gpu.KDTree([T], 24, 16); ok = ho.KDTree(To, 24, 16)
+    assert k.info()["nodes"] == ok.info()[0] and k.info()["list_entries"] == ok.info()[1]
+    assert_events_equal(k.Shoot_Batch(o, d), ok.Shoot(o, d, nthreads=16), what="C4 KDTree(24,16)")
+
+
+def test_c4_c5_voxelgrid_256_2m(gpu, hall2m):
+    """BASELINE configs 4 / 5 at size: 2 M polygons -> 256^3 cell lists, exact CSR equality with the oracle's hierarchical constructor
+    Voxel_Grid(Model, MaxDomain = 8, Avg_polys = 0) (Voxel_Grid.cs:128-254), for the flat build and for the library's own
+    hierarchical build (8, 0); then 200 k Shoots."""
+    mesh, T, To = hall2m
+    og = ho.Voxel_Grid(To, 8, mode="hier", avg_polys=0, nthreads=16)
+    ooff, opol = og.csr()
+    g = gpu.Voxel_Grid([T], 256)
+    off, pol = g.csr()
+    assert np.array_equal(off, ooff) and np.array_equal(pol, opol)
+    ga = gpu.Voxel_Grid([T], 8, 0)
+    assert tuple(ga.info()[2]) == (256, 256, 256)
+    off, pol = ga.csr()
+    assert np.array_equal(off, ooff) and np.array_equal(pol, opol)
+    o, d = rays_from_sources(200_000, meshes.sources(8), stream=4)
+    assert_events_equal(g.Shoot_Batch(o, d), og.Shoot(o, d, nthreads=16), uv=False, what="C4 Voxel_Grid 256")

@@ -111,6 +111,51 @@ def test_upload_validation(host_only):
     assert vd.tolist() == [1.0, 1.0, 1.0] and n == 8 and g.Char_Step == 1.0
 
 
+def test_upload_rejects_malformed_trees_and_offsets(host_only):
+    """a cycle (first_child[0] = 0) used to hang the depth scan, a child index <= its parent silently broke the packing
+    passes, and decreasing cell offsets made the kernels read out of bounds.  All are refused now -- also through hare_part_load."""
+    T = hb.Topology.from_mesh(meshes.shoebox())
+    z6 = lambda n: np.zeros((n, 6))
+    with pytest.raises(hb.HareError, match="non-decreasing"):
+        hb.Voxel_Grid.from_lists([T], [0, 0, 0, 2, 2, 2], [2, 2, 2], [0, 3, 2, 4, 5, 5, 6, 7, 8], np.arange(8) % 6)
+    with pytest.raises(hb.HareError, match=r"cell_offset\[0\]"):
+        hb.Voxel_Grid.from_lists([T], [0, 0, 0, 1, 1, 1], [1, 1, 1], [1, 2], [0, 1])
+    with pytest.raises(hb.HareError, match="follow their parent"):          # the root is its own child: a cycle
+        hb.Octree.from_nodes([T], z6(9), [0] + [-1] * 8, [0] * 9, [0] * 9, [0])
+    with pytest.raises(hb.HareError, match="follow their parent"):          # child block in front of its parent
+        hb.Octree.from_nodes([T], z6(17), [9, -1, -1, -1, -1, -1, -1, -1, -1, 1] + [-1] * 7, [0] * 17, [0] * 17, [0])
+    with pytest.raises(hb.HareError, match="two parents"):                  # nodes 1 and 2 share the block 9..16
+        hb.Octree.from_nodes([T], z6(17), [1, 9, 9] + [-1] * 14, [0] * 17, [0] * 17, [0])
+    with pytest.raises(hb.HareError, match="not reachable"):                # 8 orphan nodes behind the root's children
+        hb.Octree.from_nodes([T], z6(17), [1] + [-1] * 16, [0] * 17, [0] * 17, [0])
+    with pytest.raises(hb.HareError, match="bad internal node"):            # kd cycle: left[0] = 0
+        hb.KDTree.from_nodes([T], z6(3), [0.0] * 3, [0, -1, -1], [0, -1, -1], [0] * 3, [0] * 3, [0])
+    with pytest.raises(hb.HareError, match="two parents"):
+        hb.KDTree.from_nodes([T], z6(5), [0.0] * 5, [0, 1, 1, -1, -1], [1, 3, 3, -1, -1], [0] * 5, [0] * 5, [0])
+    with pytest.raises(hb.HareError, match="not reachable"):
+        hb.KDTree.from_nodes([T], z6(5), [0.0] * 5, [0, -1, -1, -1, -1], [1, -1, -1, -1, -1], [0] * 5, [0] * 5, [0])
+    # a chain deeper than the kernels' frame budget
+    n = 8 * 21 + 1
+    fc = np.full(n, -1, np.int32); fc[0] = 1
+    for k in range(1, 21):
+        fc[8 * (k - 1) + 1] = 8 * k + 1
+    with pytest.raises(NotImplementedError, match="deeper"):
+        hb.Octree.from_nodes([T], z6(n), fc, np.zeros(n), np.zeros(n), [0])
+
+
+def test_topology_outlives_its_partitions(host_only):
+    """a partition reads its Topology's records; the library refuses to free a Topology with live partitions, and the
+    Python mirror refuses to re-finish one."""
+    T = hb.Topology.from_mesh(meshes.shoebox())
+    t = hb.Octree([T], 3, 2)
+    assert hb.lib().hare_topology_destroy(T._h) != 0 and b"still alive" in hb.lib().hare_last_error()
+    with pytest.raises(hb.HareError, match="still alive"):
+        T.Finish_Topology()
+    assert t.info()["nodes"] > 1            # the partition is intact
+    del t
+    T.Finish_Topology()                     # fine once the partition is gone
+
+
 def test_no_cpu_fallback(host_only):
     """Host-only handles cannot compute: Shoot, chains and the GPU grid build fail with HARE_ERR_CUDA."""
     T = hb.Topology.from_mesh(meshes.shoebox())
@@ -159,3 +204,26 @@ def test_partition_save_load_roundtrip(host_only, tmp_path, kind, args):
         fh.truncate(200)
     with pytest.raises(hb.HareError):
         getattr(hb, kind).Load([T], f)
+
+
+def test_sass_has_no_contracted_fp64_multiply_adds():
+    """Bit-exactness against the reference's C# doubles needs every a*b+c to stay two roundings (nvcc -fmad=false).  Guard on the
+    shipped SASS: the kernels that are pure mul/add chains (the SAT of the grid and Octree builds) contain NO DFMA at all although
+    they hold > 100 DMUL and DADD each; in every other kernel DFMA only occurs in the IEEE division / reciprocal sequences
+    (MUFU.RCP64H + Newton steps, <= 9 DFMA per division) and in the handful of explicit fma() calls of the conservative culls."""
+    import re
+    out = subprocess.run(["cuobjdump", "-sass", _lib.SO_PATH], capture_output=True, text=True).stdout
+    parts = re.split(r"\n\s*Function : ", out)[1:]
+    assert len(parts) >= 30
+    seen = set()
+    for p in parts:
+        name = p.split("\n", 1)[0].strip()
+        dfma = len(re.findall(r"\bDFMA\b", p)); rcp = len(re.findall(r"MUFU\.RCP64H", p))
+        dmul = len(re.findall(r"\bDMUL\b", p)); dadd = len(re.findall(r"\bDADD\b", p))
+        if "vg_refine_kernelILi0" in name or "oct_mask_kernel" in name:
+            seen.add(name[:40])
+            assert dfma == 0 and dmul > 100 and dadd > 100, (name, dfma, dmul, dadd)
+        assert dfma <= 9 * rcp + 8, (name, dfma, rcp)
+    assert len(seen) == 2
+    for k in ("vg_wave_kernel", "oct_wave_kernel", "kd_wave_kernel"):
+        assert any(k in p.split("\n", 1)[0] for p in parts), k
