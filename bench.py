@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--no-extras", action="store_true", help="do not append the short lines of the other configurations at N = 1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--presort", action="store_true", help="experiment: hand the rays over sorted by (origin, direction cell) instead of in generator order")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer stores into rank 0 (default) or NCCL gather after the kernel")
     return ap.parse_args()
 
@@ -369,6 +370,18 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
     # rays of this rank's block, generated straight into page-locked host arrays (the e2e leg shoots from them)
     o = pinned(x, (N, 3), np.float64); d = pinned(x, (N, 3), np.float64)
     rays_from_sources(N, get_sources(cfg), stream=cfg["stream"], first=lo, threads=x.cores, out=(o, d))
+    if getattr(args, "presort", False):
+        a = np.abs(d); face = np.argmax(a, axis=1); sgn = (np.take_along_axis(d, face[:, None], 1)[:, 0] < 0)
+        u = np.take_along_axis(d, ((face + 1) % 3)[:, None], 1)[:, 0] / np.take_along_axis(a, face[:, None], 1)[:, 0]
+        v = np.take_along_axis(d, ((face + 2) % 3)[:, None], 1)[:, 0] / np.take_along_axis(a, face[:, None], 1)[:, 0]
+        ui = np.clip(((u + 1) * 32).astype(np.int64), 0, 63); vi = np.clip(((v + 1) * 32).astype(np.int64), 0, 63)
+        mort = np.zeros(N, np.int64)
+        for b in range(6):
+            mort |= ((ui >> b) & 1) << (2 * b) | ((vi >> b) & 1) << (2 * b + 1)
+        src = (np.arange(N) + lo) % max(1, cfg["nsrc"])
+        key = ((src * 6 + face * 2 + sgn) << 12) | mort
+        perm = np.argsort(key, kind="stable")
+        o[:] = o[perm]; d[:] = d[perm]
     cpu = None
     if x.rank == 0 and do_cpu:
         # the CPU leg runs first, on an otherwise idle host
@@ -528,6 +541,19 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
                 ok = all(np.array_equal(got[k], ref[k]) for k in (("poly_id", "t", "xyz") if cfg["part"] == "Voxel_Grid" else ("poly_id", "t", "xyz", "uv")))
             assert ok, f"{cfg['name']}: GPU results differ from the oracle on the first {n} rays"
             parity = {"rays_compared": n, "bit_exact": True, "fields": "poly_id, t, X_Point" + ("" if cfg["part"] == "Voxel_Grid" else ", u, v")}
+            if x.world > 1 and not chain:
+                # rows that arrived from the OTHER ranks: the first rays of every remote block, re-generated here, against the oracle and
+                # against this rank's own kernel
+                m = 200 if cfg["part"] == "KDTree" else max(2_000, min(50_000, n // 8))    # the KDTree oracle is O(P) per ray
+                checked = 0
+                for r in range(1, x.world):
+                    rlo = shard(cfg, r, x.world)[0]
+                    ro, rd = rays_from_sources(m, get_sources(cfg), stream=cfg["stream"], first=rlo, threads=cores)
+                    want = cpu["part"].Shoot(ro, rd, nthreads=cores)
+                    for k in (("poly_id", "t", "xyz") if cfg["part"] == "Voxel_Grid" else ("poly_id", "t", "xyz", "uv")):
+                        assert np.array_equal(dev_res[k][rlo:rlo + m].cpu().numpy(), want[k]), f"{cfg['name']}: rows delivered by rank {r} differ from the oracle ({k})"
+                    checked += m
+                parity["remote_rows_compared"] = checked
             ref_bytes, ref_avg = algorithmic_bytes(cpu["counters"], cpu["shots"], cfg["part"])
             cpu_line = {"value": cpu["mrays"], "unit": "Mrays/s", "cores": cores, "kind": "port",
                         "sample": f"first {n} rays" + (f" x {order}-order chains" if chain else "") +
@@ -544,11 +570,13 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
         achieved = shots_per_launch * contract_bytes / (kernel_ms * 1e-3) / 1e9
         achieved_gpu = shots_per_launch * gpu_bytes / (kernel_ms * 1e-3) / 1e9
         act = ncu_actual(cfg)
-        kname = {"Voxel_Grid": "vg_wave_kernel", "Octree": "oct_walk_kernel", "KDTree": "kd_walk_kernel"}[cfg["part"]]
+        kname = {"Voxel_Grid": "vg_wave_kernel", "Octree": "oct_wave_kernel", "KDTree": "kd_wave_kernel"}[cfg["part"]]
         roof = {"bound": (act or {}).get("bound", "issue/latency (see actual)"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_reference_bytes": achieved / peak,
                 "frac_flag": "exceeds 1: the culls legitimately skip most of the reference's fetches; read achieved_gpu_counted / actual instead" if achieved / peak > 1.0 else None,
-                "traffic": (act or {}).get("traffic_bytes_per_launch"), "peak_kind": peak_kind, "kernel": kname, "kernel_ms": kernel_ms, "kernel_ms_max_over_ranks": kernel_ms_max,
+                "traffic": ((act or {}).get("traffic_bytes_per_ray") or 0) * shots_per_launch or None,
+                "traffic_note": "ncu dram__bytes_read + dram__bytes_write per Shoot of the committed capture x the Shoots of one launch here" if act else None,
+                "peak_kind": peak_kind, "kernel": kname, "kernel_ms": kernel_ms, "kernel_ms_max_over_ranks": kernel_ms_max,
                 "bytes_per_shoot": contract_bytes, "per_shoot": contract_avg, "counted_by": contract_src,
                 "formula": f"56 + {EVENT_BYTES[cfg['part']]} + {HEADER_BYTES[cfg['part']]}*nodes_or_cells + 4*entries + 128*tests (SURVEY.md 8(d))",
                 "achieved_gpu_counted": achieved_gpu, "frac_gpu_counted": achieved_gpu / peak, "gpu_bytes_per_shoot": gpu_bytes, "gpu_per_shoot": gpu_avg,

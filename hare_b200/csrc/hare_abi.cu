@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "oct_wave.cuh"
 #include "kd_wave.cuh"
+#include "ray_bin.cuh"
 #include "pack.hpp"
 
 using namespace hare;
@@ -1129,12 +1130,12 @@ struct ShootArgs {
 // One CTA of HARE_WAVE_WARPS warps per SM; dynamic shared memory = occupancy bitmap (when it fits) + the pools.
 template <bool CHAIN, bool COUNT, bool OCC_SMEM>
 static int launch_vg_wave2(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
-                           const int32_t* rid, int64_t N, int order, const WalkOut& w, int warps, size_t smem, cudaStream_t st) {
+                           const int32_t* rid, int64_t N, int order, const uint32_t* perm, const WalkOut& w, int warps, size_t smem, cudaStream_t st) {
     auto k = vg_wave_kernel<CHAIN, COUNT, OCC_SMEM, HARE_WAVE_SLOTS, HARE_WAVE_WMAX>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = warps * 32;
     int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms);
-    k<<<(unsigned)blocks, threads, smem, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, w);
+    k<<<(unsigned)blocks, threads, smem, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, perm, w);
     ++g_launches;
     CK(cudaGetLastError());
     return HARE_OK;
@@ -1144,7 +1145,7 @@ static const size_t kSmemMax = 227 * 1024;
 
 template <bool CHAIN>
 static int launch_vg_wave(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
-                          const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+                          const int32_t* rid, int64_t N, int order, const uint32_t* perm, const WalkOut& w, cudaStream_t st) {
     const size_t pool = WavePool<HARE_WAVE_SLOTS>::STRIDE;
     const size_t occ_bytes = ((((size_t)(g.nx + 2) * (g.ny + 2) * (g.nz + 2) + 31) / 32 + 3) & ~(size_t)3) * 4;   // padded grid, see vg_wave.cuh
     // the occupancy bitmap rides in shared memory next to the pools; a larger grid gives up warps for it (down to half),
@@ -1155,21 +1156,21 @@ static int launch_vg_wave(const VGrid& g, const PartDev& d, const double* o, con
     if (!in_smem) warps = HARE_WAVE_WARPS;
     const size_t smem = (in_smem ? occ_bytes : 0) + warps * pool;
     if (w.counters) {
-        if (in_smem) return launch_vg_wave2<CHAIN, true, true>(g, d, o, dd, o1, o2, rid, N, order, w, warps, smem, st);
-        return launch_vg_wave2<CHAIN, true, false>(g, d, o, dd, o1, o2, rid, N, order, w, warps, smem, st);
+        if (in_smem) return launch_vg_wave2<CHAIN, true, true>(g, d, o, dd, o1, o2, rid, N, order, perm, w, warps, smem, st);
+        return launch_vg_wave2<CHAIN, true, false>(g, d, o, dd, o1, o2, rid, N, order, perm, w, warps, smem, st);
     }
-    if (in_smem) return launch_vg_wave2<CHAIN, false, true>(g, d, o, dd, o1, o2, rid, N, order, w, warps, smem, st);
-    return launch_vg_wave2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, w, warps, smem, st);
+    if (in_smem) return launch_vg_wave2<CHAIN, false, true>(g, d, o, dd, o1, o2, rid, N, order, perm, w, warps, smem, st);
+    return launch_vg_wave2<CHAIN, false, false>(g, d, o, dd, o1, o2, rid, N, order, perm, w, warps, smem, st);
 }
 
 template <bool CHAIN>
 static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
-                          const int32_t* rid, int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+                          const int32_t* rid, int64_t N, int order, const uint32_t* perm, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
     // the kernel packs ray numbers into 32 bits and the bounce into 16, and walks the border-padded bitmap (grids below 2^32 padded voxels)
     if (N >= (1LL << 32) || order >= 65536) return fail(HARE_ERR_INVALID, "Voxel_Grid Shoot: at most 2^32-1 rays and 65535 bounces per call");
     if (!g.occp) return fail(HARE_ERR_UNSUPPORTED, "Voxel_Grid Shoot: grid with 2^32 or more padded voxels");
-    return launch_vg_wave<CHAIN>(g, d, o, dd, o1, o2, rid, N, order, w, st);
+    return launch_vg_wave<CHAIN>(g, d, o, dd, o1, o2, rid, N, order, perm, w, st);
 }
 
 #ifndef HARE_OCTW_SLOTS
@@ -1183,7 +1184,7 @@ static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, con
 // The spilled traversal frames live in a scratch area allocated stream-ordered for this launch (24 bytes per slot and level).
 template <bool CHAIN, bool COUNT>
 static int launch_oct_wave2(const OctDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
-                            int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+                            int64_t N, int order, const uint32_t* perm, const WalkOut& w, cudaStream_t st) {
     auto k = oct_wave_kernel<CHAIN, COUNT, HARE_OCTW_SLOTS, HARE_OCTW_NMAX>;
     const size_t smem = (size_t)HARE_OCTW_WARPS * OctPool<HARE_OCTW_SLOTS>::STRIDE;
     static_assert((size_t)HARE_OCTW_WARPS * OctPool<HARE_OCTW_SLOTS>::STRIDE <= 227 * 1024, "ray pools exceed the shared memory of an SM");
@@ -1196,7 +1197,7 @@ static int launch_oct_wave2(const OctDev& t, const PartDev& d, const double* o, 
     void* scratch = nullptr;
     CK(cudaMallocAsync(&scratch, nfr * (sizeof(double2) + sizeof(uint2)), st));
     F.ab = reinterpret_cast<double2*>(scratch); F.cq = reinterpret_cast<uint2*>(F.ab + nfr);
-    k<<<(unsigned)blocks, threads, smem, st>>>(t, F, d.polys, o, dd, o1, o2, N, order, w);
+    k<<<(unsigned)blocks, threads, smem, st>>>(t, F, d.polys, o, dd, o1, o2, N, order, perm, w);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
@@ -1206,11 +1207,11 @@ static int launch_oct_wave2(const OctDev& t, const PartDev& d, const double* o, 
 
 template <bool CHAIN>
 static int launch_oct_walk(const OctDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2,
-                           int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+                           int64_t N, int order, const uint32_t* perm, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
     if (N >= (1LL << 32) || order >= 65536) return fail(HARE_ERR_INVALID, "Octree Shoot: at most 2^32-1 rays and 65535 bounces per call");
-    if (w.counters) return launch_oct_wave2<CHAIN, true>(t, d, o, dd, o1, o2, N, order, w, st);
-    return launch_oct_wave2<CHAIN, false>(t, d, o, dd, o1, o2, N, order, w, st);
+    if (w.counters) return launch_oct_wave2<CHAIN, true>(t, d, o, dd, o1, o2, N, order, perm, w, st);
+    return launch_oct_wave2<CHAIN, false>(t, d, o, dd, o1, o2, N, order, perm, w, st);
 }
 
 #ifndef HARE_KDW_SLOTS
@@ -1224,7 +1225,7 @@ static int launch_oct_walk(const OctDev& t, const PartDev& d, const double* o, c
 // scratch area allocated stream-ordered for this launch (4 bytes per slot and level)
 template <bool CHAIN, bool COUNT>
 static int launch_kd_wave2(const KdDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2, const int32_t* rid,
-                           int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+                           int64_t N, int order, const uint32_t* perm, const WalkOut& w, cudaStream_t st) {
     auto k = kd_wave_kernel<CHAIN, COUNT, HARE_KDW_SLOTS, HARE_KDW_NMAX>;
     const size_t smem = (size_t)HARE_KDW_WARPS * KdPool<HARE_KDW_SLOTS>::STRIDE;
     static_assert((size_t)HARE_KDW_WARPS * KdPool<HARE_KDW_SLOTS>::STRIDE <= 227 * 1024, "ray pools exceed the shared memory of an SM");
@@ -1237,7 +1238,7 @@ static int launch_kd_wave2(const KdDev& t, const PartDev& d, const double* o, co
     void* scratch = nullptr;
     CK(cudaMallocAsync(&scratch, n * sizeof(uint32_t), st));
     S.st = reinterpret_cast<uint32_t*>(scratch);
-    k<<<(unsigned)blocks, threads, smem, st>>>(t, S, d.polys, o, dd, o1, o2, rid, N, order, w);
+    k<<<(unsigned)blocks, threads, smem, st>>>(t, S, d.polys, o, dd, o1, o2, rid, N, order, perm, w);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
@@ -1247,31 +1248,67 @@ static int launch_kd_wave2(const KdDev& t, const PartDev& d, const double* o, co
 
 template <bool CHAIN>
 static int launch_kd_walk(const KdDev& t, const PartDev& d, const double* o, const double* dd, const int32_t* o1, const int32_t* o2, const int32_t* rid,
-                          int64_t N, int order, const WalkOut& w, cudaStream_t st) {
+                          int64_t N, int order, const uint32_t* perm, const WalkOut& w, cudaStream_t st) {
     if (N <= 0) return HARE_OK;
     if (N >= (1LL << 32) || order >= 65536) return fail(HARE_ERR_INVALID, "KDTree Shoot: at most 2^32-1 rays and 65535 bounces per call");
-    if (w.counters) return launch_kd_wave2<CHAIN, true>(t, d, o, dd, o1, o2, rid, N, order, w, st);
-    return launch_kd_wave2<CHAIN, false>(t, d, o, dd, o1, o2, rid, N, order, w, st);
+    if (w.counters) return launch_kd_wave2<CHAIN, true>(t, d, o, dd, o1, o2, rid, N, order, perm, w, st);
+    return launch_kd_wave2<CHAIN, false>(t, d, o, dd, o1, o2, rid, N, order, perm, w, st);
+}
+
+// Coherence pre-pass (ray_bin.cuh): a permutation of the batch grouped by origin cell and direction cell, in `*perm` (stream-ordered
+// allocation, released by the caller after the traversal launch).  Small batches are shot in the caller's order.
+static const int64_t kRayBinMin = 1 << 16;
+static int bin_rays(hare_part_s* p, const PartDev& d, const double* o, const double* dd, int64_t N, cudaStream_t st, uint32_t** perm) {
+    *perm = nullptr;
+    if (N < kRayBinMin) return HARE_OK;
+    const HostTopo& M = p->topo->host;
+    RayBinGeom g;
+    g.ox = (float)M.minmax[0]; g.oy = (float)M.minmax[1]; g.oz = (float)M.minmax[2];
+    g.sx = 4.0f / std::max((float)(M.minmax[3] - M.minmax[0]), 1e-30f); g.sy = 4.0f / std::max((float)(M.minmax[4] - M.minmax[1]), 1e-30f);
+    g.sz = 4.0f / std::max((float)(M.minmax[5] - M.minmax[2]), 1e-30f);
+    g.dirbits = ray_bin_dirbits(N);
+    StreamTemps tmp(st);
+    uint32_t *keys = nullptr, *counts = nullptr, *offs = nullptr, *tiles = nullptr, *pm = nullptr;
+    const int64_t nb = ray_bin_buckets(g.dirbits);
+    CK(tmp.get(&keys, (size_t)N)); CK(tmp.get(&counts, (size_t)nb)); CK(tmp.get(&offs, (size_t)nb + 1));
+    CK(tmp.get(&tiles, (size_t)((nb + HARE_SCAN_TILE - 1) / HARE_SCAN_TILE + 1))); CK(tmp.get(&pm, (size_t)N));
+    CK(cudaMemsetAsync(counts, 0, (size_t)nb * 4, st));
+    const unsigned blocks = (unsigned)std::min<int64_t>((N + 255) / 256, (int64_t)d.sms * 16);
+    ray_bin_count<<<blocks, 256, 0, st>>>(o, dd, N, g, keys, counts);
+    ++g_launches;
+    int r = scan_u32(counts, nb, offs, tiles, st);
+    if (r) return r;
+    ray_bin_scatter<<<blocks, 256, 0, st>>>(keys, N, offs, pm);
+    ++g_launches;
+    CK(cudaGetLastError());
+    tmp.keep(pm);
+    *perm = pm;
+    return HARE_OK;
 }
 
 static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
+    uint32_t* perm = nullptr;
+    int rc = bin_rays(p, d, a.o, a.d, a.N, st, &perm);
+    if (rc) return rc;
+    WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
     switch (p->kind) {
-        case HARE_VOXEL_GRID: {
-            WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
-            return launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
-        }
+        case HARE_VOXEL_GRID:
+            rc = launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, perm, w, st);
+            break;
         case HARE_OCTREE: {
             OctDev t = { (const OctNode*)d.nodes, d.lists, d.cbox, d.gbox, d.pbox, d.nbox, p->oct.depth, p->oct_regular ? 1 : 0 };
-            WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
-            return launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, w, st);
+            rc = launch_oct_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.N, 1, perm, w, st);
+            break;
         }
         case HARE_KDTREE: {
             KdDev t = { (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
-            WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
-            return launch_kd_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, w, st);
+            rc = launch_kd_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, perm, w, st);
+            break;
         }
+        default: rc = fail(HARE_ERR_INVALID, "unknown partition kind");
     }
-    return fail(HARE_ERR_INVALID, "unknown partition kind");
+    if (perm) cudaFreeAsync(perm, st);
+    return rc;
 }
 
 struct ChainArgs {
@@ -1284,17 +1321,17 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
     switch (p->kind) {
         case HARE_VOXEL_GRID: {
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
-            return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
+            return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, nullptr, w, st);
         }
         case HARE_OCTREE: {
             OctDev t = { (const OctNode*)d.nodes, d.lists, d.cbox, d.gbox, d.pbox, d.nbox, p->oct.depth, p->oct_regular ? 1 : 0 };
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
-            return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, w, st);
+            return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, nullptr, w, st);
         }
         case HARE_KDTREE: {
             KdDev t = { (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
-            return launch_kd_walk<true>(t, d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, w, st);
+            return launch_kd_walk<true>(t, d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, nullptr, w, st);
         }
     }
     return fail(HARE_ERR_INVALID, "unknown partition kind");

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(HARE_KDW_WARPS * 32, 1)
 kd_wave_kernel(const KdDev T, const KdStacks S, const PolyRec* __restrict__ polys,
                const double* __restrict__ o, const double* __restrict__ d,
                const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a, const int32_t* __restrict__ rid,
-               long long N, int order, const WalkOut out) {
+               long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, const WalkOut out) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     KdPool<SLOTS> p;
@@ -394,7 +394,7 @@ kd_wave_kernel(const KdDev T, const KdStacks S, const PolyRec* __restrict__ poly
             bool ready = act;
             if (noray) {
                 const long long ray = wave_ray_number(cur + __popc(want & lt), gw, tw);
-                if (ray < N) kdw_fetch<SLOTS>(p, s, ray, o, d, o1a, o2a, rid);
+                if (ray < N) kdw_fetch<SLOTS>(p, s, perm ? (long long)__ldg(perm + ray) : ray, o, d, o1a, o2a, rid);
                 else ready = false;
             }
             cur += __popc(want);

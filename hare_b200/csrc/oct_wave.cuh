@@ -113,6 +113,13 @@ HD uint4 oct_ld_u4(const uint4* q) {
     return *q;
 #endif
 }
+HD uint32_t oct_ld_u32(const uint32_t* q) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(q)); return r;
+#else
+    return *q;
+#endif
+}
 HD float4 oct_ld_f4(const float4* q) {
 #if defined(__CUDA_ARCH__)
     float4 r; asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(q)); return r;
@@ -338,42 +345,61 @@ HD uint32_t octw_node(const OctDev& T, const OctFrames& F, size_t gslot, const O
             fa = ab.x; fb = ab.y; fchild = cq.x; qmask = cq.y;
             continue;
         }
-        const int q = hare_fls(qmask);                                       // pushed near->far, popped far->near
-        qmask &= ~(1u << q);
-        const uint32_t child = fchild + (uint32_t)(q ^ sgn);
-        // the candidate's content box and its node record are fetched together (one round trip); the ray's line missing everything
-        // listed below the child means entering it could change nothing (only a successful test updates closestT or returns)
-        const float4* e = T.nbox + 2 * (size_t)child;
-        const double2* nq = reinterpret_cast<const double2*>(T.nodes + child);
-        const float4 nlo = oct_ld_f4(e), nhi = oct_ld_f4(e + 1);
-        const double2 na = oct_ld_d2(nq), nb = oct_ld_d2(nq + 1), nc = oct_ld_d2(nq + 2);
-        const uint4 m = oct_ld_u4(reinterpret_cast<const uint4*>(nq) + 3);      // first_child, list_off, list_cnt, pad
-        // this was the frame's last octant: unless the child opens a level of its own, the next thing needed is the parent's frame --
-        // fetch it in the same round trip
-        const bool last_q = qmask == 0 && sp > 0;
+        // The next TWO octants of the frame (pushed near->far, popped far->near) are fetched together -- content box and node record
+        // of each, one round trip: more than half of the candidates are rejected, and the one behind a rejected candidate is then
+        // already here.  (If the first one is entered, the second stays in the frame and is fetched again when the walk returns.)
+        const int q0 = hare_fls(qmask);
+        const uint32_t rest = qmask & ~(1u << q0);
+        const int q1 = rest ? hare_fls(rest) : q0;
+        const uint32_t child0 = fchild + (uint32_t)(q0 ^ sgn), child1 = fchild + (uint32_t)(q1 ^ sgn);
+        float4 nlo[2], nhi[2]; double2 na[2], nb[2], nc[2]; uint4 m[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t child = k ? child1 : child0;
+            const float4* e = T.nbox + 2 * (size_t)child;
+            const double2* nq = reinterpret_cast<const double2*>(T.nodes + child);
+            nlo[k] = oct_ld_f4(e); nhi[k] = oct_ld_f4(e + 1);
+            na[k] = oct_ld_d2(nq); nb[k] = oct_ld_d2(nq + 1); nc[k] = oct_ld_d2(nq + 2);
+            m[k] = oct_ld_u4(reinterpret_cast<const uint4*>(nq) + 3);      // first_child, list_off, list_cnt, pad
+        }
+        // when this is the frame's last octant the next thing needed -- unless the child opens a level of its own -- is the parent's
+        // frame: fetch it in the same round trip
+        const bool last_q = rest == 0 && sp > 0;
         double2 pab = make_double2(0.0, 0.0); uint2 pcq = make_uint2(0u, 0u);
         if (last_q) { pab = fab[sp - 1]; pcq = fcq[sp - 1]; }
-        double lo, hi;
-        oct_interval_of(na, nb, nc, ox, oy, oz, ix, iy, iz, lo, hi);
-        const double ca = fmax(lo, fa), cb = fmin(hi, fb);
-        const bool enter = !cull_box(nlo, nhi, fpx, fpy, fpz, fix, fiy, fiz) &&
-                           !(hi < lo || hi < 0 || lo > fb || hi < fa) &&         // push-time filter :268
-                           !(cb < ca || cb < 0) && !(hit && closest <= ca) &&    // pop-time prunes :207-211
-                           !((int)m.x < 0 && m.z == 0);                          // (an empty leaf changes nothing)
-        if (enter && (int)m.x >= 0) {
+        bool enter = false; int k = 0;
+        double ca = 0, cb = 0;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            if (!enter && (kk == 0 || rest != 0)) {
+                // the ray's line missing everything listed below the child means entering it could change nothing (only a successful
+                // test updates closestT or returns)
+                double lo, hi;
+                oct_interval_of(na[kk], nb[kk], nc[kk], ox, oy, oz, ix, iy, iz, lo, hi);
+                ca = fmax(lo, fa); cb = fmin(hi, fb);
+                enter = !cull_box(nlo[kk], nhi[kk], fpx, fpy, fpz, fix, fiy, fiz) &&
+                        !(hi < lo || hi < 0 || lo > fb || hi < fa) &&         // push-time filter :268
+                        !(cb < ca || cb < 0) && !(hit && closest <= ca) &&    // pop-time prunes :207-211
+                        !((int)m[kk].x < 0 && m[kk].z == 0);                  // (an empty leaf changes nothing)
+                k = kk;
+                qmask = kk ? (rest & ~(1u << q1)) : rest;                     // this octant is consumed, entered or not
+            }
+        }
+        const uint4 mm = k ? m[1] : m[0];
+        if (enter && (int)mm.x >= 0) {
             // an internal node opens a level; the current top goes to the spill area -- unless it is exhausted: nothing would ever
             // be read from it again
             c.cell();
             if (qmask != 0) { fab[sp] = make_double2(fa, fb); fcq[sp] = make_uint2(fchild, qmask); ++sp; }
-            fchild = m.x; qmask = oct_perm_mask(m.w, sgn); fa = ca; fb = cb;
-            if (T.regular) qmask &= oct_child_filter(na, nb, nc, ox, oy, oz, ix, iy, iz, fa, fb, sgn);
+            fchild = mm.x; qmask = oct_perm_mask(mm.w, sgn); fa = ca; fb = cb;
+            if (T.regular) qmask &= oct_child_filter(k ? na[1] : na[0], k ? nb[1] : nb[0], k ? nc[1] : nc[0], ox, oy, oz, ix, iy, iz, fa, fb, sgn);
             continue;
         }
-        if (last_q) { --sp; fa = pab.x; fb = pab.y; fchild = pcq.x; qmask = pcq.y; }
+        if (last_q) { --sp; fa = pab.x; fb = pab.y; fchild = pcq.x; qmask = pcq.y; }     // (rest == 0: the frame is exhausted either way)
         if (enter) {                                                         // a leaf with a list
             c.cell();
-            lpos = m.y; lend = m.y + m.z;
-            p.U(OU_CIDX, s) = m.w; p.D(OD_CA, s) = ca;
+            lpos = mm.y; lend = mm.y + mm.z;
+            p.U(OU_CIDX, s) = mm.w; p.D(OD_CA, s) = ca;
             break;
         }
     }
@@ -397,30 +423,19 @@ HD uint32_t octw_group(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COU
     const float fpx = p.F(OF_PX, s), fpy = p.F(OF_PY, s), fpz = p.F(OF_PZ, s);
     const uint32_t left = lend - lpos, nch = (left + 7u) / 8u < 8u ? (left + 7u) / 8u : 8u;
     uint32_t em = 0;
-    // the group box and the first four chunk boxes are fetched together (one round trip); most groups of a long leaf list are
-    // nowhere near the ray and end here
+    // the group box and its (up to) eight chunk boxes are fetched together: one round trip (the registers are there: 16 warps per SM)
     const float4* ge = T.gbox + 2 * (size_t)(cidx >> 3);
     const float4 glo = oct_ld_f4(ge), ghi = oct_ld_f4(ge + 1);
-    float4 lo[4], hi[4];
+    float4 lo[8], hi[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
         const float4* e = T.cbox + 2 * (size_t)(cidx + (j < (int)nch ? j : 0));
         lo[j] = oct_ld_f4(e); hi[j] = oct_ld_f4(e + 1);
     }
     if (!cull_box(glo, ghi, fpx, fpy, fpz, fix, fiy, fiz)) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 8; ++j)
             em |= (j < (int)nch && !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz)) ? (1u << j) : 0u;
-        if (nch > 4u) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4* e = T.cbox + 2 * (size_t)(cidx + (4 + j < (int)nch ? 4 + j : 0));
-                lo[j] = oct_ld_f4(e); hi[j] = oct_ld_f4(e + 1);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                em |= (4 + j < (int)nch && !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz)) ? (1u << (4 + j)) : 0u;
-        }
     }
     const uint32_t adv = left < 64u ? left : 64u;
     p.U(OU_CPOS, s) = lpos; p.U(OU_CIDX, s) = cidx + nch;
@@ -450,21 +465,18 @@ HD uint32_t octw_cull(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COUN
     uint32_t bm = 0, first_id = 0;
     // poly_origin skip (:218); a polygon already tested for this ray (it sits in several leaves) cannot change anything:
     // its t is not below closestT any more, so neither the update nor the early return fires
+    uint32_t ids[8]; float4 lo[8], hi[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        uint32_t ids[4]; float4 lo[4], hi[4];
+    for (int j = 0; j < 8; ++j) ids[j] = oct_ld_u32(T.lists + base + (j < (int)n ? j : 0));                                   // round trip 1: the ids
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ids[j] = hare_ldg(T.lists + base + (4 * h + j < (int)n ? 4 * h + j : 0));
+    for (int j = 0; j < 8; ++j) { const float4* e = T.pbox + 2 * (size_t)ids[j]; lo[j] = oct_ld_f4(e); hi[j] = oct_ld_f4(e + 1); }   // round trip 2: their boxes
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float4* e = T.pbox + 2 * (size_t)ids[j]; lo[j] = oct_ld_f4(e); hi[j] = oct_ld_f4(e + 1); }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t i = ids[j];
-            const bool keep = (4 * h + j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
-                              !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz);
-            first_id = (keep && bm == 0) ? i : first_id;
-            bm |= keep ? (1u << (4 * h + j)) : 0u;
-        }
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t i = ids[j];
+        const bool keep = (j < (int)n) && !((int)i == or1 || (int)i == or2 || i == last || (int)i == pid) &&
+                          !cull_box(lo[j], hi[j], fpx, fpy, fpz, fix, fiy, fiz);
+        first_id = (keep && bm == 0) ? i : first_id;
+        bm |= keep ? (1u << j) : 0u;
     }
     // the lowest survivor's id rides in the slot, so that the test phase fetches its record without re-reading the list
     masks = (masks & 0xffu) | (emask << 8) | (bm << 16) | ((uint32_t)kc << OM_KC_SHIFT) | (bm ? (uint32_t)OM_PEND : 0u);
@@ -516,7 +528,7 @@ __global__ void __launch_bounds__(HARE_OCTW_WARPS * 32, 1)
 oct_wave_kernel(const OctDev T, const OctFrames F, const PolyRec* __restrict__ polys,
                 const double* __restrict__ o, const double* __restrict__ d,
                 const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a,
-                long long N, int order, const WalkOut out) {
+                long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, const WalkOut out) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     OctPool<SLOTS> p;
@@ -582,7 +594,7 @@ oct_wave_kernel(const OctDev T, const OctFrames F, const PolyRec* __restrict__ p
             bool ready = act;
             if (noray) {
                 const long long ray = wave_ray_number(cur + __popc(want & lt), gw, tw);
-                if (ray < N) octw_fetch<SLOTS>(p, s, ray, o, d, o1a, o2a);
+                if (ray < N) octw_fetch<SLOTS>(p, s, perm ? (long long)__ldg(perm + ray) : ray, o, d, o1a, o2a);
                 else ready = false;
             }
             cur += __popc(want);

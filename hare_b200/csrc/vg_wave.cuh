@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(HARE_WAVE_WARPS * 32, 1)
 vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                const double* __restrict__ o, const double* __restrict__ d,
                const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a, const int32_t* __restrict__ rid,
-               long long N, int order, const WalkOut out) {
+               long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, const WalkOut out) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_occ = reinterpret_cast<uint32_t*>(s_raw);
     uint32_t occ_words = 0;
@@ -442,7 +442,7 @@ vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
             bool ready = act;
             if (noray) {
                 const long long ray = wave_ray_number(cur + __popc(want & lt), gw, tw);
-                if (ray < N) wave_fetch<SLOTS>(p, s, ray, o, d, o1a, o2a, rid);
+                if (ray < N) wave_fetch<SLOTS>(p, s, perm ? (long long)__ldg(perm + ray) : ray, o, d, o1a, o2a, rid);
                 else ready = false;
             }
             cur += __popc(want);

@@ -187,3 +187,14 @@ extern "C" void emu_cull_box(const double* verts, const int32_t* vcount, const d
 
 // ---- the DDA step selection exactly as the kernel uses it (quirk Q4 unit test) ----------
 extern "C" int emu_dda_axis(double tx, double ty, double tz) { return dda_axis(tx, ty, tz); }
+
+// ---- the coherence pre-pass key (ray_bin.cuh), for its range / degenerate-input test ----------
+#include "../../hare_b200/csrc/ray_bin.cuh"
+extern "C" void emu_ray_bin_keys(const double* o, const double* d, int64_t n, const double* minmax, uint32_t* keys, uint32_t* buckets) {
+    RayBinGeom g;
+    g.ox = (float)minmax[0]; g.oy = (float)minmax[1]; g.oz = (float)minmax[2];
+    g.sx = 4.0f / (float)(minmax[3] - minmax[0]); g.sy = 4.0f / (float)(minmax[4] - minmax[1]); g.sz = 4.0f / (float)(minmax[5] - minmax[2]);
+    g.dirbits = ray_bin_dirbits(n);
+    for (int64_t i = 0; i < n; ++i) keys[i] = ray_bin_key(o + 3 * i, d + 3 * i, g);
+    *buckets = ray_bin_buckets(g.dirbits);
+}

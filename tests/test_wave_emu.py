@@ -136,3 +136,36 @@ def test_wave_degenerate_rays(hall):
         got = wave_emu.run(ta, gi, csr, o, d, slots=slots, wmax=wmax, n_warps=1)
         for k in ("poly_id", "t", "xyz", "o"):
             assert np.array_equal(got[k], ref[k]), k
+
+
+def test_ray_bin_keys_stay_in_range_and_group_coherent_rays():
+    """ray_bin.cuh: the coherence pre-pass scatters rays through per-bucket counters, so a key outside [0, buckets) would be an
+    out-of-bounds atomic on the device -- whatever the ray holds (zero / NaN / Inf / huge components).  And the key does its job:
+    rays from one source into a narrow cone share a bucket or neighbouring ones."""
+    import ctypes as C
+    from tests.emu import wave_emu
+    L = wave_emu.lib()
+    rng = np.random.default_rng(5)
+    n = 200_000
+    o = rng.uniform(-50, 80, (n, 3)); d = rng.normal(size=(n, 3))
+    special = np.array([0.0, -0.0, np.nan, np.inf, -np.inf, 1e308, -1e308, 1e-320, 1.0, -1.0])
+    o[:5000] = rng.choice(special, (5000, 3)); d[5000:10000] = rng.choice(special, (5000, 3))
+    d[10000:11000] = 0.0
+    mm = np.array([0.0, 0.0, 0.0, 30.0, 40.0, 17.0])
+    keys = np.zeros(n, np.uint32); nb = C.c_uint32()
+    L.emu_ray_bin_keys(o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_int64(n), mm.ctypes.data_as(C.c_void_p),
+                       keys.ctypes.data_as(C.c_void_p), C.byref(nb))
+    assert keys.max() < nb.value
+    assert len(np.unique(keys[11000:])) > 10_000                      # isotropic rays from everywhere spread over the buckets
+    # a 0.5-degree cone from one point: a handful of buckets
+    axis = np.array([0.3, -0.5, 0.81]); axis /= np.linalg.norm(axis)
+    dd = axis + 0.004 * rng.normal(size=(5000, 3)); oo = np.tile([15.0, 6.0, 5.0], (5000, 1))
+    k2 = np.zeros(5000, np.uint32)
+    L.emu_ray_bin_keys(oo.ctypes.data_as(C.c_void_p), np.ascontiguousarray(dd).ctypes.data_as(C.c_void_p), C.c_int64(5000), mm.ctypes.data_as(C.c_void_p),
+                       k2.ctypes.data_as(C.c_void_p), C.byref(nb))
+    assert len(np.unique(k2)) <= 16
+    for n2 in (1, 70_000, 3_000_000):          # the key always fits the bucket count chosen for the batch size
+        kk = np.zeros(min(n2, n), np.uint32)
+        L.emu_ray_bin_keys(o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_int64(len(kk)), mm.ctypes.data_as(C.c_void_p),
+                           kk.ctypes.data_as(C.c_void_p), C.byref(nb))
+        assert kk.max() < nb.value
