@@ -347,6 +347,54 @@ def free_pins(x):
     x.pins = []
 
 
+class SharedEvents:
+    """t, xyz, poly_id, uv for `n_total` rays in POSIX shared memory created by rank 0; rank r works on rows [lo, lo + n)."""
+    FIELDS = (("t", (), np.float64), ("xyz", (3,), np.float64), ("poly_id", (), np.int32), ("uv", (2,), np.float64))
+
+    def __init__(self, x, n_total, lo, n):
+        from multiprocessing import shared_memory
+        self.x, self.n_total, self.lo, self.n = x, n_total, lo, n
+        names = [None] * len(self.FIELDS)
+        self.seg = []
+        if x.rank == 0:
+            for k, (name, tail, dt) in enumerate(self.FIELDS):
+                nbytes = n_total * int(np.prod(tail, dtype=np.int64)) * np.dtype(dt).itemsize
+                sm = shared_memory.SharedMemory(create=True, size=max(nbytes, 8))
+                self.seg.append(sm); names[k] = sm.name
+        x.dist.broadcast_object_list(names, src=0)
+        if x.rank != 0:
+            self.seg = [shared_memory.SharedMemory(name=nm) for nm in names]
+        self.arr = [np.ndarray((n_total,) + tail, dtype=dt, buffer=sm.buf) for sm, (name, tail, dt) in zip(self.seg, self.FIELDS)]
+        self.registered = True
+        self._reg = []
+        for a in self.arr:
+            row = a[lo:lo + n]
+            if row.nbytes == 0:
+                continue
+            rc = x.L.hare_host_register(C.c_void_p(row.ctypes.data), row.nbytes)
+            if rc != 0:
+                self.registered = False
+            else:
+                self._reg.append(row.ctypes.data)
+
+    def rows(self):
+        return tuple(a[self.lo:self.lo + self.n] for a in self.arr)
+
+    def whole(self):
+        return self.arr
+
+    def close(self):
+        for p in self._reg:
+            self.x.L.hare_host_unregister(C.c_void_p(p))
+        self.arr = None
+        for sm in self.seg:
+            sm.close()
+        self.x.dist.barrier()
+        if self.x.rank == 0:
+            for sm in self.seg:
+                sm.unlink()
+
+
 def reduce_max_sum(x, ms, count):
     torch, dist = x.torch, x.dist
     tms = torch.tensor([ms], dtype=torch.float64, device=x.dev); sh = torch.tensor([count], dtype=torch.int64, device=x.dev)
@@ -491,7 +539,14 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
                 return tot.value
             h2d, d2h, api = 48, 52, "hare_reflect_chain (host buffers, page-locked)"
         else:
-            t_h = pinned(x, (N,), np.float64); xyz_h = pinned(x, (N, 3), np.float64); pid_h = pinned(x, (N,), np.int32); uv_h = pinned(x, (N, 2), np.float64)
+            shm = None
+            if x.world > 1:
+                # one host copy of the whole batch's events, shared by the ranks (POSIX shared memory created by rank 0): every rank
+                # page-locks its own rows (hare_host_register) and hare_shoot_batch writes them there -- the gather ends in ONE host array
+                shm = SharedEvents(x, total_rays(cfg, x.world), lo, N)
+                t_h, xyz_h, pid_h, uv_h = shm.rows()
+            else:
+                t_h = pinned(x, (N,), np.float64); xyz_h = pinned(x, (N, 3), np.float64); pid_h = pinned(x, (N,), np.int32); uv_h = pinned(x, (N, 2), np.float64)
 
             def step_host():
                 check(L.hare_shoot_batch(part._h, o.ctypes.data, d.ctypes.data, None, None, None, N, t_h.ctypes.data, xyz_h.ctypes.data,
@@ -510,12 +565,22 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
         dt, e_all = reduce_max_sum(x, dt, e_shots)
         e2e = {"value": e_all / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(total_rays(cfg, x.world) * h2d),
                "d2h_bytes_per_step": int(total_rays(cfg, x.world) * d2h), "steps": e_steps, "api": api,
-               "note": "every rank shoots its block from and into its own page-locked host arrays" if x.world > 1 else None}
+               "note": (("every rank shoots its block from its own page-locked ray arrays into its rows of ONE shared host array "
+                         "(POSIX shared memory owned by rank 0, rows page-locked with hare_host_register: " + ("yes" if shm.registered else "no, pageable") + ")")
+                        if (x.world > 1 and not chain) else ("every rank shoots its own chains from and into its own page-locked host arrays" if x.world > 1 else None))}
         if chain:
             assert np.array_equal(ns_h, dev_res["nshots"]), "host-buffer and device-resident legs disagree"
         elif x.world == 1:
             assert np.array_equal(pid_h, dev_res["poly_id"].cpu().numpy()) and np.array_equal(t_h, dev_res["t"].cpu().numpy()), \
                 "host-buffer and device-resident legs disagree"
+        else:
+            dist.barrier()
+            if x.rank == 0:      # the shared host array holds every rank's rows: compare all of it with what the device leg delivered to rank 0
+                full = shm.whole()
+                assert np.array_equal(full[2], dev_res["poly_id"].cpu().numpy()) and np.array_equal(full[0], dev_res["t"].cpu().numpy()), \
+                    "host-buffer (shared host array) and device-resident legs disagree"
+            dist.barrier()
+            shm.close()
 
     line = None
     if x.rank == 0:

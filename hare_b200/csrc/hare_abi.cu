@@ -112,23 +112,27 @@ struct hare_topo_s {
     std::vector<float> pbox;         // host copy of the padded FP32 bounding boxes (P x 6: lo xyz, hi xyz), see cull_box()
 };
 
+// streams (and staging sets) per device of the host-buffer entry points: with three, the H2D copy of chunk k+1, the kernel of chunk k and
+// the D2H copy of chunk k-1 overlap (two leave the copy engines idle while the second kernel runs)
+static const int kStreams = 3;
+
 struct PartDev {
     int dev = 0, sms = 0;
-    cudaStream_t stream[2] = { nullptr, nullptr };
+    cudaStream_t stream[kStreams] = {};
     const PolyRec* polys = nullptr;
     // voxel grid
     uint2* cells = nullptr; uint32_t* cell_poly = nullptr; uint32_t* occ = nullptr; uint32_t* occp = nullptr; uint32_t* cell_offset = nullptr;
     float4* list_box = nullptr;   // per list entry: padded FP32 bounding box + polygon id (VGrid::lbox; vg_wave.cuh's cull)
     // trees
-    void* nodes = nullptr; uint32_t* lists = nullptr;
+    void* nodes = nullptr; uint32_t* lists = nullptr; KdNodeC* kd_hot = nullptr; KdWide* kd_wide = nullptr;
     double* ref_box = nullptr; float4* cbox = nullptr; float4* gbox = nullptr; float4* tbox = nullptr; float4* nbox = nullptr; float4* pbox = nullptr;   // octree chunk boxes; per tree-list entry boxes (+ polygon id); octree node content boxes
     // staging (per stream), sized for `cap` rays
     int64_t cap = 0;
-    double *s_o[2] = {}, *s_d[2] = {}, *s_t[2] = {}, *s_xyz[2] = {}, *s_uv[2] = {}, *s_om[2] = {};
-    int32_t *s_o1[2] = {}, *s_o2[2] = {}, *s_rid[2] = {}, *s_pid[2] = {};
+    double *s_o[kStreams] = {}, *s_d[kStreams] = {}, *s_t[kStreams] = {}, *s_xyz[kStreams] = {}, *s_uv[kStreams] = {}, *s_om[kStreams] = {};
+    int32_t *s_o1[kStreams] = {}, *s_o2[kStreams] = {}, *s_rid[kStreams] = {}, *s_pid[kStreams] = {};
     // chain staging
     int64_t ccap = 0, celems = 0;
-    int32_t* c_evpid[2] = {}; double* c_evt[2] = {}; int32_t* c_ns[2] = {};
+    int32_t* c_evpid[kStreams] = {}; double* c_evt[kStreams] = {}; int32_t* c_ns[kStreams] = {};
     unsigned long long* counters = nullptr;   // 4 counters + total_shots
     size_t bytes = 0;
 };
@@ -147,20 +151,20 @@ struct hare_part_s {
 
 static void free_partdev(PartDev& d) {
     cudaSetDevice(d.dev);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStreams; ++s) {
         cudaFree(d.s_o[s]); cudaFree(d.s_d[s]); cudaFree(d.s_t[s]); cudaFree(d.s_xyz[s]); cudaFree(d.s_uv[s]); cudaFree(d.s_om[s]);
         cudaFree(d.s_o1[s]); cudaFree(d.s_o2[s]); cudaFree(d.s_rid[s]); cudaFree(d.s_pid[s]);
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
-    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occp); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.lists); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.pbox); cudaFree(d.ref_box); cudaFree(d.counters);
+    cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occp); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.kd_hot); cudaFree(d.kd_wide); cudaFree(d.lists); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.pbox); cudaFree(d.ref_box); cudaFree(d.counters);
 }
 
 static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
     d.dev = dev; d.polys = polys; d.sms = dev_info(dev).sms;
     CK(cudaSetDevice(dev));
     pool_keep(dev);
-    for (int s = 0; s < 2; ++s) CK(cudaStreamCreateWithFlags(&d.stream[s], cudaStreamNonBlocking));
+    for (int s = 0; s < kStreams; ++s) CK(cudaStreamCreateWithFlags(&d.stream[s], cudaStreamNonBlocking));
     CK(dmalloc(&d.counters, 8));
     CK(cudaMemset(d.counters, 0, 8 * sizeof(unsigned long long)));
     return HARE_OK;
@@ -169,7 +173,7 @@ static int init_partdev(PartDev& d, int dev, const PolyRec* polys) {
 static int ensure_staging(PartDev& d, int64_t n) {
     if (n <= d.cap) return HARE_OK;
     CK(cudaSetDevice(d.dev));
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStreams; ++s) {
         cudaFree(d.s_o[s]); cudaFree(d.s_d[s]); cudaFree(d.s_t[s]); cudaFree(d.s_xyz[s]); cudaFree(d.s_uv[s]); cudaFree(d.s_om[s]);
         cudaFree(d.s_o1[s]); cudaFree(d.s_o2[s]); cudaFree(d.s_rid[s]); cudaFree(d.s_pid[s]);
         CK(dmalloc(&d.s_o[s], 3 * n)); CK(dmalloc(&d.s_d[s], 3 * n)); CK(dmalloc(&d.s_t[s], n)); CK(dmalloc(&d.s_xyz[s], 3 * n));
@@ -183,7 +187,7 @@ static int ensure_staging(PartDev& d, int64_t n) {
 static int ensure_chain_staging(PartDev& d, int64_t n, int order) {
     if (n * order <= d.celems && n <= d.ccap) return HARE_OK;
     CK(cudaSetDevice(d.dev));
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStreams; ++s) {
         cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
         CK(dmalloc(&d.c_evpid[s], (size_t)n * order)); CK(dmalloc(&d.c_evt[s], (size_t)n * order)); CK(dmalloc(&d.c_ns[s], n));
     }
@@ -911,19 +915,24 @@ static int kd_to_device(hare_part_s* p) {
     const KdTree& t = p->kd;
     const size_t N = t.axis.size();
     if (kd_depth(t) + 2 > HARE_KD_MAXSTACK) return fail(HARE_ERR_UNSUPPORTED, "kd-tree deeper than HARE_KD_MAXSTACK allows");
-    std::vector<KdNode> nodes;
+    std::vector<KdNode> nodes; std::vector<KdNodeC> hot;
     pack_kdtree(t, p->topo->host, nodes);   // content-tightened node boxes (pack.hpp)
+    pack_kdtree_hot(nodes, hot);            // FP32 padded boxes + links
+    std::vector<KdWide> wide;
+    pack_kdtree_wide(nodes, hot, wide);     // the walk's 128-byte records: a node's grandchildren
     for (PartDev& d : p->dev) {
         CK(cudaSetDevice(d.dev));
         KdNode* dn = nullptr;
         CK(dmalloc(&dn, N)); d.nodes = dn;
+        CK(dmalloc(&d.kd_hot, N)); CK(cudaMemcpy(d.kd_hot, hot.data(), N * sizeof(KdNodeC), cudaMemcpyHostToDevice));
+        CK(dmalloc(&d.kd_wide, N)); CK(cudaMemcpy(d.kd_wide, wide.data(), N * sizeof(KdWide), cudaMemcpyHostToDevice));
         CK(dmalloc(&d.lists, t.polys.size() + 8));
         CK(dmalloc(&d.ref_box, 6 * N));
         CK(cudaMemcpy(dn, nodes.data(), N * sizeof(KdNode), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d.ref_box, t.box.data(), 6 * N * sizeof(double), cudaMemcpyHostToDevice));   // the reference's boxes: tie rule only
         if (!t.polys.empty()) CK(cudaMemcpy(d.lists, t.polys.data(), t.polys.size() * 4, cudaMemcpyHostToDevice));
         { int r = tree_entry_boxes(d, t.polys.size(), p->topo->host.P, false); if (r) return r; }
-        d.bytes = N * (sizeof(KdNode) + 48) + t.polys.size() * 36;
+        d.bytes = N * (sizeof(KdNode) + sizeof(KdNodeC) + sizeof(KdWide) + 48) + t.polys.size() * 36;
     }
     return HARE_OK;
 }
@@ -1233,11 +1242,11 @@ static int launch_kd_wave2(const KdDev& t, const PartDev& d, const double* o, co
     const int threads = HARE_KDW_WARPS * 32;
     const int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms);
     KdStacks S;
-    S.depth = t.depth + 2;
+    S.depth = 3 * (t.depth / 2 + 2) + 4;     // a record pushes at most three entries, one record per two levels
     const size_t n = (size_t)blocks * HARE_KDW_WARPS * HARE_KDW_SLOTS * (size_t)S.depth;
     void* scratch = nullptr;
-    CK(cudaMallocAsync(&scratch, n * sizeof(uint32_t), st));
-    S.st = reinterpret_cast<uint32_t*>(scratch);
+    CK(cudaMallocAsync(&scratch, n * sizeof(uint4), st));
+    S.st = reinterpret_cast<uint4*>(scratch);
     k<<<(unsigned)blocks, threads, smem, st>>>(t, S, d.polys, o, dd, o1, o2, rid, N, order, perm, w);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -1301,7 +1310,7 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
             break;
         }
         case HARE_KDTREE: {
-            KdDev t = { (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
+            KdDev t = { d.kd_wide, d.kd_hot, (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
             rc = launch_kd_walk<false>(t, d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, perm, w, st);
             break;
         }
@@ -1329,7 +1338,7 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, nullptr, w, st);
         }
         case HARE_KDTREE: {
-            KdDev t = { (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
+            KdDev t = { d.kd_wide, d.kd_hot, (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
             WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
             return launch_kd_walk<true>(t, d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, nullptr, w, st);
         }
@@ -1337,7 +1346,10 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
     return fail(HARE_ERR_INVALID, "unknown partition kind");
 }
 
-static const int64_t kChunk = 1 << 20;   // rays per pipelined chunk of the host-buffer entry points
+static const int64_t kChunk = 1 << 20;   // chains per pipelined chunk of hare_reflect_chain
+// Rays per pipelined chunk of hare_shoot_batch: an eighth of the device's share (so that copies and kernels of neighbouring chunks
+// overlap on the two streams), between 2^18 (a chunk should fill the persistent kernel's ~150 k ray slots more than once) and 2^22
+static int64_t shoot_chunk(int64_t n_device) { return std::min<int64_t>(1 << 22, std::max<int64_t>(1 << 18, (n_device + 7) / 8)); }
 
 // CUDA call inside a lambda that reports through an int status (the caller drains every stream before returning it)
 #define CKS(call)                                                                                  \
@@ -1350,13 +1362,13 @@ static const int64_t kChunk = 1 << 20;   // rays per pipelined chunk of the host
         }                                                                                          \
     } while (0)
 
-// Wait for both streams of every device: called on EVERY exit path of the host-buffer entry points, so that no asynchronous copy
+// Wait for every stream of every device: called on EVERY exit path of the host-buffer entry points, so that no asynchronous copy
 // into the caller's arrays is still in flight when the call returns (the caller may free them right after an error).
 static int drain_streams(hare_part_s* p) {
     int rc = HARE_OK;
     for (PartDev& dv : p->dev) {
         if (cudaSetDevice(dv.dev) != cudaSuccess) { rc = HARE_ERR_CUDA; continue; }
-        for (int s = 0; s < 2; ++s) if (cudaStreamSynchronize(dv.stream[s]) != cudaSuccess) rc = HARE_ERR_CUDA;
+        for (int s = 0; s < kStreams; ++s) if (cudaStreamSynchronize(dv.stream[s]) != cudaSuccess) rc = HARE_ERR_CUDA;
     }
     return rc;
 }
@@ -1375,14 +1387,15 @@ extern "C" int hare_shoot_batch(hare_part_t p, const double* o, const double* d,
             PartDev& dv = p->dev[g];
             const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
             if (r1 <= r0) continue;
-            int rc = ensure_staging(dv, std::min<int64_t>(kChunk, r1 - r0));
+            const int64_t chunk = shoot_chunk(r1 - r0);
+            int rc = ensure_staging(dv, std::min<int64_t>(chunk, r1 - r0));
             if (rc) return rc;
             CKS(cudaSetDevice(dv.dev));
             if (counters) CKS(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
             if (counters) CKS(cudaStreamSynchronize(dv.stream[0]));
             int s = 0;
-            for (int64_t c0 = r0; c0 < r1; c0 += kChunk, s ^= 1) {
-                const int64_t n = std::min<int64_t>(kChunk, r1 - c0);
+            for (int64_t c0 = r0; c0 < r1; c0 += chunk, s = (s + 1) % kStreams) {
+                const int64_t n = std::min<int64_t>(chunk, r1 - c0);
                 cudaStream_t st = dv.stream[s];
                 CKS(cudaMemcpyAsync(dv.s_o[s], o + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
                 CKS(cudaMemcpyAsync(dv.s_d[s], d + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
@@ -1455,7 +1468,7 @@ extern "C" int hare_reflect_chain(hare_part_t p, const double* o, const double* 
             CKS(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
             CKS(cudaStreamSynchronize(dv.stream[0]));
             int s = 0;
-            for (int64_t c0 = r0; c0 < r1; c0 += chunk, s ^= 1) {
+            for (int64_t c0 = r0; c0 < r1; c0 += chunk, s = (s + 1) % kStreams) {
                 const int64_t n = std::min<int64_t>(chunk, r1 - c0);
                 cudaStream_t st = dv.stream[s];
                 CKS(cudaMemcpyAsync(dv.s_o[s], o + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));

@@ -1,5 +1,5 @@
 // kd_wave.cuh -- K4 (and K5 on a KDTree): Hare's KDTree.Shoot (KDTree.cs:198-361) under the per-warp WAVEFRONT scheduler of
-// vg_wave.cuh / oct_wave.cuh: ray state in shared-memory pools (149 bytes per slot), one converged phase per trip.
+// vg_wave.cuh / oct_wave.cuh: ray state in shared-memory pools (133 bytes per slot), one converged phase per trip.
 //
 // The reference pushes both children of every node (:355-356): it visits every leaf and keeps the strict minimum of t, i.e.
 // the global closest hit.  Here the walk goes near child first and drops a subtree when the ray's parameter interval inside
@@ -24,7 +24,7 @@ namespace hare {
 enum : uint32_t { KP_SF = 0, KP_N = 1, KP_C = 2, KP_T = 3, KP_DONE = 4, KP_COUNT = 4 };
 // slot flags: NORAY | fin(2) | hit | blind | bmask(8) << 8 | bounce(16) << 16
 enum : uint32_t { KFL_NORAY = 1u, KFL_FIN_SHIFT = 1, KFL_FIN_MASK = 3u << 1, KFL_HIT = 8u, KFL_BLIND = 16u, KFL_BMASK_SHIFT = 8, KFL_BMASK_MASK = 255u << 8, KFL_BOUNCE_SHIFT = 16 };
-enum { KD_OX, KD_OY, KD_OZ, KD_DX, KD_DY, KD_DZ, KD_IX, KD_IY, KD_IZ, KD_CLOSEST, KD_EU, KD_EV, KD_COUNT };
+enum { KD_OX, KD_OY, KD_OZ, KD_DX, KD_DY, KD_DZ, KD_CLOSEST, KD_EU, KD_EV, KD_TE /* ray parameter of the FP32 frame point */, KD_COUNT };
 enum { KU_FLAGS, KU_RAY, KU_PID, KU_OR1, KU_OR2, KU_LAST, KU_LPOS, KU_LEND, KU_CUR, KU_SP, KU_COUNT };
 enum { KF_PX, KF_PY, KF_PZ, KF_COUNT };
 #define HARE_KD_NONE 0xffffffffu
@@ -47,7 +47,7 @@ struct KdPool {
     HD float& F(int f, int s) const { return f32[f * SLOTS + s]; }
 };
 
-struct KdStacks { uint32_t* st; int depth; };   // per slot: `depth` pending node indices
+struct KdStacks { uint4* st; int depth; };   // per slot: `depth` pending entries (x, y, entry parameter as float bits, -): internal y = ~0, x = node; leaf x = list offset, y = count
 
 HD uint32_t kd_tag(uint32_t fl, uint32_t lpos, uint32_t lend) {
     if (fl & KFL_FIN_MASK) return KP_SF;
@@ -197,58 +197,111 @@ HD void kdw_fetch(const KdPool<SLOTS>& p, int s, long long ray, const double* __
 }
 
 template <bool COUNT, int SLOTS>
-HD uint32_t kdw_setup(const KdPool<SLOTS>& p, int s, CntT<COUNT>&) {
+HD uint32_t kdw_setup(const KdDev& T, const KdPool<SLOTS>& p, int s, CntT<COUNT>&) {
     uint32_t fl = p.U(KU_FLAGS, s) & (KFL_BLIND | (0xffffu << KFL_BOUNCE_SHIFT));
-    // reciprocals used only by the conservative prune (their rounding is far inside HARE_KD_PAD)
-    p.D(KD_IX, s) = 1.0 / p.D(KD_DX, s); p.D(KD_IY, s) = 1.0 / p.D(KD_DY, s); p.D(KD_IZ, s) = 1.0 / p.D(KD_DZ, s);
+    const double ox = p.D(KD_OX, s), oy = p.D(KD_OY, s), oz = p.D(KD_OZ, s), dx = p.D(KD_DX, s), dy = p.D(KD_DY, s), dz = p.D(KD_DZ, s);
     p.D(KD_CLOSEST, s) = DBL_MAX; p.D(KD_EU, s) = 0; p.D(KD_EV, s) = 0;
     p.U(KU_PID, s) = 0xffffffffu; p.U(KU_LAST, s) = 0xffffffffu;
     p.U(KU_LPOS, s) = 0; p.U(KU_LEND, s) = 0; p.U(KU_CUR, s) = 0; p.U(KU_SP, s) = 0;
+    // Frame of the FP32 walk: the point where the ray enters the root's box (the exact vertex bounds; the origin itself when it starts
+    // inside), formed in FP64 -- a ray shot from far outside the model must not lose the millimetres the padding allows to FP32.  A ray
+    // that misses the root box hits nothing.
+    const double2* q = reinterpret_cast<const double2*>(T.nodes);
+    double te = 0.0;
+    const bool in = kd_box_reachable_hd(hare_ldg(q), hare_ldg(q + 1), hare_ldg(q + 2), ox, oy, oz, dx, dy, dz, 1.0 / dx, 1.0 / dy, 1.0 / dz, DBL_MAX, te);
+    p.D(KD_TE, s) = te;
+    const float fix = cull_rcp((float)dx), fiy = cull_rcp((float)dy), fiz = cull_rcp((float)dz);
+    p.F(KF_PX, s) = (float)fma(dx, te, ox) * fix; p.F(KF_PY, s) = (float)fma(dy, te, oy) * fiy; p.F(KF_PZ, s) = (float)fma(dz, te, oz) * fiz;
     // Ray_ID == 0 against a fresh mailbox: every polygon is rejected (KDTree.cs:58-66, 224-229)
-    if (fl & KFL_BLIND) fl |= FIN_MISS << KFL_FIN_SHIFT;
+    if ((fl & KFL_BLIND) || !in) fl |= FIN_MISS << KFL_FIN_SHIFT;
+    uint32_t lpos = 0, lend = 0;
+    {   // a tree that is a single leaf has no KdWide record: its list is scanned directly
+        const uint32_t rb = hare_ldg(&T.hot[0].b);
+        if ((rb & 3u) == 3u) {
+            p.U(KU_CUR, s) = HARE_KD_NONE;
+            if (!(fl & KFL_FIN_MASK)) { lpos = hare_ldg(&T.hot[0].a); lend = lpos + (rb >> 2); }
+        }
+    }
+    p.U(KU_LPOS, s) = lpos; p.U(KU_LEND, s) = lend;
     p.U(KU_FLAGS, s) = fl;
-    return kd_tag(fl, 0, 0);
+    return kd_tag(fl, lpos, lend);
 }
 
+// closest - te as a float that is not below the exact difference (the prune compares a box's entry parameter against it)
+HD float kd_upper_float(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = f > 0.0f ? f * 1.0000002f : f * 0.9999998f;      // one step up (x is finite and far from the float range's ends)
+    return f;
+}
+
+// ---- N: descend until a reachable leaf with a non-empty list is found, the stack runs empty, or N_MAX records were looked at.
+// One KdWide record = a node's (up to four) grandchildren = two levels of the reference's binary tree per dependent fetch.
+// FP32 on padded boxes: slab test of the ray's line against each entry's box in the ray's frame (as cull_box), then the ray's own
+// extent: a box wholly behind the ray's start (tf < -te) or wholly beyond the closest hit (tn > closest - te) holds no polygon that
+// could still improve or tie the result.  Boxes are padded by >= 1e-3 m in space while the FP32 evaluation is good to ~1e-5 m, so the
+// computed interval contains every hit parameter inside the unpadded box: nothing reachable is ever skipped.  The reference's
+// first/second rule (KDTree.cs:249-353) only fixes the order in which its exhaustive walk meets the leaves -- the result is the
+// global minimum of t either way --, so the nearest reachable entry goes first and the others wait on the stack WITH their entry
+// parameter: an entry that a closer hit has overtaken in the meantime is dropped at pop time without touching memory.
 template <bool COUNT, int SLOTS, int N_MAX>
 HD uint32_t kdw_node(const KdDev& T, const KdStacks& S, size_t gslot, const KdPool<SLOTS>& p, int s, CntT<COUNT>& c) {
     uint32_t fl = p.U(KU_FLAGS, s);
-    const double ox = p.D(KD_OX, s), oy = p.D(KD_OY, s), oz = p.D(KD_OZ, s), dx = p.D(KD_DX, s), dy = p.D(KD_DY, s), dz = p.D(KD_DZ, s);
-    const double ix = p.D(KD_IX, s), iy = p.D(KD_IY, s), iz = p.D(KD_IZ, s);
-    const double closest = p.D(KD_CLOSEST, s);
+    const float fdx = (float)p.D(KD_DX, s), fdy = (float)p.D(KD_DY, s), fdz = (float)p.D(KD_DZ, s);
+    const float fix = cull_rcp(fdx), fiy = cull_rcp(fdy), fiz = cull_rcp(fdz);
+    const float fpx = p.F(KF_PX, s), fpy = p.F(KF_PY, s), fpz = p.F(KF_PZ, s);
+    const double closest = p.D(KD_CLOSEST, s), te = p.D(KD_TE, s);
+    const float crel = (fl & KFL_HIT) ? kd_upper_float(closest - te) : 3.0e38f;
+    const float tback = -kd_upper_float(te);                      // the ray's own start, seen from the frame point
     uint32_t cur = p.U(KU_CUR, s), sp = p.U(KU_SP, s);
-    uint32_t* st = S.st + gslot * (size_t)S.depth;
+    uint4* st = S.st + gslot * (size_t)S.depth;
     uint32_t fin = FIN_RUN, lpos = 0, lend = 0;
 #pragma unroll 1
     for (int guard = 0; guard < N_MAX; ++guard) {
         if (cur == HARE_KD_NONE) {
             if (sp == 0) { fin = (fl & KFL_HIT) ? FIN_HIT : FIN_MISS; break; }
-            cur = st[--sp];
+            const uint4 e = st[--sp];
+            if (hare_u2f(e.z) > crel) continue;                   // overtaken by a closer hit since it was pushed
+            if (e.y != 0xffffffffu) { lpos = e.x; lend = e.x + e.y; break; }
+            cur = e.x;
         }
-        const double2* q = reinterpret_cast<const double2*>(T.nodes + cur);
-        const double2 a = hare_ldg(q), b = hare_ldg(q + 1), cc = hare_ldg(q + 2), dd = hare_ldg(q + 3);
-        double t_in;
-        if (!kd_box_reachable_hd(a, b, cc, ox, oy, oz, dx, dy, dz, ix, iy, iz, closest, t_in)) { cur = HARE_KD_NONE; continue; }
-        c.cell();
-        const int left = kd_lo32(dd.y), axis = kd_hi32(dd.y);
-        if (left < 0) {
-            const uint32_t off = (uint32_t)kd_lo32(dd.x), cnt = (uint32_t)kd_hi32(dd.x);
-            cur = HARE_KD_NONE;
-            if (cnt) {
-                lpos = off; lend = off + cnt;
-                // cull_box frame: the ray point where the leaf's box is entered, divided by d
-                const float fix = cull_rcp((float)dx), fiy = cull_rcp((float)dy), fiz = cull_rcp((float)dz);
-                p.F(KF_PX, s) = (float)fma(dx, t_in, ox) * fix; p.F(KF_PY, s) = (float)fma(dy, t_in, oy) * fiy; p.F(KF_PZ, s) = (float)fma(dz, t_in, oz) * fiz;
-                break;
+        const float4* q = reinterpret_cast<const float4*>(T.wide + cur);
+        float4 lo[4], hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { lo[k] = hare_ldg(q + 2 * k); hi[k] = hare_ldg(q + 2 * k + 1); }     // mnx mny mnz mxx | mxy mxz a b
+        float tn[4]; bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ax = fmaf(lo[k].x, fix, -fpx), bx = fmaf(lo[k].w, fix, -fpx);
+            const float ay = fmaf(lo[k].y, fiy, -fpy), by = fmaf(hi[k].x, fiy, -fpy);
+            const float az = fmaf(lo[k].z, fiz, -fpz), bz = fmaf(hi[k].y, fiz, -fpz);
+            tn[k] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            const uint32_t b = hare_f2u(hi[k].w);
+            ok[k] = !(tn[k] > tf || tf < tback || tn[k] > crel) && (b & 3u) != 2u && !((b & 3u) == 3u && (b >> 2) == 0u);
+            if (ok[k]) c.cell();
+        }
+        // the nearest reachable entry is taken now, the others are pushed farthest first
+        int best = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (ok[k] && (best < 0 || tn[k] < tn[best])) best = k;
+        cur = HARE_KD_NONE;
+        if (best < 0) continue;
+#pragma unroll
+        for (int round = 0; round < 3; ++round) {
+            int far = -1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (ok[k] && k != best && (far < 0 || tn[k] > tn[far])) far = k;
+            if (far >= 0) {
+                ok[far] = false;
+                const uint32_t b = hare_f2u(hi[far].w);
+                const bool leaf = (b & 3u) == 3u;
+                if ((int)sp < S.depth) st[sp++] = make_uint4(leaf ? hare_f2u(hi[far].z) : (b >> 2), leaf ? (b >> 2) : 0xffffffffu, hare_f2u(tn[far]), 0u);
             }
-        } else {
-            // The reference's first/second rule (KDTree.cs:249-353) only fixes the order in which its exhaustive walk meets the
-            // leaves; the result is the global minimum of t either way.  Here the child on the origin's side goes first so that
-            // the prune can cut the far side as early as possible.
-            const double oa = axis == 0 ? ox : (axis == 1 ? oy : oz);
-            const bool right_first = oa > dd.x;
-            if ((int)sp < S.depth) st[sp++] = (uint32_t)(right_first ? left : left + 1);
-            cur = (uint32_t)(right_first ? left + 1 : left);
+        }
+        {
+            const uint32_t b = hare_f2u(hi[best].w);
+            if ((b & 3u) == 3u) { lpos = hare_f2u(hi[best].z); lend = lpos + (b >> 2); break; }
+            cur = b >> 2;
         }
     }
     fl |= fin << KFL_FIN_SHIFT;
@@ -398,7 +451,7 @@ kd_wave_kernel(const KdDev T, const KdStacks S, const PolyRec* __restrict__ poly
                 else ready = false;
             }
             cur += __popc(want);
-            if (ready) nt = kdw_setup<COUNT, SLOTS>(p, s, c);
+            if (ready) nt = kdw_setup<COUNT, SLOTS>(T, p, s, c);
         }
         if (act) p.tag[s] = (uint8_t)nt;
         __syncwarp();

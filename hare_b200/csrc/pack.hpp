@@ -149,6 +149,51 @@ inline void pack_kdtree(const KdTree& t, const HostTopo& M, std::vector<KdNode>&
     }
 }
 
+// the walk's 32-byte FP32 records (KdNodeC) from the packed FP64 ones: box rounded outwards and padded like a polygon box
+inline void pack_kdtree_hot(const std::vector<KdNode>& nodes, std::vector<KdNodeC>& hot) {
+    hot.resize(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const KdNode& n = nodes[i];
+        const double mn[3] = { n.mnx, n.mny, n.mnz }, mx[3] = { n.mxx, n.mxy, n.mxz };
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            if (!(mn[a] <= mx[a])) { lo[a] = INFINITY; hi[a] = -INFINITY; continue; }     // empty content: never reachable
+            const double pad = hare_box_pad(mn[a], mx[a]);
+            lo[a] = (float)(mn[a] - pad); while ((double)lo[a] > mn[a] - pad) lo[a] = std::nextafter(lo[a], -INFINITY);
+            hi[a] = (float)(mx[a] + pad); while ((double)hi[a] < mx[a] + pad) hi[a] = std::nextafter(hi[a], INFINITY);
+        }
+        KdNodeC& h = hot[i];
+        h.mnx = lo[0]; h.mny = lo[1]; h.mnz = lo[2]; h.mxx = hi[0]; h.mxy = hi[1]; h.mxz = hi[2];
+        if (n.left >= 0) { const float sp = (float)n.split; std::memcpy(&h.a, &sp, 4); h.b = ((uint32_t)n.left << 2) | (uint32_t)(n.axis & 3); }
+        else { uint64_t bits; std::memcpy(&bits, &n.split, 8); h.a = (uint32_t)(bits & 0xffffffffull); h.b = ((uint32_t)(bits >> 32) << 2) | 3u; }
+    }
+}
+
+// KdWide records: for every internal node its grandchildren (a child that is a leaf stands for itself)
+inline void pack_kdtree_wide(const std::vector<KdNode>& nodes, const std::vector<KdNodeC>& hot, std::vector<KdWide>& wide) {
+    const size_t N = nodes.size();
+    wide.resize(N);
+    KdNodeC none = {};
+    none.mnx = none.mny = none.mnz = INFINITY; none.mxx = none.mxy = none.mxz = -INFINITY; none.a = 0; none.b = 2u;
+    for (size_t i = 0; i < N; ++i) {
+        for (int k = 0; k < 4; ++k) wide[i].e[k] = none;
+        if (nodes[i].left < 0) continue;
+        int n = 0;
+        for (int c = 0; c < 2; ++c) {
+            const size_t ch = (size_t)nodes[i].left + c;
+            const size_t sub[2] = { ch, ch };
+            size_t list[2]; int m = 1; list[0] = ch;
+            if (nodes[ch].left >= 0) { list[0] = (size_t)nodes[ch].left; list[1] = list[0] + 1; m = 2; }
+            (void)sub;
+            for (int q = 0; q < m; ++q) {
+                KdNodeC e = hot[list[q]];
+                if (nodes[list[q]].left >= 0) { e.a = 0; e.b = ((uint32_t)list[q] << 2); }     // internal: link to its own record
+                wide[i].e[n++] = e;                                                             // leaf: hot[] already holds (offset, count << 2 | 3)
+            }
+        }
+    }
+}
+
 inline int kd_depth_of(const KdTree& t) {
     const size_t N = t.axis.size();
     std::vector<int> dep(N, 0);

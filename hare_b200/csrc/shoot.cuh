@@ -171,7 +171,22 @@ struct alignas(64) KdNode {
     int32_t axis;             // 0,1,2
 };
 
+// Hot form of a kd node, 32 B: the walk only needs a conservative box, a split to order the children by and the child / list
+// links.  FP32, box rounded outwards and padded (hare_box_pad): the pruned walk may visit nodes in any order and may only skip a
+// subtree that provably holds no hit at t <= closest -- exactness lives in the polygon tests and in the tie rule, which read the
+// FP64 records (KdNode, ref_box).
+//   internal: a = split as float bits, b = left << 2 | axis (0..2)        leaf: a = list offset, b = list count << 2 | 3
+struct alignas(32) KdNodeC { float mnx, mny, mnz, mxx, mxy, mxz; uint32_t a, b; };
+
+// The walk's record: a kd node together with its (up to four) grandchildren -- the two levels below it collapsed into one 128-byte
+// fetch, so that a ray pays one dependent memory round trip per TWO levels of the reference's binary tree.  Entry k: padded box,
+//   b & 3 == 0: internal node, b >> 2 = its index (and that of its own KdWide record);  b & 3 == 3: leaf, a = list offset, b >> 2 = count;
+//   b & 3 == 2: unused entry.  Indexed by the binary node's index (only internal nodes have a record).
+struct alignas(128) KdWide { KdNodeC e[4]; };
+
 struct KdDev {
+    const KdWide* __restrict__ wide;  // the walk's records (kd_wave.cuh)
+    const KdNodeC* __restrict__ hot;  // FP32 form of single nodes (root look-up)
     const KdNode* __restrict__ nodes;
     const uint32_t* __restrict__ lists;
     const float4* __restrict__ lbox;  // per leaf-list entry: its polygon's padded box, polygon id in lo.w (cull_box)

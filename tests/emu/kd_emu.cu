@@ -17,8 +17,9 @@ template <bool CHAIN, int SLOTS, int N_MAX>
 void run(const KdDev& T, const PolyRec* polys, const double* o, const double* d, const int32_t* o1a, const int32_t* o2a, const int32_t* rid,
          long long N, int order, const WalkOut& out, int tw, Stats& st, unsigned long long* counters) {
     std::vector<unsigned char> mem(KdPool<SLOTS>::STRIDE + 64);
-    std::vector<uint32_t> stk((size_t)SLOTS * (T.depth + 2));
-    KdStacks S = { stk.data(), T.depth + 2 };
+    const int sdepth = 3 * (T.depth / 2 + 2) + 4;
+    std::vector<uint4> stk((size_t)SLOTS * sdepth);
+    KdStacks S = { stk.data(), sdepth };
     CntT<true> c;
     unsigned long long total = 0;
     for (long long gw = 0; gw < tw; ++gw) {
@@ -53,7 +54,7 @@ void run(const KdDev& T, const PolyRec* polys, const double* o, const double* d,
                         if (ray < N) kdw_fetch<SLOTS>(p, sel[l], ray, o, d, o1a, o2a, rid);
                         else ready = false;
                     }
-                    nt[l] = ready ? kdw_setup<true, SLOTS>(p, sel[l], c) : (uint32_t)KP_DONE;
+                    nt[l] = ready ? kdw_setup<true, SLOTS>(T, p, sel[l], c) : (uint32_t)KP_DONE;
                 }
                 cur += rank;
             }
@@ -87,8 +88,11 @@ extern "C" int kd_emu(const double* verts, const double* normals, const int32_t*
     tr.box.assign(node_box, node_box + 6 * n_nodes); tr.split.assign(split, split + n_nodes); tr.axis.assign(axis, axis + n_nodes);
     tr.left.assign(left, left + n_nodes); tr.list_off.assign(list_off, list_off + n_nodes); tr.list_cnt.assign(list_cnt, list_cnt + n_nodes);
     tr.polys.assign(lists, lists + n_list);
-    std::vector<KdNode> nodes;
+    std::vector<KdNode> nodes; std::vector<KdNodeC> hot;
     pack_kdtree(tr, M, nodes);
+    pack_kdtree_hot(nodes, hot);
+    std::vector<KdWide> wide;
+    pack_kdtree_wide(nodes, hot, wide);
     std::vector<float4> lbox(2 * (size_t)n_list + 16);
     for (int64_t k = 0; k < n_list; ++k) {
         float b[6];
@@ -96,7 +100,7 @@ extern "C" int kd_emu(const double* verts, const double* normals, const int32_t*
         lbox[2 * k] = make_float4(b[0], b[1], b[2], hare_u2f(lists[k])); lbox[2 * k + 1] = make_float4(b[3], b[4], b[5], 0.f);
     }
     KdDev T = {};
-    T.nodes = nodes.data(); T.lists = tr.polys.data(); T.lbox = lbox.data(); T.depth = kd_depth_of(tr); T.ref_box = tr.box.data();
+    T.wide = wide.data(); T.hot = hot.data(); T.nodes = nodes.data(); T.lists = tr.polys.data(); T.lbox = lbox.data(); T.depth = kd_depth_of(tr); T.ref_box = tr.box.data();
     // what-if for the tie test's teeth: evaluate the reference's first/second rule on the content-tightened device boxes (the round-1 bug)
     std::vector<double> tightbox;
     if (tie_rule_on_tight_boxes) {

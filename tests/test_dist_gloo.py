@@ -78,3 +78,49 @@ def test_shard_range_covers_everything():
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
             assert max(b[1] - b[0] for b in blocks) - min(b[1] - b[0] for b in blocks) <= 1
+
+
+def _worker_shared(rank, world, port, n, q):
+    """bench.py's strong-scaling plumbing: block shards of ONE global batch (bench.shard), every rank writing its X_Event rows at its
+    own offset into arrays owned by rank 0 (bench.SharedEvents: the host-side twin of dist.PeerResults, which needs GPUs)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    import hare_b200 as hb
+    from hare_b200.harness import meshes, rays_from_sources
+    from oracle import hare_oracle as ho
+    cfg = dict(bench.CONFIGS["C3"], name="C3", rays=n)
+    lo, hi = bench.shard(cfg, rank, world)
+    assert bench.total_rays(cfg, world) == n
+    x = bench.Ctx(); x.rank, x.world, x.dist, x.L = rank, world, dist, hb.lib()
+    mesh = meshes.hall("tiny")
+    part = ho.Octree(ho.Topology.from_mesh(mesh), 3, 4)
+    o, d = rays_from_sources(hi - lo, meshes.sources(8), stream=3, first=lo)       # every rank generates only its own block
+    r = part.Shoot(o, d)
+    ev = bench.SharedEvents(x, n, lo, hi - lo)
+    t, xyz, pid, uv = ev.rows()
+    t[:] = r["t"]; xyz[:] = r["xyz"]; pid[:] = r["poly_id"]; uv[:] = r["uv"]
+    dist.barrier()
+    if rank == 0:
+        og, dg = rays_from_sources(n, meshes.sources(8), stream=3)
+        ref = part.Shoot(og, dg)
+        T, X, P, U = ev.whole()
+        q.put(bool(np.array_equal(P, ref["poly_id"]) and np.array_equal(T, ref["t"]) and np.array_equal(X, ref["xyz"]) and np.array_equal(U, ref["uv"])))
+    dist.barrier()
+    ev.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_rows_land_in_one_shared_array():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shared, args=(r, 2, port, 5001, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
