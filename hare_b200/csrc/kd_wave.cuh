@@ -268,41 +268,37 @@ HD uint32_t kdw_node(const KdDev& T, const KdStacks& S, size_t gslot, const KdPo
         float4 lo[4], hi[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { lo[k] = hare_ldg(q + 2 * k); hi[k] = hare_ldg(q + 2 * k + 1); }     // mnx mny mnz mxx | mxy mxz a b
-        float tn[4]; bool ok[4];
+        // per entry: sort key (entry parameter, or +huge when it cannot matter) and the stack code (x, y)
+        float key[4]; uint32_t ex[4], ey[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float ax = fmaf(lo[k].x, fix, -fpx), bx = fmaf(lo[k].w, fix, -fpx);
             const float ay = fmaf(lo[k].y, fiy, -fpy), by = fmaf(hi[k].x, fiy, -fpy);
             const float az = fmaf(lo[k].z, fiz, -fpz), bz = fmaf(hi[k].y, fiz, -fpz);
-            tn[k] = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             const uint32_t b = hare_f2u(hi[k].w);
-            ok[k] = !(tn[k] > tf || tf < tback || tn[k] > crel) && (b & 3u) != 2u && !((b & 3u) == 3u && (b >> 2) == 0u);
-            if (ok[k]) c.cell();
+            const bool leaf = (b & 3u) == 3u;
+            const bool ok = !(tn > tf || tf < tback || tn > crel) && (b & 3u) != 2u && !(leaf && (b >> 2) == 0u);
+            if (ok) c.cell();
+            key[k] = ok ? fminf(tn, 1.0e38f) : 3.0e38f;
+            ex[k] = leaf ? hare_f2u(hi[k].z) : (b >> 2);
+            ey[k] = leaf ? (b >> 2) : 0xffffffffu;
         }
+        // sorting network (5 compare-exchanges, registers only): key[0] <= key[1] <= key[2] <= key[3]
+#define HARE_KD_CX(i, j) { const bool sw = key[j] < key[i]; const float tk = sw ? key[j] : key[i]; key[j] = sw ? key[i] : key[j]; key[i] = tk; \
+                           const uint32_t tx = sw ? ex[j] : ex[i]; ex[j] = sw ? ex[i] : ex[j]; ex[i] = tx; \
+                           const uint32_t ty = sw ? ey[j] : ey[i]; ey[j] = sw ? ey[i] : ey[j]; ey[i] = ty; }
+        HARE_KD_CX(0, 1) HARE_KD_CX(2, 3) HARE_KD_CX(0, 2) HARE_KD_CX(1, 3) HARE_KD_CX(1, 2)
+#undef HARE_KD_CX
         // the nearest reachable entry is taken now, the others are pushed farthest first
-        int best = -1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (ok[k] && (best < 0 || tn[k] < tn[best])) best = k;
         cur = HARE_KD_NONE;
-        if (best < 0) continue;
+        if (!(key[0] < 2.0e38f)) continue;
 #pragma unroll
-        for (int round = 0; round < 3; ++round) {
-            int far = -1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (ok[k] && k != best && (far < 0 || tn[k] > tn[far])) far = k;
-            if (far >= 0) {
-                ok[far] = false;
-                const uint32_t b = hare_f2u(hi[far].w);
-                const bool leaf = (b & 3u) == 3u;
-                if ((int)sp < S.depth) st[sp++] = make_uint4(leaf ? hare_f2u(hi[far].z) : (b >> 2), leaf ? (b >> 2) : 0xffffffffu, hare_f2u(tn[far]), 0u);
-            }
-        }
-        {
-            const uint32_t b = hare_f2u(hi[best].w);
-            if ((b & 3u) == 3u) { lpos = hare_f2u(hi[best].z); lend = lpos + (b >> 2); break; }
-            cur = b >> 2;
-        }
+        for (int k = 3; k >= 1; --k)
+            if (key[k] < 2.0e38f && (int)sp < S.depth) st[sp++] = make_uint4(ex[k], ey[k], hare_f2u(key[k]), 0u);
+        if (ey[0] != 0xffffffffu) { lpos = ex[0]; lend = ex[0] + ey[0]; break; }
+        cur = ex[0];
     }
     fl |= fin << KFL_FIN_SHIFT;
     p.U(KU_FLAGS, s) = fl; p.U(KU_CUR, s) = cur; p.U(KU_SP, s) = sp;
