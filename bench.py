@@ -67,7 +67,9 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="do not append the short lines of the other configurations at N = 1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--presort", action="store_true", help="experiment: hand the rays over sorted by (origin, direction cell) instead of in generator order")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer stores into rank 0 (default) or NCCL gather after the kernel")
+    ap.add_argument("--gather", default="peer", choices=["peer", "peer-store", "nccl"],
+                    help="N > 1: 'peer' = each rank's batch in 8 chunks, chunk k's rows copied into rank 0's buffers over NVLink while chunk k+1 traverses "
+                         "(default); 'peer-store' = the kernels store their rows into rank 0's buffers directly; 'nccl' = NCCL gather after the kernel")
     return ap.parse_args()
 
 
@@ -450,7 +452,7 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
         outs = [fin_o, fin_d, nshots]
     else:
         ntot = total_rays(cfg, x.world)
-        if x.world > 1 and gather == "peer":
+        if x.world > 1 and gather in ("peer", "peer-store"):
             try:
                 peer = hd.PeerResults(ntot, x.local, dst=0)
             except Exception as e:   # no peer access between these devices: NCCL gather after the kernel instead
@@ -461,7 +463,8 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
                 peer = None
-        if peer is not None:
+        direct = peer is not None and (gather == "peer-store" or x.rank == 0)      # rank 0's own rows never need a copy
+        if direct:
             pt, pxyz, ppid, puv = peer.out_ptrs(lo)
         else:
             t_d = torch.empty(N, dtype=torch.float64, device=x.dev); xyz_d = torch.empty((N, 3), dtype=torch.float64, device=x.dev)
@@ -470,21 +473,42 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
             outs = [pid_d, t_d, xyz_d, uv_d]
     sizes = [shard(cfg, r, x.world)[1] - shard(cfg, r, x.world)[0] for r in range(x.world)]
     gathered = None
+    # 'peer': the batch goes through the kernel in K chunks; chunk k's rows travel to rank 0 on a second stream (large coalesced peer
+    # copies over NVLink) while chunk k + 1 is traversed -- the step ends when the last chunk's copy has landed
+    chunks = 8 if (peer is not None and gather == "peer" and not chain) else 1
+    bounds = [(N * k) // chunks for k in range(chunks + 1)]
+    copy_stream = torch.cuda.Stream(device=x.dev) if (chunks > 1 and x.rank != 0) else None
+    if copy_stream is not None:
+        remote = {k: peer.arrays[k].torch() for k in ("poly_id", "t", "xyz", "uv")}
+        local = {"poly_id": pid_d, "t": t_d, "xyz": xyz_d, "uv": uv_d}
 
     def kernel():
         stream = cur_stream(torch)
         if chain:
             check(L.hare_reflect_chain_device(part._h, o_d.data_ptr(), d_d.data_ptr(), N, order, None, None, fin_o.data_ptr(), fin_d.data_ptr(),
                                               nshots.data_ptr(), total.data_ptr(), None, C.c_void_p(stream)), "hare_reflect_chain_device")
-        else:
-            check(L.hare_shoot_batch_device(part._h, o_d.data_ptr(), d_d.data_ptr(), None, None, None, N, C.c_void_p(pt), C.c_void_p(pxyz),
-                                            C.c_void_p(ppid), C.c_void_p(puv), None, None, C.c_void_p(stream)), "hare_shoot_batch_device")
+            return
+        for k in range(chunks):
+            a, b = bounds[k], bounds[k + 1]
+            if b <= a:
+                continue
+            check(L.hare_shoot_batch_device(part._h, o_d.data_ptr() + 24 * a, d_d.data_ptr() + 24 * a, None, None, None, b - a,
+                                            C.c_void_p(pt + 8 * a), C.c_void_p(pxyz + 24 * a), C.c_void_p(ppid + 4 * a), C.c_void_p(puv + 16 * a),
+                                            None, None, C.c_void_p(stream)), "hare_shoot_batch_device")
+            if copy_stream is not None:
+                ev_k = torch.cuda.Event(); ev_k.record()
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev_k)
+                    for name in ("poly_id", "t", "xyz", "uv"):
+                        remote[name][lo + a:lo + b].copy_(local[name][a:b], non_blocking=True)
 
     def deliver():
         nonlocal gathered
         if x.world == 1:
             return
         if peer is not None:
+            if copy_stream is not None:
+                torch.cuda.current_stream().wait_stream(copy_stream)
             peer.fence()
         else:
             gathered = [hd.gather_rows(a, 0, sizes) for a in outs]
@@ -651,7 +675,10 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
                 "data": "synthetic", "config": workload_config(cfg, mesh, x.world, {"build_seconds_gpu": build_s}),
                 "roofline": roof, "cpu_baseline": cpu_line, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "shots_per_step": shots_all // steps, "parity": parity,
-                "result_delivery": None if x.world == 1 else ("peer stores from the traversal kernel into rank 0 (CUDA IPC over NVLink) + 4-byte NCCL fence" if peer is not None else "NCCL gather after the kernel")}
+                "result_delivery": None if x.world == 1 else (
+                    ("8 chunks per rank; chunk k's rows copied into rank 0's buffers (CUDA IPC mapping, NVLink) on a second stream while chunk k+1 traverses; 4-byte NCCL fence"
+                     if gather == "peer" else "peer stores from the traversal kernel straight into rank 0's buffers (CUDA IPC over NVLink) + 4-byte NCCL fence")
+                    if peer is not None else "NCCL gather after the kernel")}
     if peer is not None:
         dev_res = None
         peer.close()

@@ -4,7 +4,7 @@
 // The first-generation kernel tied one ray to one thread: every trip the warp ran its S / N / C / T phases with
 // whichever lanes happened to be in each -- ncu showed 6 of 32 lanes per issued instruction and 6.9 long-scoreboard
 // stall cycles per issue (profiles/r1_ncu_octree_oct4_summary.txt).  Here the ray state lives in SHARED MEMORY: every
-// warp owns a pool of SLOTS ray slots (structure-of-arrays, 185 bytes per slot) with a one-byte phase tag each; per trip
+// warp owns a pool of SLOTS ray slots (structure-of-arrays, 169 bytes per slot) with a one-byte phase tag each; per trip
 // the warp counts its slots per phase, picks the fullest phase, compacts up to 32 of its slots onto the lanes and runs
 // that ONE phase converged on 32 different rays.
 //
@@ -40,8 +40,10 @@ enum : uint32_t {
 // OU_MASKS: qmask (octants of the top frame still to pop) | emask << 8 (surviving chunks of the current group) | bmask << 16 (surviving entries of the
 // current chunk) | kc << 24 (which chunk of the group that is) | OM_PEND (OU_PEND holds the id of the lowest surviving entry)
 enum : uint32_t { OM_KC_SHIFT = 24, OM_KC_MASK = 7u << 24, OM_PEND = 1u << 27 };
-enum { OD_OX, OD_OY, OD_OZ, OD_DX, OD_DY, OD_DZ, OD_IX, OD_IY, OD_IZ, OD_CLOSEST, OD_EU, OD_EV, OD_CA, OD_FA, OD_FB, OD_COUNT };
-enum { OU_FLAGS, OU_RAY, OU_PID, OU_OR1, OU_OR2, OU_LAST, OU_LPOS, OU_LEND, OU_CIDX, OU_CPOS, OU_PEND, OU_FCHILD, OU_MASKS, OU_COUNT };
+enum { OD_OX, OD_OY, OD_OZ, OD_DX, OD_DY, OD_DZ, OD_IX, OD_IY, OD_IZ, OD_CLOSEST, OD_CA, OD_FA, OD_FB, OD_COUNT };
+// OU_LAST doubles as the id of the lowest surviving entry between C and T (OM_PEND): T makes that polygon the last one tested anyway.
+// The event's u, v are not kept in the slot: T writes them to the output row whenever closestT improves (the last write is the winner's).
+enum { OU_FLAGS, OU_RAY, OU_PID, OU_OR1, OU_OR2, OU_LAST, OU_LPOS, OU_LEND, OU_CIDX, OU_CPOS, OU_FCHILD, OU_MASKS, OU_COUNT };
 enum { OF_PX, OF_PY, OF_PZ, OF_COUNT };   // cull_box frame point, already divided by d (FP32)
 
 template <int SLOTS>
@@ -238,7 +240,7 @@ HD void octw_finish(const PolyRec* __restrict__ polys, const OctPool<SLOTS>& p, 
         out.pid[ray] = h ? pid : -1;
         if (out.t) out.t[ray] = h ? closest : 0.0;
         if (out.xyz) { out.xyz[3 * ray] = h ? bx : 0.0; out.xyz[3 * ray + 1] = h ? by : 0.0; out.xyz[3 * ray + 2] = h ? bz : 0.0; }
-        if (out.uv) { out.uv[2 * ray] = h ? p.D(OD_EU, s) : 0.0; out.uv[2 * ray + 1] = h ? p.D(OD_EV, s) : 0.0; }
+        if (out.uv && !h) { out.uv[2 * ray] = 0.0; out.uv[2 * ray + 1] = 0.0; }     // a hit's u, v were written by the test that found it
         if (out.omoved) { out.omoved[3 * ray] = R.x; out.omoved[3 * ray + 1] = R.y; out.omoved[3 * ray + 2] = R.z; }   // the Octree never moves a ray
         fl |= OFL_NORAY;
     }
@@ -291,7 +293,7 @@ HD uint32_t octw_setup(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COU
     if (!(isfinite(R.x) && isfinite(R.y) && isfinite(R.z) && isfinite(R.dx) && isfinite(R.dy) && isfinite(R.dz))) fin = FIN_MISS;
     const int sgn = (R.dx >= 0 ? 0 : 4) | (R.dy >= 0 ? 0 : 2) | (R.dz >= 0 ? 0 : 1);   // ComputeTraversalOrder :286-306: order[q] = q ^ sgn
     fl |= (uint32_t)sgn << OFL_SGN_SHIFT;
-    p.D(OD_CLOSEST, s) = DBL_MAX; p.D(OD_EU, s) = 0; p.D(OD_EV, s) = 0;
+    p.D(OD_CLOSEST, s) = DBL_MAX;
     p.U(OU_PID, s) = 0xffffffffu; p.U(OU_LAST, s) = 0xffffffffu;
     uint32_t lpos = 0, lend = 0, masks = 0;
     if (fin == FIN_RUN) {
@@ -480,19 +482,20 @@ HD uint32_t octw_cull(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COUN
     }
     // the lowest survivor's id rides in the slot, so that the test phase fetches its record without re-reading the list
     masks = (masks & 0xffu) | (emask << 8) | (bm << 16) | ((uint32_t)kc << OM_KC_SHIFT) | (bm ? (uint32_t)OM_PEND : 0u);
-    p.U(OU_MASKS, s) = masks; p.U(OU_PEND, s) = first_id;
+    p.U(OU_MASKS, s) = masks;
+    if (bm) p.U(OU_LAST, s) = first_id;
     return oct_tag(0, masks, p.U(OU_LPOS, s), lend);
 }
 
 // ---- T: one exact FP64 test (slow path: u, v) of the lowest surviving entry
 template <bool COUNT, int SLOTS>
-HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const OctPool<SLOTS>& p, int s, CntT<COUNT>& c) {
+HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const OctPool<SLOTS>& p, int s, const WalkOut& out, CntT<COUNT>& c) {
     uint32_t masks = p.U(OU_MASKS, s);
     uint32_t bmask = (masks >> 16) & 0xffu;
     const int k = hare_ffs(bmask) - 1;                // lowest survivor first: stored list order
     bmask &= bmask - 1u;
     const uint32_t kc = (masks & OM_KC_MASK) >> OM_KC_SHIFT;
-    const uint32_t pend = (masks & OM_PEND) ? p.U(OU_PEND, s) : hare_ldg(T.lists + p.U(OU_CPOS, s) + kc * 8u + (uint32_t)k);
+    const uint32_t pend = (masks & OM_PEND) ? p.U(OU_LAST, s) : hare_ldg(T.lists + p.U(OU_CPOS, s) + kc * 8u + (uint32_t)k);
     masks = (masks & (0xffffu | OM_KC_MASK)) | (bmask << 16);
     c.test();
     const Ray3 R = { p.D(OD_OX, s), p.D(OD_OY, s), p.D(OD_OZ, s), p.D(OD_DX, s), p.D(OD_DY, s), p.D(OD_DZ, s) };
@@ -508,7 +511,8 @@ HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const 
     p.U(OU_LAST, s) = pend;
     uint32_t fl = p.U(OU_FLAGS, s);
     if (h && t > 0.0000000001 && t < p.D(OD_CLOSEST, s)) {
-        p.D(OD_CLOSEST, s) = t; p.D(OD_EU, s) = u; p.D(OD_EV, s) = v; p.U(OU_PID, s) = pend;
+        p.D(OD_CLOSEST, s) = t; p.U(OU_PID, s) = pend;
+        if (out.uv) { const long long ray = (long long)p.U(OU_RAY, s); out.uv[2 * ray] = u; out.uv[2 * ray + 1] = v; }
         fl |= OFL_HIT;
         if (t <= p.D(OD_CA, s)) fl |= FIN_HIT << OFL_FIN_SHIFT;            // early return :233-237 (CA = this leaf's nodeTmin)
         p.U(OU_FLAGS, s) = fl;
@@ -520,7 +524,7 @@ HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const 
 #if defined(__CUDACC__)
 
 #ifndef HARE_OCTW_WARPS
-#define HARE_OCTW_WARPS 16   /* 16 x 11.9 KB pools = 190 KB: the 196 KB shared-memory carve-out, leaving ~60 KB of L1 for the tree's upper levels (19 warps / 28 KB L1: 461 vs 595 Mrays/s on C3) */
+#define HARE_OCTW_WARPS 16   /* a multiple of 4 (one warp set per SM sub-partition: 17 / 18 warps leave one scheduler with 5 warps and 96 registers: 608 / 643 vs 727 Mrays/s); 16 x 10.6 KB pools = 170 KB: the 196 KB shared-memory carve-out, ~60 KB of L1 left for the tree's upper levels (19 warps / 28 KB L1: 461 vs 595 at the time) */
 #endif
 
 template <bool CHAIN, bool COUNT, int SLOTS, int N_MAX>
@@ -580,7 +584,7 @@ oct_wave_kernel(const OctDev T, const OctFrames F, const PolyRec* __restrict__ p
         // 4. run it
         uint32_t nt = OP_DONE;
         if (ph == OP_T) {
-            if (act) nt = octw_test<COUNT, SLOTS>(T, polys, p, s, c);
+            if (act) nt = octw_test<COUNT, SLOTS>(T, polys, p, s, out, c);
         } else if (ph == OP_C) {
             if (act) nt = octw_cull<COUNT, SLOTS>(T, p, s, c);
         } else if (ph == OP_G) {

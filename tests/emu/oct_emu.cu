@@ -42,7 +42,7 @@ void run(const OctDev& T, int depth, const PolyRec* polys, const double* o, cons
             st.exec[ph] += 1; st.lanes[ph] += cnt; st.trips += 1;
             uint32_t nt[32];
             if (ph == OP_T) {
-                for (int l = 0; l < cnt; ++l) nt[l] = octw_test<true, SLOTS>(T, polys, p, sel[l], c);
+                for (int l = 0; l < cnt; ++l) nt[l] = octw_test<true, SLOTS>(T, polys, p, sel[l], out, c);
             } else if (ph == OP_C) {
                 for (int l = 0; l < cnt; ++l) nt[l] = octw_cull<true, SLOTS>(T, p, sel[l], c);
             } else if (ph == OP_G) {
