@@ -6,8 +6,9 @@
 
 Configurations (`--config`):
     C3   (default) hall-500k, Octree(Model, 7, 32), 100 M rays in total, one Shoot each.  The batch is block-sharded over
-         the N ranks (STRONG scaling); every rank's traversal kernel stores its X_Event rows (poly_id, t, X_Point, u, v = 52 B)
-         straight into rank 0's buffers over NVLink inside the timed region -- the path's only cross-GPU step.
+         the N ranks (STRONG scaling); every rank's X_Event rows (poly_id, t, X_Point, u, v = 52 B) are delivered into rank 0's
+         buffers over NVLink inside the timed region -- the path's only cross-GPU step (peer copies overlapped with the next
+         step's traversal; --gather selects the alternatives).
     C2   hall-50k, Voxel_Grid 64^3, 10 M rays x 50-order specular chains per GPU (weak scaling).
     C4vg / C4kd   hall-2m, Voxel_Grid 256^3 / KDTree(24, 16), 100 M rays.
     C5   Voxel_Grid build: 2 M polygons -> 256^3 cell lists (count / scan / scatter).
@@ -68,7 +69,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--presort", action="store_true", help="experiment: hand the rays over sorted by (origin, direction cell) instead of in generator order")
     ap.add_argument("--gather", default="peer", choices=["peer", "peer-store", "nccl"],
-                    help="N > 1: 'peer' = each rank's batch in 8 chunks, chunk k's rows copied into rank 0's buffers over NVLink while chunk k+1 traverses "
+                    help="N > 1: 'peer' = a step's rows are copied into rank 0's buffers over NVLink (copy engines) while the next step traverses "
                          "(default); 'peer-store' = the kernels store their rows into rank 0's buffers directly; 'nccl' = NCCL gather after the kernel")
     return ap.parse_args()
 
@@ -449,6 +450,8 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
     peer = None
     if chain:
         fin_o = torch.empty_like(o_d); fin_d = torch.empty_like(d_d); nshots = torch.empty(N, dtype=torch.int32, device=x.dev)
+        # the per-bounce event streams (Poly_id, t: 12 B per Shoot) are written in the timed region: they are what a caller consumes
+        ev_pid_d = torch.empty((N, order), dtype=torch.int32, device=x.dev); ev_t_d = torch.empty((N, order), dtype=torch.float64, device=x.dev)
         outs = [fin_o, fin_d, nshots]
     else:
         ntot = total_rays(cfg, x.world)
@@ -464,43 +467,40 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
             if int(ok.item()) == 0:
                 peer = None
         direct = peer is not None and (gather == "peer-store" or x.rank == 0)      # rank 0's own rows never need a copy
+        nbuf = 1 if (peer is None or direct) else 2                                 # 'peer': double-buffered local rows
         if direct:
-            pt, pxyz, ppid, puv = peer.out_ptrs(lo)
+            pts = [peer.out_ptrs(lo)]
         else:
-            t_d = torch.empty(N, dtype=torch.float64, device=x.dev); xyz_d = torch.empty((N, 3), dtype=torch.float64, device=x.dev)
-            pid_d = torch.empty(N, dtype=torch.int32, device=x.dev); uv_d = torch.empty((N, 2), dtype=torch.float64, device=x.dev)
-            pt, pxyz, ppid, puv = t_d.data_ptr(), xyz_d.data_ptr(), pid_d.data_ptr(), uv_d.data_ptr()
+            bufs = [dict(t=torch.empty(N, dtype=torch.float64, device=x.dev), xyz=torch.empty((N, 3), dtype=torch.float64, device=x.dev),
+                         poly_id=torch.empty(N, dtype=torch.int32, device=x.dev), uv=torch.empty((N, 2), dtype=torch.float64, device=x.dev)) for _ in range(nbuf)]
+            pts = [(b["t"].data_ptr(), b["xyz"].data_ptr(), b["poly_id"].data_ptr(), b["uv"].data_ptr()) for b in bufs]
+            t_d, xyz_d, pid_d, uv_d = bufs[0]["t"], bufs[0]["xyz"], bufs[0]["poly_id"], bufs[0]["uv"]
             outs = [pid_d, t_d, xyz_d, uv_d]
     sizes = [shard(cfg, r, x.world)[1] - shard(cfg, r, x.world)[0] for r in range(x.world)]
     gathered = None
-    # 'peer': the batch goes through the kernel in K chunks; chunk k's rows travel to rank 0 on a second stream (large coalesced peer
-    # copies over NVLink) while chunk k + 1 is traversed -- the step ends when the last chunk's copy has landed
-    chunks = 8 if (peer is not None and gather == "peer" and not chain) else 1
-    bounds = [(N * k) // chunks for k in range(chunks + 1)]
-    copy_stream = torch.cuda.Stream(device=x.dev) if (chunks > 1 and x.rank != 0) else None
+    # 'peer': a rank's X_Event rows travel to rank 0 as four large peer copies (copy engines, NVLink; rank 0's buffers are mapped here
+    # through CUDA IPC) on a second stream, WHILE the next step's batch is traversed -- local rows are double-buffered.  A step's rows
+    # are complete on rank 0 one kernel later at the latest; the timed region ends only when the last step's copies have landed.
+    # (Storing the rows from inside the kernel throttles it at 8 GPUs -- 52 B per ray as four small NVLink writes from seven peers
+    # into one GPU: 51 vs 19 ms --, and cutting the batch into chunks to overlap within a step costs the persistent kernel 44 %.)
+    copy_stream = torch.cuda.Stream(device=x.dev) if (peer is not None and not direct) else None
     if copy_stream is not None:
         remote = {k: peer.arrays[k].torch() for k in ("poly_id", "t", "xyz", "uv")}
-        local = {"poly_id": pid_d, "t": t_d, "xyz": xyz_d, "uv": uv_d}
+        copied = [None] * nbuf
+    step_no = [0]
 
     def kernel():
         stream = cur_stream(torch)
         if chain:
-            check(L.hare_reflect_chain_device(part._h, o_d.data_ptr(), d_d.data_ptr(), N, order, None, None, fin_o.data_ptr(), fin_d.data_ptr(),
-                                              nshots.data_ptr(), total.data_ptr(), None, C.c_void_p(stream)), "hare_reflect_chain_device")
+            check(L.hare_reflect_chain_device(part._h, o_d.data_ptr(), d_d.data_ptr(), N, order, ev_pid_d.data_ptr(), ev_t_d.data_ptr(), fin_o.data_ptr(),
+                                              fin_d.data_ptr(), nshots.data_ptr(), total.data_ptr(), None, C.c_void_p(stream)), "hare_reflect_chain_device")
             return
-        for k in range(chunks):
-            a, b = bounds[k], bounds[k + 1]
-            if b <= a:
-                continue
-            check(L.hare_shoot_batch_device(part._h, o_d.data_ptr() + 24 * a, d_d.data_ptr() + 24 * a, None, None, None, b - a,
-                                            C.c_void_p(pt + 8 * a), C.c_void_p(pxyz + 24 * a), C.c_void_p(ppid + 4 * a), C.c_void_p(puv + 16 * a),
-                                            None, None, C.c_void_p(stream)), "hare_shoot_batch_device")
-            if copy_stream is not None:
-                ev_k = torch.cuda.Event(); ev_k.record()
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ev_k)
-                    for name in ("poly_id", "t", "xyz", "uv"):
-                        remote[name][lo + a:lo + b].copy_(local[name][a:b], non_blocking=True)
+        k = step_no[0] % nbuf
+        if copy_stream is not None and copied[k] is not None:
+            torch.cuda.current_stream().wait_event(copied[k])          # the copy that last read this buffer has finished
+        pt, pxyz, ppid, puv = pts[k]
+        check(L.hare_shoot_batch_device(part._h, o_d.data_ptr(), d_d.data_ptr(), None, None, None, N, C.c_void_p(pt), C.c_void_p(pxyz),
+                                        C.c_void_p(ppid), C.c_void_p(puv), None, None, C.c_void_p(stream)), "hare_shoot_batch_device")
 
     def deliver():
         nonlocal gathered
@@ -508,13 +508,29 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
             return
         if peer is not None:
             if copy_stream is not None:
-                torch.cuda.current_stream().wait_stream(copy_stream)
-            peer.fence()
+                k = step_no[0] % nbuf
+                done = torch.cuda.Event(); done.record()
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    for name in ("poly_id", "t", "xyz", "uv"):
+                        remote[name][lo:lo + N].copy_(bufs[k][name], non_blocking=True)
+                    copied[k] = torch.cuda.Event(); copied[k].record()
+            elif gather == "peer-store":
+                peer.fence()
+            step_no[0] += 1
         else:
             gathered = [hd.gather_rows(a, 0, sizes) for a in outs]
 
+    def drain():
+        """End of a run of steps: every rank's last copies have landed on rank 0 (stream-ordered; the barrier follows in sync_all)."""
+        if copy_stream is not None:
+            torch.cuda.current_stream().wait_stream(copy_stream)
+        if peer is not None:
+            peer.fence()
+
     for _ in range(warmup):
         kernel(); deliver()
+    drain()
     sync_all(x)
     total.zero_()
     torch.cuda.synchronize()
@@ -529,6 +545,8 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
     for k in range(steps):
         kev[k][0].record(); kernel(); kev[k][1].record()   # inner events bracket the traversal kernel alone (roofline); outer ones the step
         deliver()
+        if k == steps - 1:
+            drain()
         ev[k + 1].record()
     sync_all(x)
     launches = hb.launch_count() - launches0
@@ -594,6 +612,22 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
                         if (x.world > 1 and not chain) else ("every rank shoots its own chains from and into its own page-locked host arrays" if x.world > 1 else None))}
         if chain:
             assert np.array_equal(ns_h, dev_res["nshots"]), "host-buffer and device-resident legs disagree"
+            # the same call with the per-bounce event streams brought back to the host as well (12 B per Shoot more over PCIe)
+            try:
+                evp_h = pinned(x, (N, order), np.int32); evt_h = pinned(x, (N, order), np.float64)
+                def step_host_ev():
+                    check(L.hare_reflect_chain(part._h, o.ctypes.data, d.ctypes.data, N, order, evp_h.ctypes.data, evt_h.ctypes.data, fo_h.ctypes.data,
+                                               fd_h.ctypes.data, ns_h.ctypes.data, C.byref(tot), None), "hare_reflect_chain")
+                    return tot.value
+                step_host_ev()
+                sync_all(x)
+                t0 = time.perf_counter(); ev_shots = step_host_ev(); torch.cuda.synchronize(); dt_ev = time.perf_counter() - t0
+                dt_ev, ev_all = reduce_max_sum(x, dt_ev, ev_shots)
+                e2e["with_event_streams"] = {"value": ev_all / dt_ev / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": int(total_rays(cfg, x.world) * (52 + 12 * order)),
+                                             "note": "ev_poly_id + ev_t (N x order) copied back too"}
+                assert np.array_equal(evp_h[:1000], ev_pid_d[:1000].cpu().numpy()), "event streams of the host-buffer and device-resident legs disagree"
+            except MemoryError as e:
+                e2e["with_event_streams"] = {"error": repr(e)}
         elif x.world == 1:
             assert np.array_equal(pid_h, dev_res["poly_id"].cpu().numpy()) and np.array_equal(t_h, dev_res["t"].cpu().numpy()), \
                 "host-buffer and device-resident legs disagree"
@@ -676,7 +710,8 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
                 "roofline": roof, "cpu_baseline": cpu_line, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "shots_per_step": shots_all // steps, "parity": parity,
                 "result_delivery": None if x.world == 1 else (
-                    ("8 chunks per rank; chunk k's rows copied into rank 0's buffers (CUDA IPC mapping, NVLink) on a second stream while chunk k+1 traverses; 4-byte NCCL fence"
+                    ("each rank's rows go to rank 0's buffers (CUDA IPC mapping) as large peer copies over NVLink on a second stream while the NEXT step's batch "
+                     "is traversed (double-buffered); the timed region ends when the last step's copies have landed"
                      if gather == "peer" else "peer stores from the traversal kernel straight into rank 0's buffers (CUDA IPC over NVLink) + 4-byte NCCL fence")
                     if peer is not None else "NCCL gather after the kernel")}
     if peer is not None:

@@ -478,7 +478,7 @@ struct VoxelGrid : Partition {
     // Same result as build_flat, evaluated polygon-major over a conservative voxel
     // range (the SAT's three box-axis tests reject every voxel outside it).  NOT a
     // reference code path: an accelerated evaluation of the same predicate, checked
-    // against build_flat in tests/test_oracle_build.py.
+    // against build_flat and the committed golden lists in tests/test_oracle_pins.py (test_golden_voxelgrid_lists, test_hier_ctor_matches_flat_on_small_case).
     void build_flat_fast(int Domain) {
         bounds(); set_domain(Domain, Domain, Domain);
         lists.assign((size_t)Domain * Domain * Domain, {});
