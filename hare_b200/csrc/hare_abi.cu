@@ -1296,6 +1296,7 @@ static int bin_rays(hare_part_s* p, const PartDev& d, const double* o, const dou
 }
 
 static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cudaStream_t st) {
+    if (a.N >= (1LL << 32)) return fail(HARE_ERR_INVALID, "Shoot: at most 2^32-1 rays per call");
     uint32_t* perm = nullptr;
     int rc = bin_rays(p, d, a.o, a.d, a.N, st, &perm);
     if (rc) return rc;

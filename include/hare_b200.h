@@ -156,7 +156,9 @@ int hare_part_destroy(hare_part_t part);
  *   o_moved     N x 3 ray origin after the call: Voxel_Grid moves a ray that starts outside the
  *               grid to its entry point (AABB_Main.cs:255-257; Ray is a class, the caller sees it)
  *   counters    HARE_CNT_N totals over the batch (cells or nodes visited, list entries scanned,
- *               polygon tests, hits); costs a little time, pass NULL when not needed. */
+ *               polygon tests, hits); costs a little time, pass NULL when not needed.
+ * Rays are independent: inside the call a batch of >= 65 536 rays is traversed grouped by origin / direction cell (ray_bin.cuh) and
+ * in pipelined chunks on three streams; events are written by ray number, so the caller sees its own order and identical results. */
 int hare_shoot_batch(hare_part_t part, const double* o, const double* d,
                      const int32_t* origin1, const int32_t* origin2, const int32_t* ray_id, int64_t N,
                      double* t, double* xyz, int32_t* poly_id, double* uv, double* o_moved,

@@ -262,7 +262,7 @@ def test_large_batch_properties(gpu):
     mesh = meshes.hall("50k")
     T = gpu.Topology.from_mesh(mesh)
     g = gpu.Voxel_Grid([T], 64)
-    n = 2_200_000                                   # crosses the 2^20-ray chunk boundary twice
+    n = 2_200_000                                   # eight pipelined chunks of 275 k rays on three streams, each through the coherence pre-pass
     o, d = rays_from_sources(n, meshes.sources(4), stream=10)
     r = g.Shoot_Batch(o, d)
     assert r["hit"].mean() > 0.995
