@@ -1349,7 +1349,7 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
 
 static const int64_t kChunk = 1 << 20;   // chains per pipelined chunk of hare_reflect_chain
 // Rays per pipelined chunk of hare_shoot_batch: an eighth of the device's share (so that copies and kernels of neighbouring chunks
-// overlap on the two streams), between 2^18 (a chunk should fill the persistent kernel's ~150 k ray slots more than once) and 2^22
+// overlap on the three streams), between 2^18 (a chunk should fill the persistent kernel's ~150 k ray slots more than once) and 2^22
 static int64_t shoot_chunk(int64_t n_device) { return std::min<int64_t>(1 << 22, std::max<int64_t>(1 << 18, (n_device + 7) / 8)); }
 
 // CUDA call inside a lambda that reports through an int status (the caller drains every stream before returning it)
@@ -1382,7 +1382,7 @@ extern "C" int hare_shoot_batch(hare_part_t p, const double* o, const double* d,
     const int G = (int)p->dev.size();
     if (G == 0) return fail(HARE_ERR_CUDA, "hare_shoot_batch: host-only handle, no CUDA device (hare_b200 has no CPU fallback)");
     if (counters) std::memset(counters, 0, HARE_CNT_N * sizeof(uint64_t));
-    // block-shard the batch over the devices; per device, pipeline chunks over two streams
+    // block-shard the batch over the devices; per device, pipeline chunks over kStreams streams
     auto enqueue = [&]() -> int {
         for (int g = 0; g < G; ++g) {
             PartDev& dv = p->dev[g];

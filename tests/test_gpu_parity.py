@@ -583,3 +583,25 @@ def test_c4_c5_voxelgrid_256_2m(gpu, hall2m):
     assert np.array_equal(off, ooff) and np.array_equal(pol, opol)
     o, d = rays_from_sources(200_000, meshes.sources(8), stream=4)
     assert_events_equal(g.Shoot_Batch(o, d), og.Shoot(o, d, nthreads=16), uv=False, what="C4 Voxel_Grid 256")
+
+
+def test_results_do_not_depend_on_ray_order_or_batch_cut(gpu):
+    """Size-independent property behind the coherence pre-pass (ray_bin.cuh) and the chunked pipeline: a ray's event depends on
+    nothing but the ray.  The same 300 k rays in generator order, shuffled, and cut into uneven batches (below and above the
+    65 536-ray threshold of the pre-pass) give identical events ray by ray, on all three partitions."""
+    mesh = meshes.hall("10k")
+    T = gpu.Topology.from_mesh(mesh)
+    n = 300_000
+    o, d = rays_from_sources(n, meshes.sources(8), stream=21)
+    perm = np.random.default_rng(7).permutation(n)
+    for part, fields in ((gpu.Voxel_Grid([T], 32), ("poly_id", "t", "xyz")), (gpu.Octree([T], 6, 16), ("poly_id", "t", "xyz", "uv")),
+                         (gpu.KDTree([T], 18, 16), ("poly_id", "t", "xyz", "uv"))):
+        a = part.Shoot_Batch(o, d)
+        b = part.Shoot_Batch(o[perm], d[perm])
+        for k in fields:
+            assert np.array_equal(a[k][perm], b[k]), (type(part).__name__, k, "shuffled")
+        cuts = [0, 1, 1000, 70_000, 70_001, 200_000, n]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            c = part.Shoot_Batch(o[lo:hi], d[lo:hi])
+            for k in fields:
+                assert np.array_equal(a[k][lo:hi], c[k]), (type(part).__name__, k, lo, hi)
