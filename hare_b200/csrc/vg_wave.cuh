@@ -358,8 +358,40 @@ HD uint32_t wave_test(const VGrid& g, const PolyRec* __restrict__ polys, const W
     return wave_tag(fl, lpos, lend);
 }
 
-// number of the c-th ray consumed by warp gw out of tw warps: warps take rays in interleaved groups of 32
-HD long long wave_ray_number(long long c, long long gw, long long tw) { return ((c >> 5) * tw + gw) * 32 + (c & 31); }
+// ---- ray supply of a warp (shared by the three traversal kernels) ------------------------------------------------------------
+// The batch is handed out on demand, in blocks of HARE_FEED_BLOCK consecutive rays (of the coherence order, ray_bin.cuh) claimed from
+// a device counter.  A persistent kernel lasts as long as its slowest warp, and the work behind a share of the batch varies (4 % per
+// warp over 12.5 M binned rays, CPU replay): with a fixed interleave of the groups over the warps the Octree ran 728 Mrays/s on C3,
+// with this supply 825 (Voxel_Grid 888 -> 983, KDTree 271 -> 300; a mixed scheme -- fixed for the first 7/8 or 3/4 of the batch --
+// landed in between: 794 / 800).  A warp always holds one block in reserve, claimed by lane 0 when the previous one was opened and
+// read only when that one is used up, many trips later: the atomic's round trip is never waited for.
+#ifndef HARE_FEED_BLOCK
+#define HARE_FEED_BLOCK 64          /* >= 32: one trip takes at most 32 rays, i.e. touches at most two blocks */
+#endif
+struct RayFeed {                    // warp-uniform, except b1: lane 0's until it is broadcast at the next SF trip
+    long long b0, b1;               // ray number of the first ray of the open block / of the block in reserve
+    int used;                       // rays taken from the open block (< HARE_FEED_BLOCK)
+};
+// claim the next block (one lane per warp); *ctr is zero before the launch
+HD long long feed_claim(unsigned long long* ctr) {
+#if defined(__CUDA_ARCH__)
+    return (long long)atomicAdd(ctr, (unsigned long long)HARE_FEED_BLOCK);
+#else
+    const unsigned long long old = *ctr; *ctr = old + HARE_FEED_BLOCK; return (long long)old;
+#endif
+}
+// ray number of the rank-th ray taken in this trip; b1 = the reserve block's first ray (broadcast)
+HD long long feed_ray(const RayFeed& f, long long b1, int rank) {
+    const int off = f.used + rank;
+    return off < HARE_FEED_BLOCK ? f.b0 + off : b1 + (off - HARE_FEED_BLOCK);
+}
+// `need` rays were taken; true when the open block is used up: the reserve has been opened and a new one must be claimed into f.b1
+HD bool feed_advance(RayFeed& f, int need, long long b1) {
+    f.used += need;
+    if (f.used < HARE_FEED_BLOCK) return false;
+    f.used -= HARE_FEED_BLOCK; f.b0 = b1;
+    return true;
+}
 
 #if defined(__CUDACC__)
 
@@ -372,7 +404,7 @@ __global__ void __launch_bounds__(HARE_WAVE_WARPS * 32, 1)
 vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                const double* __restrict__ o, const double* __restrict__ d,
                const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a, const int32_t* __restrict__ rid,
-               long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, const WalkOut out) {
+               long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, unsigned long long* __restrict__ feed /* RayFeed counter, zero */, const WalkOut out) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_occ = reinterpret_cast<uint32_t*>(s_raw);
     uint32_t occ_words = 0;
@@ -396,8 +428,9 @@ vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
 
     CntT<COUNT> c;
     unsigned int shots = 0;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp, tw = (long long)gridDim.x * (blockDim.x >> 5);
-    long long cur = 0;   // rays this warp has consumed (warp-uniform)
+    RayFeed f = { 0, 0, 0 };   // see RayFeed in vg_wave.cuh
+    if (lane == 0) { f.b0 = feed_claim(feed); f.b1 = feed_claim(feed); }
+    f.b0 = __shfl_sync(0xffffffffu, f.b0, 0);
     const unsigned lt = (1u << lane) - 1u;
 
     while (true) {
@@ -440,12 +473,13 @@ vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
             const bool noray = act && (p.U(U_FLAGS, s) & WF_NORAY);
             const unsigned want = __ballot_sync(0xffffffffu, noray);
             bool ready = act;
+            const long long b1 = __shfl_sync(0xffffffffu, f.b1, 0);
             if (noray) {
-                const long long ray = wave_ray_number(cur + __popc(want & lt), gw, tw);
+                const long long ray = feed_ray(f, b1, __popc(want & lt));
                 if (ray < N) wave_fetch<SLOTS>(p, s, perm ? (long long)__ldg(perm + ray) : ray, o, d, o1a, o2a, rid);
                 else ready = false;
             }
-            cur += __popc(want);
+            if (feed_advance(f, __popc(want), b1) && lane == 0) f.b1 = feed_claim(feed);
             if (ready) nt = wave_setup<COUNT, SLOTS>(g, occ, OCC_SMEM, p, s, c);
         }
         if (act) p.tag[s] = (uint8_t)nt;

@@ -22,11 +22,13 @@ void run(const KdDev& T, const PolyRec* polys, const double* o, const double* d,
     KdStacks S = { stk.data(), sdepth };
     CntT<true> c;
     unsigned long long total = 0;
+    unsigned long long feed_ctr = 0;   // the launch's claim counter: the simulated warps run one after the other, so the first one takes the whole batch and the others find it empty
     for (long long gw = 0; gw < tw; ++gw) {
         KdPool<SLOTS> p;
         p.bind(mem.data());
         for (int s = 0; s < SLOTS; ++s) { p.U(KU_FLAGS, s) = KFL_NORAY; p.U(KU_LPOS, s) = 0; p.U(KU_LEND, s) = 0; p.tag[s] = (uint8_t)KP_SF; }
-        long long cur = 0;
+        RayFeed f = { 0, 0, 0 };
+        f.b0 = feed_claim(&feed_ctr); f.b1 = feed_claim(&feed_ctr);
         unsigned int shots = 0;
         while (true) {
             int n[KP_COUNT] = {};
@@ -49,14 +51,14 @@ void run(const KdDev& T, const PolyRec* polys, const double* o, const double* d,
                 for (int l = 0; l < cnt; ++l) {
                     bool ready = true;
                     if (p.U(KU_FLAGS, sel[l]) & KFL_NORAY) {
-                        const long long ray = wave_ray_number(cur + rank, gw, tw);
+                        const long long ray = feed_ray(f, f.b1, rank);
                         ++rank;
                         if (ray < N) kdw_fetch<SLOTS>(p, sel[l], ray, o, d, o1a, o2a, rid);
                         else ready = false;
                     }
                     nt[l] = ready ? kdw_setup<true, SLOTS>(T, p, sel[l], c) : (uint32_t)KP_DONE;
                 }
-                cur += rank;
+                if (feed_advance(f, rank, f.b1)) f.b1 = feed_claim(&feed_ctr);
             }
             for (int l = 0; l < cnt; ++l) p.tag[sel[l]] = (uint8_t)nt[l];
         }

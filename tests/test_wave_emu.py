@@ -169,3 +169,20 @@ def test_ray_bin_keys_stay_in_range_and_group_coherent_rays():
         L.emu_ray_bin_keys(o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_int64(len(kk)), mm.ctypes.data_as(C.c_void_p),
                            kk.ctypes.data_as(C.c_void_p), C.byref(nb))
         assert kk.max() < nb.value
+
+
+@pytest.mark.parametrize("n,tw", [(0, 7), (1, 3), (31, 2), (1000, 40), (70_001, 9), (300_000, 148 * 2), (1_000_003, 64)])
+def test_ray_feed_hands_out_every_ray_exactly_once(n, tw):
+    """RayFeed (vg_wave.cuh): the warps claim blocks of the batch from a counter, one block always in reserve -- whatever the order
+    in which they come for rays and however many they take per trip, rays 0..N-1 go out once each, and the claims past the end of
+    the batch stay bounded."""
+    import ctypes as C
+    from tests.emu import wave_emu
+    L = wave_emu.lib()
+    L.emu_ray_feed.restype = C.c_longlong
+    for seed in (1, 2, 3):
+        counts = np.zeros(max(n, 1), np.uint32)
+        blocks = L.emu_ray_feed(C.c_int64(n), C.c_int64(tw), C.c_uint64(seed), counts.ctypes.data_as(C.c_void_p))
+        assert blocks >= 0
+        assert np.all(counts[:n] == 1)
+        assert blocks * 64 <= n + tw * 64 * 4
