@@ -1129,12 +1129,15 @@ struct ShootArgs {
     double *t, *xyz; int32_t* pid; double *uv, *om; unsigned long long* counters;
 };
 
-// Ray supply of a traversal launch (RayFeed in vg_wave.cuh): the counter the warps claim their rays from, zeroed in stream order
-static int make_feed(cudaStream_t st, unsigned long long** ctr) {
-    *ctr = nullptr;
-    CK(cudaMallocAsync(reinterpret_cast<void**>(ctr), sizeof(unsigned long long), st));
-    cudaError_t e = cudaMemsetAsync(*ctr, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) { cudaFreeAsync(*ctr, st); CK(e); }
+// Ray supply of a traversal launch of `total_warps` warps (RayFeed in vg_wave.cuh): block size and the counter the warps claim their
+// rays from, zeroed in stream order
+static int make_feed(int64_t N, int64_t total_warps, cudaStream_t st, RayFeedArgs* feed) {
+    feed->block = feed_block_for(N, total_warps);
+    feed->first = total_warps * feed->block;
+    feed->ctr = nullptr;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&feed->ctr), sizeof(unsigned long long), st));
+    cudaError_t e = cudaMemsetAsync(feed->ctr, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) { cudaFreeAsync(feed->ctr, st); CK(e); }
     return HARE_OK;
 }
 
@@ -1153,13 +1156,13 @@ static int launch_vg_wave2(const VGrid& g, const PartDev& d, const double* o, co
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = warps * 32;
     int64_t blocks = std::min<int64_t>((N + threads - 1) / threads, (int64_t)d.sms);
-    unsigned long long* feed = nullptr;
-    int rc = make_feed(st, &feed);
+    RayFeedArgs feed;
+    int rc = make_feed(N, blocks * warps, st, &feed);
     if (rc) return rc;
     k<<<(unsigned)blocks, threads, smem, st>>>(g, d.polys, o, dd, o1, o2, rid, N, order, perm, feed, w);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(feed, st);
+    cudaFreeAsync(feed.ctr, st);
     CK(e);
     return HARE_OK;
 }
@@ -1220,14 +1223,14 @@ static int launch_oct_wave2(const OctDev& t, const PartDev& d, const double* o, 
     void* scratch = nullptr;
     CK(cudaMallocAsync(&scratch, nfr * (sizeof(double2) + sizeof(uint2)), st));
     F.ab = reinterpret_cast<double2*>(scratch); F.cq = reinterpret_cast<uint2*>(F.ab + nfr);
-    unsigned long long* feed = nullptr;
-    int rc = make_feed(st, &feed);
+    RayFeedArgs feed;
+    int rc = make_feed(N, blocks * HARE_OCTW_WARPS, st, &feed);
     if (rc) { cudaFreeAsync(scratch, st); return rc; }
     k<<<(unsigned)blocks, threads, smem, st>>>(t, F, d.polys, o, dd, o1, o2, N, order, perm, feed, w);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
-    cudaFreeAsync(feed, st);
+    cudaFreeAsync(feed.ctr, st);
     CK(e);
     return HARE_OK;
 }
@@ -1265,14 +1268,14 @@ static int launch_kd_wave2(const KdDev& t, const PartDev& d, const double* o, co
     void* scratch = nullptr;
     CK(cudaMallocAsync(&scratch, n * sizeof(uint4), st));
     S.st = reinterpret_cast<uint4*>(scratch);
-    unsigned long long* feed = nullptr;
-    int rc = make_feed(st, &feed);
+    RayFeedArgs feed;
+    int rc = make_feed(N, blocks * HARE_KDW_WARPS, st, &feed);
     if (rc) { cudaFreeAsync(scratch, st); return rc; }
     k<<<(unsigned)blocks, threads, smem, st>>>(t, S, d.polys, o, dd, o1, o2, rid, N, order, perm, feed, w);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
-    cudaFreeAsync(feed, st);
+    cudaFreeAsync(feed.ctr, st);
     CK(e);
     return HARE_OK;
 }

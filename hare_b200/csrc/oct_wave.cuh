@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(HARE_OCTW_WARPS * 32, 1)
 oct_wave_kernel(const OctDev T, const OctFrames F, const PolyRec* __restrict__ polys,
                 const double* __restrict__ o, const double* __restrict__ d,
                 const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a,
-                long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, unsigned long long* __restrict__ feed /* RayFeed counter, zero */, const WalkOut out) {
+                long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, const RayFeedArgs feed, const WalkOut out) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     OctPool<SLOTS> p;
@@ -549,9 +549,8 @@ oct_wave_kernel(const OctDev T, const OctFrames F, const PolyRec* __restrict__ p
     unsigned int shots = 0;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     const size_t gslot0 = (size_t)gw * SLOTS;
-    RayFeed f = { 0, 0, 0 };   // see RayFeed in vg_wave.cuh
-    if (lane == 0) { f.b0 = feed_claim(feed); f.b1 = feed_claim(feed); }
-    f.b0 = __shfl_sync(0xffffffffu, f.b0, 0);
+    RayFeed f = { gw * feed.block, 0, 0 };   // see RayFeed in vg_wave.cuh
+    if (lane == 0) f.b1 = feed_claim(feed);
     const unsigned lt = (1u << lane) - 1u;
 
     while (true) {
@@ -600,11 +599,11 @@ oct_wave_kernel(const OctDev T, const OctFrames F, const PolyRec* __restrict__ p
             bool ready = act;
             const long long b1 = __shfl_sync(0xffffffffu, f.b1, 0);
             if (noray) {
-                const long long ray = feed_ray(f, b1, __popc(want & lt));
+                const long long ray = feed_ray(f, feed, b1, __popc(want & lt));
                 if (ray < N) octw_fetch<SLOTS>(p, s, perm ? (long long)__ldg(perm + ray) : ray, o, d, o1a, o2a);
                 else ready = false;
             }
-            if (feed_advance(f, __popc(want), b1) && lane == 0) f.b1 = feed_claim(feed);
+            if (feed_advance(f, feed, __popc(want), b1) && lane == 0) f.b1 = feed_claim(feed);
             if (ready) nt = octw_setup<COUNT, SLOTS>(T, p, s, c);
         }
         if (act) p.tag[s] = (uint8_t)nt;

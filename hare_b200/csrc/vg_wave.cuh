@@ -359,37 +359,46 @@ HD uint32_t wave_test(const VGrid& g, const PolyRec* __restrict__ polys, const W
 }
 
 // ---- ray supply of a warp (shared by the three traversal kernels) ------------------------------------------------------------
-// The batch is handed out on demand, in blocks of HARE_FEED_BLOCK consecutive rays (of the coherence order, ray_bin.cuh) claimed from
-// a device counter.  A persistent kernel lasts as long as its slowest warp, and the work behind a share of the batch varies (4 % per
-// warp over 12.5 M binned rays, CPU replay): with a fixed interleave of the groups over the warps the Octree ran 728 Mrays/s on C3,
-// with this supply 825 (Voxel_Grid 888 -> 983, KDTree 271 -> 300; a mixed scheme -- fixed for the first 7/8 or 3/4 of the batch --
-// landed in between: 794 / 800).  A warp always holds one block in reserve, claimed by lane 0 when the previous one was opened and
-// read only when that one is used up, many trips later: the atomic's round trip is never waited for.
+// The batch is handed out on demand, in blocks of consecutive rays (of the coherence order, ray_bin.cuh) claimed from a device
+// counter.  A persistent kernel lasts as long as its slowest warp, and the work behind a share of the batch varies (4 % per warp
+// over 12.5 M binned rays, CPU replay): with a fixed interleave of the groups over the warps the Octree ran 728 Mrays/s on C3, with
+// this supply 829 (Voxel_Grid 888 -> 982, KDTree 271 -> 302; a mixed scheme -- fixed for the first 7/8 or 3/4 of the batch --
+// landed in between: 794 / 800; blocks of 32 / 64 / 128 / 512 rays: 802 / 829 / 844 / 834 on 100 M rays, 713 / 721 / 708 on 12.5 M).
+// A warp always holds one block in reserve, claimed by lane 0 when the previous one was opened and read only when that one is used
+// up, many trips later: the atomic's round trip is never waited for.  The first block of a warp is its own number (no atomic, and
+// a small batch still spreads over all the warps); the counter hands out the blocks after those.
 #ifndef HARE_FEED_BLOCK
-#define HARE_FEED_BLOCK 64          /* >= 32: one trip takes at most 32 rays, i.e. touches at most two blocks */
+#define HARE_FEED_BLOCK 64
 #endif
+struct RayFeedArgs {
+    unsigned long long* ctr;        // rays claimed beyond the warps' first blocks; zero before the launch
+    long long first;                // first ray handed out through the counter = warps of the launch x block
+    int block;                      // rays per block, >= 32: one trip takes at most 32 rays, i.e. touches at most two blocks
+};
 struct RayFeed {                    // warp-uniform, except b1: lane 0's until it is broadcast at the next SF trip
     long long b0, b1;               // ray number of the first ray of the open block / of the block in reserve
-    int used;                       // rays taken from the open block (< HARE_FEED_BLOCK)
+    int used;                       // rays taken from the open block (< block)
 };
-// claim the next block (one lane per warp); *ctr is zero before the launch
-HD long long feed_claim(unsigned long long* ctr) {
+// rays per block for a batch of N rays on tw warps: HARE_FEED_BLOCK, 32 when that would leave fewer than eight blocks per warp
+HD int feed_block_for(long long N, long long tw) { return N >= tw * HARE_FEED_BLOCK * 8 ? HARE_FEED_BLOCK : 32; }
+// claim the next block (one lane per warp)
+HD long long feed_claim(const RayFeedArgs& A) {
 #if defined(__CUDA_ARCH__)
-    return (long long)atomicAdd(ctr, (unsigned long long)HARE_FEED_BLOCK);
+    return A.first + (long long)atomicAdd(A.ctr, (unsigned long long)A.block);
 #else
-    const unsigned long long old = *ctr; *ctr = old + HARE_FEED_BLOCK; return (long long)old;
+    const unsigned long long old = *A.ctr; *A.ctr = old + (unsigned long long)A.block; return A.first + (long long)old;
 #endif
 }
 // ray number of the rank-th ray taken in this trip; b1 = the reserve block's first ray (broadcast)
-HD long long feed_ray(const RayFeed& f, long long b1, int rank) {
+HD long long feed_ray(const RayFeed& f, const RayFeedArgs& A, long long b1, int rank) {
     const int off = f.used + rank;
-    return off < HARE_FEED_BLOCK ? f.b0 + off : b1 + (off - HARE_FEED_BLOCK);
+    return off < A.block ? f.b0 + off : b1 + (off - A.block);
 }
 // `need` rays were taken; true when the open block is used up: the reserve has been opened and a new one must be claimed into f.b1
-HD bool feed_advance(RayFeed& f, int need, long long b1) {
+HD bool feed_advance(RayFeed& f, const RayFeedArgs& A, int need, long long b1) {
     f.used += need;
-    if (f.used < HARE_FEED_BLOCK) return false;
-    f.used -= HARE_FEED_BLOCK; f.b0 = b1;
+    if (f.used < A.block) return false;
+    f.used -= A.block; f.b0 = b1;
     return true;
 }
 
@@ -404,7 +413,7 @@ __global__ void __launch_bounds__(HARE_WAVE_WARPS * 32, 1)
 vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
                const double* __restrict__ o, const double* __restrict__ d,
                const int32_t* __restrict__ o1a, const int32_t* __restrict__ o2a, const int32_t* __restrict__ rid,
-               long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, unsigned long long* __restrict__ feed /* RayFeed counter, zero */, const WalkOut out) {
+               long long N, int order, const uint32_t* __restrict__ perm /* ray order of ray_bin.cuh, or null */, const RayFeedArgs feed, const WalkOut out) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_occ = reinterpret_cast<uint32_t*>(s_raw);
     uint32_t occ_words = 0;
@@ -428,9 +437,9 @@ vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
 
     CntT<COUNT> c;
     unsigned int shots = 0;
-    RayFeed f = { 0, 0, 0 };   // see RayFeed in vg_wave.cuh
-    if (lane == 0) { f.b0 = feed_claim(feed); f.b1 = feed_claim(feed); }
-    f.b0 = __shfl_sync(0xffffffffu, f.b0, 0);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    RayFeed f = { gw * feed.block, 0, 0 };   // see RayFeed in vg_wave.cuh
+    if (lane == 0) f.b1 = feed_claim(feed);
     const unsigned lt = (1u << lane) - 1u;
 
     while (true) {
@@ -475,11 +484,11 @@ vg_wave_kernel(const VGrid g, const PolyRec* __restrict__ polys,
             bool ready = act;
             const long long b1 = __shfl_sync(0xffffffffu, f.b1, 0);
             if (noray) {
-                const long long ray = feed_ray(f, b1, __popc(want & lt));
+                const long long ray = feed_ray(f, feed, b1, __popc(want & lt));
                 if (ray < N) wave_fetch<SLOTS>(p, s, perm ? (long long)__ldg(perm + ray) : ray, o, d, o1a, o2a, rid);
                 else ready = false;
             }
-            if (feed_advance(f, __popc(want), b1) && lane == 0) f.b1 = feed_claim(feed);
+            if (feed_advance(f, feed, __popc(want), b1) && lane == 0) f.b1 = feed_claim(feed);
             if (ready) nt = wave_setup<COUNT, SLOTS>(g, occ, OCC_SMEM, p, s, c);
         }
         if (act) p.tag[s] = (uint8_t)nt;

@@ -22,13 +22,14 @@ void run(const KdDev& T, const PolyRec* polys, const double* o, const double* d,
     KdStacks S = { stk.data(), sdepth };
     CntT<true> c;
     unsigned long long total = 0;
-    unsigned long long feed_ctr = 0;   // the launch's claim counter: the simulated warps run one after the other, so the first one takes the whole batch and the others find it empty
+    unsigned long long feed_ctr = 0;   // the launch's claim counter: the simulated warps run one after the other, so the first one takes everything but the other warps' first blocks
+    const RayFeedArgs feed = { &feed_ctr, tw * feed_block_for(N, tw), feed_block_for(N, tw) };
     for (long long gw = 0; gw < tw; ++gw) {
         KdPool<SLOTS> p;
         p.bind(mem.data());
         for (int s = 0; s < SLOTS; ++s) { p.U(KU_FLAGS, s) = KFL_NORAY; p.U(KU_LPOS, s) = 0; p.U(KU_LEND, s) = 0; p.tag[s] = (uint8_t)KP_SF; }
-        RayFeed f = { 0, 0, 0 };
-        f.b0 = feed_claim(&feed_ctr); f.b1 = feed_claim(&feed_ctr);
+        RayFeed f = { gw * feed.block, 0, 0 };
+        f.b1 = feed_claim(feed);
         unsigned int shots = 0;
         while (true) {
             int n[KP_COUNT] = {};
@@ -51,14 +52,14 @@ void run(const KdDev& T, const PolyRec* polys, const double* o, const double* d,
                 for (int l = 0; l < cnt; ++l) {
                     bool ready = true;
                     if (p.U(KU_FLAGS, sel[l]) & KFL_NORAY) {
-                        const long long ray = feed_ray(f, f.b1, rank);
+                        const long long ray = feed_ray(f, feed, f.b1, rank);
                         ++rank;
                         if (ray < N) kdw_fetch<SLOTS>(p, sel[l], ray, o, d, o1a, o2a, rid);
                         else ready = false;
                     }
                     nt[l] = ready ? kdw_setup<true, SLOTS>(T, p, sel[l], c) : (uint32_t)KP_DONE;
                 }
-                if (feed_advance(f, rank, f.b1)) f.b1 = feed_claim(&feed_ctr);
+                if (feed_advance(f, feed, rank, f.b1)) f.b1 = feed_claim(feed);
             }
             for (int l = 0; l < cnt; ++l) p.tag[sel[l]] = (uint8_t)nt[l];
         }

@@ -26,13 +26,14 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
     CntT<true> c;
     const WaveGeom wg = wave_geom(g);
     unsigned long long total = 0;
-    unsigned long long feed_ctr = 0;   // the launch's claim counter: the simulated warps run one after the other, so the first one takes the whole batch and the others find it empty
+    unsigned long long feed_ctr = 0;   // the launch's claim counter: the simulated warps run one after the other, so the first one takes everything but the other warps' first blocks
+    const RayFeedArgs feed = { &feed_ctr, tw * feed_block_for(N, tw), feed_block_for(N, tw) };
     for (long long gw = 0; gw < tw; ++gw) {
         WavePool<SLOTS> p;
         p.bind(mem.data());
         for (int s = 0; s < SLOTS; ++s) { p.U(U_FLAGS, s) = WF_NORAY; p.U(U_LPOS, s) = 0; p.U(U_LEND, s) = 0; p.tag[s] = (uint8_t)PH_SF; }
-        RayFeed f = { 0, 0, 0 };
-        f.b0 = feed_claim(&feed_ctr); f.b1 = feed_claim(&feed_ctr);
+        RayFeed f = { gw * feed.block, 0, 0 };
+        f.b1 = feed_claim(feed);
         unsigned int shots = 0;
         while (true) {
             int n[PH_COUNT] = { 0, 0, 0, 0 };
@@ -79,14 +80,14 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
                 for (int l = 0; l < cnt; ++l) {
                     bool ready = true;
                     if (p.U(U_FLAGS, sel[l]) & WF_NORAY) {
-                        const long long ray = feed_ray(f, f.b1, rank);
+                        const long long ray = feed_ray(f, feed, f.b1, rank);
                         ++rank;
                         if (ray < N) wave_fetch<SLOTS>(p, sel[l], ray, o, d, o1a, o2a, rid);
                         else ready = false;
                     }
                     nt[l] = ready ? wave_setup<true, SLOTS>(g, g.occp, false, p, sel[l], c) : (uint32_t)PH_DONE;
                 }
-                if (feed_advance(f, rank, f.b1)) f.b1 = feed_claim(&feed_ctr);
+                if (feed_advance(f, feed, rank, f.b1)) f.b1 = feed_claim(feed);
             }
             for (int l = 0; l < cnt; ++l) p.tag[sel[l]] = (uint8_t)nt[l];
         }
@@ -202,13 +203,14 @@ extern "C" void emu_ray_bin_keys(const double* o, const double* d, int64_t n, co
 }
 
 // ---- the ray supply (RayFeed, vg_wave.cuh): tw simulated warps take rays in a random interleaving, 1..32 at a time -------------
-// counts[r] = how often ray r was handed out; returns the number of blocks claimed.  A warp stops once 64 of its requests in a row
+// counts[r] = how often ray r was handed out; returns the number of rays the claimed blocks cover.  A warp stops once 64 of its requests in a row
 // were answered with ray numbers >= N (in the kernels: every slot of its pool has gone to DONE).
 extern "C" long long emu_ray_feed(int64_t N, int64_t tw, uint64_t seed, uint32_t* counts) {
     unsigned long long ctr = 0;
+    const RayFeedArgs feed = { &ctr, tw * feed_block_for(N, tw), feed_block_for(N, tw) };
     std::vector<RayFeed> f((size_t)tw);
     std::vector<int> dry((size_t)tw, 0);
-    for (int64_t w = 0; w < tw; ++w) { f[w] = RayFeed{ 0, 0, 0 }; f[w].b0 = feed_claim(&ctr); f[w].b1 = feed_claim(&ctr); }
+    for (int64_t w = 0; w < tw; ++w) { f[w] = RayFeed{ w * feed.block, 0, 0 }; f[w].b1 = feed_claim(feed); }
     uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
     auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
     int64_t live = tw;
@@ -217,12 +219,12 @@ extern "C" long long emu_ray_feed(int64_t N, int64_t tw, uint64_t seed, uint32_t
         if (dry[w] >= 64) continue;
         const int need = 1 + (int)(rnd() % 32);
         for (int r = 0; r < need; ++r) {
-            const long long ray = feed_ray(f[w], f[w].b1, r);
+            const long long ray = feed_ray(f[w], feed, f[w].b1, r);
             if (ray < 0) return -1;
             if (ray < N) { ++counts[ray]; dry[w] = 0; } else ++dry[w];
         }
-        if (feed_advance(f[w], need, f[w].b1)) f[w].b1 = feed_claim(&ctr);
+        if (feed_advance(f[w], feed, need, f[w].b1)) f[w].b1 = feed_claim(feed);
         if (dry[w] >= 64) --live;
     }
-    return (long long)(ctr / HARE_FEED_BLOCK);
+    return feed.first + (long long)ctr;
 }

@@ -182,7 +182,7 @@ def test_ray_feed_hands_out_every_ray_exactly_once(n, tw):
     L.emu_ray_feed.restype = C.c_longlong
     for seed in (1, 2, 3):
         counts = np.zeros(max(n, 1), np.uint32)
-        blocks = L.emu_ray_feed(C.c_int64(n), C.c_int64(tw), C.c_uint64(seed), counts.ctypes.data_as(C.c_void_p))
-        assert blocks >= 0
+        covered = L.emu_ray_feed(C.c_int64(n), C.c_int64(tw), C.c_uint64(seed), counts.ctypes.data_as(C.c_void_p))
+        assert covered >= n
         assert np.all(counts[:n] == 1)
-        assert blocks * 64 <= n + tw * 64 * 4
+        assert covered <= n + tw * 64 * 4
