@@ -16,6 +16,7 @@ PY
 }
 for n in $names; do
   case $n in
+    c3_driver) run c3_driver --steps 20 --warmup 5 ;;
     c3_peer) run c3_peer --steps 5 --warmup 3 --cpu-seconds 6 ;;
     c3_peer_fast) run c3_peer_fast --steps 10 --warmup 3 --no-cpu-baseline --no-e2e ;;
     c3_store) run c3_store --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --gather peer-store ;;
