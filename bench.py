@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--no-extras", action="store_true", help="do not append the short lines of the other configurations at N = 1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--ray-order", default="source-major", choices=["source-major", "interleaved"],
+                    help="which source a ray of the workload starts at: 'source-major' = one source after the other, as a caller that loops over its "
+                         "sources produces them (default); 'interleaved' = round-robin over the sources")
     ap.add_argument("--presort", action="store_true", help="experiment: hand the rays over sorted by (origin, direction cell) instead of in generator order")
     ap.add_argument("--gather", default="peer", choices=["peer", "peer-store", "nccl"],
                     help="N > 1: 'peer' = a step's rows are copied into rank 0's buffers over NVLink (copy engines) while the next step traverses "
@@ -83,6 +86,7 @@ def cfg_of(args, name=None):
                 c[k] = getattr(args, k)
         if args.args is not None:
             c["args"] = tuple(args.args)
+    c["ray_order"] = getattr(args, "ray_order", "source-major")
     return c
 
 
@@ -165,6 +169,21 @@ def get_sources(cfg):
     return np.array([[5.0, 3.5, 1.5]]) if cfg["mesh"] == "shoebox" else meshes.sources(cfg["nsrc"])
 
 
+def gen_rays(cfg, world, n, first, threads=None, out=None):
+    """Rays first .. first + n - 1 of the configuration's workload (global ray numbers)."""
+    from hare_b200.harness import rays_from_sources
+    return rays_from_sources(n, get_sources(cfg), stream=cfg["stream"], first=first, threads=threads, out=out,
+                             order=cfg["ray_order"], total=total_rays(cfg, world))
+
+
+def take(a, idx):
+    """Rows idx of a numpy array or a device tensor, as numpy."""
+    if isinstance(a, np.ndarray):
+        return a[idx]
+    import torch
+    return a[torch.from_numpy(idx).to(a.device)].cpu().numpy()
+
+
 def shard(cfg, rank, world):
     """[lo, hi) of the global ray sequence this rank shoots."""
     if cfg["scaling"] == "weak":
@@ -184,10 +203,11 @@ def workload_config(cfg, mesh, world, extra=None):
         w = (f"{cfg['name']}: procedural auditorium hall-{cfg['mesh']} ({mesh.P} polygons), {ctor}, "
              f"{cfg['rays']} rays x {cfg['order']}-order specular chains per GPU")
     else:
-        w = (f"{cfg['name']}: procedural hall {mesh.name} ({mesh.P} polygons), {ctor}, {total_rays(cfg, world)} rays in total, one closest-hit Shoot each, "
-             f"block-sharded over {world} GPU(s)" + (", X_Event rows delivered to rank 0 over NVLink inside the timed region" if world > 1 else ""))
+        w = (f"{cfg['name']}: procedural hall {mesh.name} ({mesh.P} polygons), {ctor}, {total_rays(cfg, world)} rays in total from {cfg['nsrc']} source(s) "
+             f"({cfg['ray_order']} order), one closest-hit Shoot each, block-sharded over {world} GPU(s)" + (", X_Event rows delivered to rank 0 over NVLink inside the timed region" if world > 1 else ""))
     c = {"workload": w, "partition": cfg["part"], "ctor_args": list(cfg["args"]), "polygons": mesh.P,
          "rays_total": total_rays(cfg, world) if cfg["kind"] != "build" else None,
+         "ray_order": cfg["ray_order"] if cfg["kind"] != "build" else None,
          "l2": "ray inputs and event outputs stream through HBM every step (far larger than the 126 MB L2); geometry is re-read from L2/HBM as the walk needs it"}
     if cfg["kind"] == "chain":
         c["order"] = cfg["order"]
@@ -211,23 +231,29 @@ def algorithmic_bytes(counters, shots, part):
 
 
 def cpu_leg(cfg, mesh, o, d, seconds, nthreads):
-    """Time the oracle (C++ restatement of the reference's CPU path) on a bounded sample: the first n rays of the batch."""
+    """Time the oracle (C++ restatement of the reference's CPU path) on a bounded sample of the batch: 64 evenly spaced runs of
+    consecutive rays (every source is in it whatever the ray order), sized for about `seconds` of CPU time."""
+    from hare_b200.harness import sample_blocks
     t0 = time.perf_counter()
     part = oracle_partition(cfg, mesh, nthreads)
     build_s = time.perf_counter() - t0
     n0 = int(min(len(o), max(256, cfg["cpu_min"] // 8)))
     if cfg["kind"] == "chain":
-        run = lambda n: part.reflect_chain(o[:n], d[:n], cfg["order"], events=False, nthreads=nthreads)
+        run = lambda oo, dd: part.reflect_chain(oo, dd, cfg["order"], events=False, nthreads=nthreads)
         shots_of = lambda r: int(r["nshots"].sum())
     else:
-        run = lambda n: part.Shoot(o[:n], d[:n], nthreads=nthreads)
+        run = lambda oo, dd: part.Shoot(oo, dd, nthreads=nthreads)
         shots_of = lambda r: len(r["poly_id"])
-    t0 = time.perf_counter(); r = run(n0); dt = time.perf_counter() - t0
-    per_ray = dt / n0
+    idx = sample_blocks(len(o), n0)
+    oo, dd = np.ascontiguousarray(o[idx]), np.ascontiguousarray(d[idx])
+    t0 = time.perf_counter(); r = run(oo, dd); dt = time.perf_counter() - t0
+    per_ray = dt / max(1, len(idx))
     n = int(min(len(o), cfg["cpu_cap"], max(cfg["cpu_min"], seconds / max(per_ray, 1e-12))))
-    t0 = time.perf_counter(); r = run(n); dt = time.perf_counter() - t0
+    idx = sample_blocks(len(o), n)
+    oo, dd = np.ascontiguousarray(o[idx]), np.ascontiguousarray(d[idx])
+    t0 = time.perf_counter(); r = run(oo, dd); dt = time.perf_counter() - t0
     shots = shots_of(r)
-    return dict(mrays=shots / dt / 1e6, shots=shots, n=n, seconds=dt, build_seconds=build_s, counters=r["counters"], result=r, part=part)
+    return dict(mrays=shots / dt / 1e6, shots=shots, n=len(idx), idx=idx, seconds=dt, build_seconds=build_s, counters=r["counters"], result=r, part=part)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -243,14 +269,23 @@ def run_reference(args):
     world = args.gpus
     if cfg["kind"] == "build":
         return run_reference_build(args, cfg, mesh, cores)
-    from hare_b200.harness import rays_from_sources
+    from hare_b200.harness import sample_rays
     per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     n_gen = int(min(cfg["rays"], cfg["cpu_cap"]))
-    o, d = rays_from_sources(n_gen, get_sources(cfg), stream=cfg["stream"])
+    # a bounded sample of the workload: 64 evenly spaced runs of consecutive rays (every source is in it)
+    _, o, d = sample_rays(total_rays(cfg, world), n_gen, get_sources(cfg), stream=cfg["stream"], order=cfg["ray_order"])
+    n_gen = len(o)
     part = oracle_partition(cfg, mesh, cores)
     chain = cfg["kind"] == "chain"
-    run = (lambda n: int(part.reflect_chain(o[:n], d[:n], cfg["order"], events=False, nthreads=cores)["nshots"].sum())) if chain else \
-          (lambda n: len(part.Shoot(o[:n], d[:n], nthreads=cores)["poly_id"]))
+    picked = {}
+
+    def pick(n):   # n of the sample's rays, again spread over all of it (cached: the copy stays out of the timed steps)
+        if n not in picked:
+            k = max(1, n_gen // max(1, n))
+            picked[n] = (np.ascontiguousarray(o[::k][:n]), np.ascontiguousarray(d[::k][:n]))
+        return picked[n]
+    run = (lambda n: int(part.reflect_chain(*pick(n), cfg["order"], events=False, nthreads=cores)["nshots"].sum())) if chain else \
+          (lambda n: len(part.Shoot(*pick(n), nthreads=cores)["poly_id"]))
     n0 = int(min(n_gen, max(256, cfg["cpu_min"] // 8)))
     t0 = time.perf_counter(); run(n0); dt = time.perf_counter() - t0
     n = int(min(n_gen, max(n0, per_step / (dt / n0))))
@@ -261,7 +296,7 @@ def run_reference(args):
         shots += run(n)
     dt = time.perf_counter() - t0
     val = shots / dt / 1e6
-    sample = (f"first {n} rays" + (f" x {cfg['order']}-order chains" if chain else "") +
+    sample = (f"{n} rays spread evenly over the workload" + (f" x {cfg['order']}-order chains" if chain else "") +
               f" per step ({shots // max(1, args.steps)} Shoots/step) of the {total_rays(cfg, world)}-ray workload")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
@@ -420,7 +455,7 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
     x.pins = []
     # rays of this rank's block, generated straight into page-locked host arrays (the e2e leg shoots from them)
     o = pinned(x, (N, 3), np.float64); d = pinned(x, (N, 3), np.float64)
-    rays_from_sources(N, get_sources(cfg), stream=cfg["stream"], first=lo, threads=x.cores, out=(o, d))
+    gen_rays(cfg, x.world, N, lo, threads=x.cores, out=(o, d))
     if getattr(args, "presort", False):
         a = np.abs(d); face = np.argmax(a, axis=1); sgn = (np.take_along_axis(d, face[:, None], 1)[:, 0] < 0)
         u = np.take_along_axis(d, ((face + 1) % 3)[:, None], 1)[:, 0] / np.take_along_axis(a, face[:, None], 1)[:, 0]
@@ -429,7 +464,8 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
         mort = np.zeros(N, np.int64)
         for b in range(6):
             mort |= ((ui >> b) & 1) << (2 * b) | ((vi >> b) & 1) << (2 * b + 1)
-        src = (np.arange(N) + lo) % max(1, cfg["nsrc"])
+        from hare_b200.harness import source_index
+        src = source_index(np.arange(N) + lo, max(1, cfg["nsrc"]), cfg["ray_order"], total_rays(cfg, x.world))
         key = ((src * 6 + face * 2 + sgn) << 12) | mort
         perm = np.argsort(key, kind="stable")
         o[:] = o[perm]; d[:] = d[perm]
@@ -560,7 +596,7 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
 
     # results of the device leg on the host (rank 0: everything that was delivered to it)
     if chain:
-        dev_res = dict(nshots=nshots.cpu().numpy(), o=fin_o[:cfg["cpu_cap"]].cpu().numpy())
+        dev_res = dict(nshots=nshots.cpu().numpy(), o=fin_o)
     elif peer is not None:
         dev_res = {k: peer.arrays[k].torch() for k in ("poly_id", "t", "xyz", "uv")} if x.rank == 0 else None
     elif x.world > 1:
@@ -646,23 +682,27 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
         cores = os.cpu_count() or 1
         cpu_line, parity = None, None
         # GPU's own walk counters on a sample (nodes/cells entered, list entries scanned, exact tests)
-        ns = min(N, 200_000)
+        from hare_b200.harness import sample_blocks
+        sidx = sample_blocks(N, 200_000)
+        ns = len(sidx)
+        so, sd = np.ascontiguousarray(o[sidx]), np.ascontiguousarray(d[sidx])
         if chain:
-            r = part.Reflect_Chain(o[:ns], d[:ns], order, events=False, counters=True)
+            r = part.Reflect_Chain(so, sd, order, events=False, counters=True)
             gpu_cnt, gpu_shots = r["counters"], r["total_shots"]
         else:
-            r = part.Shoot_Batch(o[:ns], d[:ns], counters=True)
+            r = part.Shoot_Batch(so, sd, counters=True)
             gpu_cnt, gpu_shots = r["counters"], ns
         gpu_bytes, gpu_avg = algorithmic_bytes(gpu_cnt, gpu_shots, cfg["part"])
         if cpu is not None:
             n = cpu["n"]
             ref = cpu["result"]
+            cidx = cpu["idx"]
             if chain:
-                ok = np.array_equal(ref["nshots"], dev_res["nshots"][:n]) and np.array_equal(ref["o"], dev_res["o"][:n])
+                ok = np.array_equal(ref["nshots"], take(dev_res["nshots"], cidx)) and np.array_equal(ref["o"], take(dev_res["o"], cidx))
             else:
-                got = {k: dev_res[k][:n].cpu().numpy() for k in ("poly_id", "t", "xyz", "uv")}
+                got = {k: take(dev_res[k], cidx) for k in ("poly_id", "t", "xyz", "uv")}
                 ok = all(np.array_equal(got[k], ref[k]) for k in (("poly_id", "t", "xyz") if cfg["part"] == "Voxel_Grid" else ("poly_id", "t", "xyz", "uv")))
-            assert ok, f"{cfg['name']}: GPU results differ from the oracle on the first {n} rays"
+            assert ok, f"{cfg['name']}: GPU results differ from the oracle on the {n} sampled rays"
             parity = {"rays_compared": n, "bit_exact": True, "fields": "poly_id, t, X_Point" + ("" if cfg["part"] == "Voxel_Grid" else ", u, v")}
             if x.world > 1 and not chain:
                 # rows that arrived from the OTHER ranks: the first rays of every remote block, re-generated here, against the oracle and
@@ -671,7 +711,7 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
                 checked = 0
                 for r in range(1, x.world):
                     rlo = shard(cfg, r, x.world)[0]
-                    ro, rd = rays_from_sources(m, get_sources(cfg), stream=cfg["stream"], first=rlo, threads=cores)
+                    ro, rd = gen_rays(cfg, x.world, m, rlo, threads=cores)
                     want = cpu["part"].Shoot(ro, rd, nthreads=cores)
                     for k in (("poly_id", "t", "xyz") if cfg["part"] == "Voxel_Grid" else ("poly_id", "t", "xyz", "uv")):
                         assert np.array_equal(dev_res[k][rlo:rlo + m].cpu().numpy(), want[k]), f"{cfg['name']}: rows delivered by rank {r} differ from the oracle ({k})"
@@ -679,7 +719,7 @@ def run_shoot_config(x, args, cfg, steps, warmup, cpu_seconds, do_e2e=True, do_c
                 parity["remote_rows_compared"] = checked
             ref_bytes, ref_avg = algorithmic_bytes(cpu["counters"], cpu["shots"], cfg["part"])
             cpu_line = {"value": cpu["mrays"], "unit": "Mrays/s", "cores": cores, "kind": "port",
-                        "sample": f"first {n} rays" + (f" x {order}-order chains" if chain else "") +
+                        "sample": f"{n} rays in 64 evenly spaced runs" + (f" x {order}-order chains" if chain else "") +
                                   f" ({cpu['shots']} Shoots, {cpu['seconds']:.1f} s) of the {total_rays(cfg, x.world)}-ray workload; "
                                   f"oracle partition build {cpu['build_seconds']:.1f} s not included"}
         else:

@@ -6,4 +6,4 @@ same arrays.
 """
 from .rng import splitmix64, uniform01, unit_directions  # noqa: F401
 from .meshes import shoebox, hall, Mesh  # noqa: F401
-from .rays import rays_from_sources  # noqa: F401
+from .rays import rays_from_sources, sample_blocks, sample_rays, source_index  # noqa: F401
