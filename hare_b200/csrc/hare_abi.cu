@@ -1390,9 +1390,9 @@ static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cu
 
 static const int64_t kChunk = 1 << 20;   // chains per pipelined chunk of hare_reflect_chain
 
-// Chunk sizes of a device's share of a hare_shoot_batch call.  The traversal kernels run faster on larger batches -- the coherence
-// order puts more similar rays next to each other the more rays there are (C3: 606 Mrays/s on 4 M rays, 742 on 16 M, 814 on 64 M) --
-// but what is copied in before the first kernel and out after the last one is not overlapped with anything.  So the chunks start
+// Chunk sizes of a device's share of a hare_shoot_batch call.  A traversal launch has a fixed part of about 2 ms (pool fill and drain
+// at low lane occupancy, the last CTAs, a cold L2: C3 runs 606 Mrays/s on 4 M rays, 742 on 16 M, 814 on 64 M), so few large launches
+// beat many small ones -- but what is copied in before the first kernel and out after the last one is not overlapped with anything.  So the chunks start
 // small (an eighth of the share, 2^18 .. 2^20 rays), grow by half each time up to 2^24 rays, and shrink again the same way towards
 // the end; the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap on the three streams.  (Uniform
 // 4 M-ray chunks: 163 ms for the 100 M rays of C3 where the kernel alone takes 121.)

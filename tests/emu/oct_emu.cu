@@ -20,7 +20,7 @@ struct Stats { double exec[OP_COUNT] = {}, lanes[OP_COUNT] = {}, trips = 0, nste
 
 template <bool CHAIN, int SLOTS, int N_MAX>
 void run(const OctDev& T, int depth, const PolyRec* polys, const double* o, const double* d, const int32_t* o1a, const int32_t* o2a,
-         long long N, int order, const WalkOut& out, int tw, Stats& st, unsigned long long* counters) {
+         long long N, int order, const WalkOut& out, int tw, Stats& st, unsigned long long* counters, uint32_t* ray_steps) {
     std::vector<unsigned char> mem(OctPool<SLOTS>::STRIDE + 64);
     std::vector<double2> fab((size_t)SLOTS * (depth + 1)); std::vector<uint2> fcq((size_t)SLOTS * (depth + 1));
     OctFrames F = { fab.data(), fcq.data(), depth + 1 };
@@ -43,6 +43,7 @@ void run(const OctDev& T, int depth, const PolyRec* polys, const double* o, cons
             int sel[32], cnt = 0;
             for (int s = 0; s < SLOTS && cnt < 32; ++s) if (p.tag[s] == ph) sel[cnt++] = s;
             st.exec[ph] += 1; st.lanes[ph] += cnt; st.trips += 1;
+            if (ray_steps && ph != OP_SF) for (int l = 0; l < cnt; ++l) ++ray_steps[p.U(OU_RAY, sel[l])];   // length of the ray's dependent chain of phase executions
             uint32_t nt[32];
             if (ph == OP_T) {
                 for (int l = 0; l < cnt; ++l) nt[l] = octw_test<true, SLOTS>(T, polys, p, sel[l], out, c);
@@ -84,7 +85,7 @@ extern "C" int oct_emu(const double* verts, const double* normals, const int32_t
                        const double* o, const double* d, const int32_t* o1, const int32_t* o2, int64_t N, int chain, int order,
                        double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
                        int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
-                       int slots, int nmax, int n_warps, int regular_ok, double* stats, unsigned long long* counters) {
+                       int slots, int nmax, int n_warps, int regular_ok, double* stats, unsigned long long* counters, uint32_t* ray_steps) {
     std::vector<PolyRec> recs((size_t)P);
     std::vector<float> pbox6((size_t)P * 6);
     for (int64_t i = 0; i < P; ++i) {
@@ -114,8 +115,8 @@ extern "C" int oct_emu(const double* verts, const double* normals, const int32_t
     T.depth = depth; T.regular = (pk.regular && regular_ok) ? 1 : 0;
     WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
     Stats st;
-#define RUN(S, M) if (slots == S && nmax == M) { if (chain) run<true, S, M>(T, depth, recs.data(), o, d, o1, o2, N, order, out, n_warps, st, counters); \
-                                                 else run<false, S, M>(T, depth, recs.data(), o, d, o1, o2, N, order, out, n_warps, st, counters); ok = 1; }
+#define RUN(S, M) if (slots == S && nmax == M) { if (chain) run<true, S, M>(T, depth, recs.data(), o, d, o1, o2, N, order, out, n_warps, st, counters, ray_steps); \
+                                                 else run<false, S, M>(T, depth, recs.data(), o, d, o1, o2, N, order, out, n_warps, st, counters, ray_steps); ok = 1; }
     int ok = 0;
     RUN(64, 4) RUN(64, 1) RUN(64, 2) RUN(64, 8) RUN(48, 4) RUN(32, 4) RUN(40, 2) RUN(96, 4)
 #undef RUN

@@ -23,7 +23,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, chain=False, order=1, slots=64, nmax=4, n_warps=4, regular=True):
+def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, chain=False, order=1, slots=64, nmax=4, n_warps=4, regular=True, ray_steps=False):
     """topo_arrays = oracle Topology.arrays(); tree_arrays = oracle Octree.arrays() = (box, first_child, list_off, list_cnt, polys)."""
     verts, normals, vcount, _ = topo_arrays
     box, fc, lo, lc, pol = tree_arrays
@@ -37,6 +37,7 @@ def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, chain=False,
     o1 = None if origin1 is None else np.ascontiguousarray(origin1, np.int32)
     o2 = None if origin2 is None else np.ascontiguousarray(origin2, np.int32)
     stats = np.zeros(16); counters = np.zeros(4, np.uint64)
+    steps = np.zeros(N, np.uint32) if ray_steps else None   # per ray: phase executions it took part in (its dependent chain)
     if chain:
         ev_pid = np.zeros((N, order), np.int32); ev_t = np.zeros((N, order)); fo = np.zeros((N, 3)); fd = np.zeros((N, 3))
         ns = np.zeros(N, np.int32); tot = np.zeros(1, np.uint64)
@@ -48,9 +49,11 @@ def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, chain=False,
         res = dict(t=t, xyz=xyz, poly_id=pid, uv=uv, o=om)
     rc = lib().oct_emu(_p(verts), _p(normals), _p(vcount), C.c_int64(len(vcount)), _p(box), _p(fc), _p(lo), _p(lc), _p(pol),
                        C.c_int64(len(fc)), C.c_int64(npol), _p(o), _p(d), _p(o1), _p(o2), C.c_int64(N), int(chain), int(order),
-                       *args, int(slots), int(nmax), int(n_warps), int(regular), _p(stats), _p(counters))
+                       *args, int(slots), int(nmax), int(n_warps), int(regular), _p(stats), _p(counters), _p(steps))
     if rc != 0:
         raise ValueError("oct_emu: unsupported (slots, nmax)")
     res["stats"] = dict(exec=dict(zip(PHASES, stats[0:5])), lanes=dict(zip(PHASES, stats[5:10])), trips=stats[10])
     res["counters"] = counters
+    if ray_steps:
+        res["ray_steps"] = steps
     return res
