@@ -157,8 +157,10 @@ int hare_part_destroy(hare_part_t part);
  *               grid to its entry point (AABB_Main.cs:255-257; Ray is a class, the caller sees it)
  *   counters    HARE_CNT_N totals over the batch (cells or nodes visited, list entries scanned,
  *               polygon tests, hits); costs a little time, pass NULL when not needed.
- * Rays are independent: inside the call a batch of >= 65 536 rays is traversed grouped by origin / direction cell (ray_bin.cuh) and
- * in pipelined chunks on three streams; events are written by ray number, so the caller sees its own order and identical results. */
+ * Rays are independent: inside the call a batch of >= 65 536 rays is traversed grouped by origin / direction cell (ray_bin.cuh), the
+ * warps claim their rays on demand, and the batch is cut into pipelined chunks on three streams (1 M rays growing to 16 M and shrinking
+ * again; device staging of up to 3 x 2^24 rays x 52..136 bytes is allocated on first use and kept with the handle); events are written
+ * by ray number, so the caller sees its own order and identical results whatever the batch size or the rays around a ray. */
 int hare_shoot_batch(hare_part_t part, const double* o, const double* d,
                      const int32_t* origin1, const int32_t* origin2, const int32_t* ray_id, int64_t N,
                      double* t, double* xyz, int32_t* poly_id, double* uv, double* o_moved,
@@ -191,7 +193,7 @@ int hare_reflect_chain_device(hare_part_t part, const double* o, const double* d
 /* ---- host and device buffers for the batched calls --------------------------------- */
 /* Page-locked host memory.  The reference's callers hold managed arrays; C# `fixed` / GCHandle only pins an array for the
  * garbage collector -- it does NOT page-lock it for CUDA, and cudaMemcpyAsync from pageable memory is staged and
- * synchronous, so the two-stream copy/compute pipeline of hare_shoot_batch / hare_reflect_chain degenerates to serial
+ * synchronous, so the three-stream copy/compute pipeline of hare_shoot_batch / hare_reflect_chain degenerates to serial
  * copies.  Either allocate the ray / event arrays here (hare_host_alloc; wrap the pointer in a Span<T> / Memory<T>), or
  * page-lock an existing pinned array for the lifetime of the batches (hare_host_register, after GCHandle.Alloc(Pinned)).
  * hare_host_is_pinned reports how the library sees a pointer (1 page-locked, 0 pageable). */
