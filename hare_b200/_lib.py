@@ -85,6 +85,8 @@ def lib():
     L.hare_shoot_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.hare_reflect_chain.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
     L.hare_reflect_chain_device.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.hare_reflect_chain_events.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.hare_reflect_chain_events_device.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hare_launch_count.restype = u64
     sz = C.c_size_t
     L.hare_host_alloc.argtypes = [sz, pp]

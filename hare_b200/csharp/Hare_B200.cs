@@ -80,6 +80,11 @@ namespace Hare.Geometry.Native
         [DllImport(Lib, CallingConvention = CC)]
         public static extern int hare_reflect_chain(IntPtr part, double[] o, double[] d, long N, int order, int[] ev_poly_id, double[] ev_t,
                                                     double[] fin_o, double[] fin_d, int[] nshots, out ulong total_shots, ulong[] counters);
+        // + per-bounce X_Point (N x order x 3) and u, v (N x order x 2); any event array may be null
+        [DllImport(Lib, CallingConvention = CC)]
+        public static extern int hare_reflect_chain_events(IntPtr part, double[] o, double[] d, long N, int order, int[] ev_poly_id, double[] ev_t,
+                                                           double[] ev_xyz, double[] ev_uv, double[] fin_o, double[] fin_d, int[] nshots,
+                                                           out ulong total_shots, ulong[] counters);
 
         public static void Check(int rc, string what)
         {

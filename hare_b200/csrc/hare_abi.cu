@@ -133,6 +133,7 @@ struct PartDev {
     // chain staging
     int64_t ccap = 0, celems = 0;
     int32_t* c_evpid[kStreams] = {}; double* c_evt[kStreams] = {}; int32_t* c_ns[kStreams] = {};
+    double* c_evxyz[kStreams] = {}; double* c_evuv[kStreams] = {}; int64_t cxyz = 0, cuv = 0;   // per-bounce X_Point / u, v rows (elements of capacity)
     unsigned long long* counters = nullptr;   // 4 counters + total_shots
     size_t bytes = 0;
 };
@@ -154,7 +155,7 @@ static void free_partdev(PartDev& d) {
     for (int s = 0; s < kStreams; ++s) {
         cudaFree(d.s_o[s]); cudaFree(d.s_d[s]); cudaFree(d.s_t[s]); cudaFree(d.s_xyz[s]); cudaFree(d.s_uv[s]); cudaFree(d.s_om[s]);
         cudaFree(d.s_o1[s]); cudaFree(d.s_o2[s]); cudaFree(d.s_rid[s]); cudaFree(d.s_pid[s]);
-        cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]);
+        cudaFree(d.c_evpid[s]); cudaFree(d.c_evt[s]); cudaFree(d.c_ns[s]); cudaFree(d.c_evxyz[s]); cudaFree(d.c_evuv[s]);
         if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
     }
     cudaFree(d.cells); cudaFree(d.cell_poly); cudaFree(d.list_box); cudaFree(d.occp); cudaFree(d.occ); cudaFree(d.cell_offset); cudaFree(d.nodes); cudaFree(d.kd_hot); cudaFree(d.kd_wide); cudaFree(d.lists); cudaFree(d.cbox); cudaFree(d.gbox); cudaFree(d.tbox); cudaFree(d.nbox); cudaFree(d.pbox); cudaFree(d.ref_box); cudaFree(d.counters);
@@ -208,6 +209,25 @@ static int ensure_chain_staging(PartDev& d, int64_t n, int order) {
         CK(dmalloc(&d.c_evpid[s], (size_t)n * order)); CK(dmalloc(&d.c_evt[s], (size_t)n * order)); CK(dmalloc(&d.c_ns[s], n));
     }
     d.ccap = n; d.celems = n * order;
+    return HARE_OK;
+}
+
+// staging for the optional per-bounce X_Point (3 doubles) / u, v (2 doubles) rows of n chains x order bounces
+static int ensure_chain_rows(PartDev& d, int64_t n, int order, bool xyz, bool uv) {
+    CK(cudaSetDevice(d.dev));
+    const int64_t rows = n * order;
+    if (xyz && 3 * rows > d.cxyz) {
+        for (int s = 0; s < kStreams; ++s) { cudaFree(d.c_evxyz[s]); d.c_evxyz[s] = nullptr; }
+        d.cxyz = 0;
+        for (int s = 0; s < kStreams; ++s) CK(dmalloc(&d.c_evxyz[s], (size_t)(3 * rows)));
+        d.cxyz = 3 * rows;
+    }
+    if (uv && 2 * rows > d.cuv) {
+        for (int s = 0; s < kStreams; ++s) { cudaFree(d.c_evuv[s]); d.c_evuv[s] = nullptr; }
+        d.cuv = 0;
+        for (int s = 0; s < kStreams; ++s) CK(dmalloc(&d.c_evuv[s], (size_t)(2 * rows)));
+        d.cuv = 2 * rows;
+    }
     return HARE_OK;
 }
 
@@ -1341,7 +1361,7 @@ static int launch_shoot(hare_part_s* p, const PartDev& d, const ShootArgs& a, cu
     uint32_t* perm = nullptr;
     int rc = bin_rays(p, d, a.o, a.d, a.N, st, &perm);
     if (rc) return rc;
-    WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters };
+    WalkOut w = { a.t, a.xyz, a.pid, a.uv, a.om, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.counters, nullptr, nullptr };
     switch (p->kind) {
         case HARE_VOXEL_GRID:
             rc = launch_vg_walk<false>(make_vgrid(p, d), d, a.o, a.d, a.o1, a.o2, a.rid, a.N, 1, perm, w, st);
@@ -1366,22 +1386,23 @@ struct ChainArgs {
     const double *o, *d; int64_t N; int order;
     int32_t* ev_pid; double* ev_t; double *fin_o, *fin_d; int32_t* nshots;
     unsigned long long *total, *counters;
+    double *ev_xyz, *ev_uv;
 };
 
 static int launch_chain(hare_part_s* p, const PartDev& d, const ChainArgs& a, cudaStream_t st) {
     switch (p->kind) {
         case HARE_VOXEL_GRID: {
-            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
+            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters, a.ev_xyz, a.ev_uv };
             return launch_vg_walk<true>(make_vgrid(p, d), d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, nullptr, w, st);
         }
         case HARE_OCTREE: {
             OctDev t = { (const OctNode*)d.nodes, d.lists, d.cbox, d.gbox, d.pbox, d.nbox, p->oct.depth, p->oct_regular ? 1 : 0 };
-            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
+            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters, a.ev_xyz, a.ev_uv };
             return launch_oct_walk<true>(t, d, a.o, a.d, nullptr, nullptr, a.N, a.order, nullptr, w, st);
         }
         case HARE_KDTREE: {
             KdDev t = { d.kd_wide, d.kd_hot, (const KdNode*)d.nodes, d.lists, d.tbox, p->kd.depth, d.ref_box };
-            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters };
+            WalkOut w = { nullptr, nullptr, nullptr, nullptr, nullptr, a.ev_pid, a.ev_t, a.fin_o, a.fin_d, a.nshots, a.total, a.counters, a.ev_xyz, a.ev_uv };
             return launch_kd_walk<true>(t, d, a.o, a.d, nullptr, nullptr, nullptr, a.N, a.order, nullptr, w, st);
         }
     }
@@ -1508,11 +1529,17 @@ extern "C" int hare_shoot_batch_device(hare_part_t p, const double* o, const dou
 extern "C" int hare_reflect_chain(hare_part_t p, const double* o, const double* d, int64_t N, int order,
                                   int32_t* ev_poly_id, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots,
                                   uint64_t* total_shots, uint64_t* counters) {
+    return hare_reflect_chain_events(p, o, d, N, order, ev_poly_id, ev_t, nullptr, nullptr, fin_o, fin_d, nshots, total_shots, counters);
+}
+
+extern "C" int hare_reflect_chain_events(hare_part_t p, const double* o, const double* d, int64_t N, int order,
+                                         int32_t* ev_poly_id, double* ev_t, double* ev_xyz, double* ev_uv, double* fin_o, double* fin_d,
+                                         int32_t* nshots, uint64_t* total_shots, uint64_t* counters) {
     if (!p || N < 0 || order < 1 || (N && (!o || !d))) return fail(HARE_ERR_INVALID, "hare_reflect_chain: bad argument");
     std::lock_guard<std::mutex> lk(p->mu);
     const int G = (int)p->dev.size();
     if (G == 0) return fail(HARE_ERR_CUDA, "hare_reflect_chain: host-only handle, no CUDA device (hare_b200 has no CPU fallback)");
-    const bool events = ev_poly_id || ev_t;
+    const bool events = ev_poly_id || ev_t || ev_xyz || ev_uv;
     const int64_t chunk = events ? std::max<int64_t>(1024, kChunk / order) : kChunk;
     if (counters) std::memset(counters, 0, HARE_CNT_N * sizeof(uint64_t));
     if (total_shots) *total_shots = 0;
@@ -1525,6 +1552,7 @@ extern "C" int hare_reflect_chain(hare_part_t p, const double* o, const double* 
             if (rc) return rc;
             if (events) { rc = ensure_chain_staging(dv, std::min<int64_t>(chunk, r1 - r0), order); if (rc) return rc; }
             else if (nshots) { rc = ensure_chain_staging(dv, std::min<int64_t>(chunk, r1 - r0), 1); if (rc) return rc; }
+            if (ev_xyz || ev_uv) { rc = ensure_chain_rows(dv, std::min<int64_t>(chunk, r1 - r0), order, ev_xyz != nullptr, ev_uv != nullptr); if (rc) return rc; }
             CKS(cudaSetDevice(dv.dev));
             CKS(cudaMemsetAsync(dv.counters, 0, 8 * sizeof(unsigned long long), dv.stream[0]));
             CKS(cudaStreamSynchronize(dv.stream[0]));
@@ -1536,9 +1564,11 @@ extern "C" int hare_reflect_chain(hare_part_t p, const double* o, const double* 
                 CKS(cudaMemcpyAsync(dv.s_d[s], d + 3 * c0, n * 24, cudaMemcpyHostToDevice, st));
                 ChainArgs a = { dv.s_o[s], dv.s_d[s], n, order, ev_poly_id ? dv.c_evpid[s] : nullptr, ev_t ? dv.c_evt[s] : nullptr,
                                 fin_o ? dv.s_xyz[s] : nullptr, fin_d ? dv.s_om[s] : nullptr, nshots ? dv.c_ns[s] : nullptr,
-                                dv.counters + 4, counters ? dv.counters : nullptr };
+                                dv.counters + 4, counters ? dv.counters : nullptr, ev_xyz ? dv.c_evxyz[s] : nullptr, ev_uv ? dv.c_evuv[s] : nullptr };
                 int rc2 = launch_chain(p, dv, a, st);
                 if (rc2) return rc2;
+                if (ev_xyz) CKS(cudaMemcpyAsync(ev_xyz + 3 * c0 * order, dv.c_evxyz[s], (size_t)n * order * 24, cudaMemcpyDeviceToHost, st));
+                if (ev_uv) CKS(cudaMemcpyAsync(ev_uv + 2 * c0 * order, dv.c_evuv[s], (size_t)n * order * 16, cudaMemcpyDeviceToHost, st));
                 if (ev_poly_id) CKS(cudaMemcpyAsync(ev_poly_id + c0 * order, dv.c_evpid[s], (size_t)n * order * 4, cudaMemcpyDeviceToHost, st));
                 if (ev_t) CKS(cudaMemcpyAsync(ev_t + c0 * order, dv.c_evt[s], (size_t)n * order * 8, cudaMemcpyDeviceToHost, st));
                 if (fin_o) CKS(cudaMemcpyAsync(fin_o + 3 * c0, dv.s_xyz[s], n * 24, cudaMemcpyDeviceToHost, st));
@@ -1566,11 +1596,19 @@ extern "C" int hare_reflect_chain(hare_part_t p, const double* o, const double* 
 extern "C" int hare_reflect_chain_device(hare_part_t p, const double* o, const double* d, int64_t N, int order,
                                          int32_t* ev_poly_id, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots,
                                          uint64_t* total_shots_device, uint64_t* counters_device, void* cuda_stream) {
+    return hare_reflect_chain_events_device(p, o, d, N, order, ev_poly_id, ev_t, nullptr, nullptr, fin_o, fin_d, nshots, total_shots_device,
+                                            counters_device, cuda_stream);
+}
+
+extern "C" int hare_reflect_chain_events_device(hare_part_t p, const double* o, const double* d, int64_t N, int order,
+                                                int32_t* ev_poly_id, double* ev_t, double* ev_xyz, double* ev_uv, double* fin_o, double* fin_d,
+                                                int32_t* nshots, uint64_t* total_shots_device, uint64_t* counters_device, void* cuda_stream) {
     if (!p || N < 0 || order < 1 || (N && (!o || !d)) || !total_shots_device) return fail(HARE_ERR_INVALID, "hare_reflect_chain_device: bad argument");
     if (p->dev.size() != 1) return fail(p->dev.empty() ? HARE_ERR_CUDA : HARE_ERR_INVALID, "hare_reflect_chain_device: needs a single-device partition handle");
     PartDev& dv = p->dev[0];
     CK(cudaSetDevice(dv.dev));
-    ChainArgs a = { o, d, N, order, ev_poly_id, ev_t, fin_o, fin_d, nshots, (unsigned long long*)total_shots_device, (unsigned long long*)counters_device };
+    ChainArgs a = { o, d, N, order, ev_poly_id, ev_t, fin_o, fin_d, nshots, (unsigned long long*)total_shots_device, (unsigned long long*)counters_device,
+                    ev_xyz, ev_uv };
     return launch_chain(p, dv, a, cuda_stream ? (cudaStream_t)cuda_stream : dv.stream[0]);
 }
 

@@ -150,6 +150,8 @@ HD void kdw_finish(const PolyRec* __restrict__ polys, const KdPool<SLOTS>& p, in
         ++shots;
         if (out.ev_pid) out.ev_pid[ray * order + bounce] = h ? pid : -1;
         if (out.ev_t) out.ev_t[ray * order + bounce] = h ? closest : 0.0;
+        chain_row_xyz(out, ray, order, bounce, h, bx, by, bz);
+        chain_row_uv(out, ray, order, bounce, h ? p.D(KD_EU, s) : 0.0, h ? p.D(KD_EV, s) : 0.0);
         ++bounce;
         bool go_on = false;
         if (h) {
@@ -169,6 +171,7 @@ HD void kdw_finish(const PolyRec* __restrict__ polys, const KdPool<SLOTS>& p, in
                 if (out.ev_pid) out.ev_pid[ray * order + q] = -3;
                 if (out.ev_t) out.ev_t[ray * order + q] = 0;
             }
+            chain_rows_clear(out, ray, order, (int)bounce);
             if (out.fin_o) { out.fin_o[3 * ray] = R.x; out.fin_o[3 * ray + 1] = R.y; out.fin_o[3 * ray + 2] = R.z; }
             if (out.fin_d) { out.fin_d[3 * ray] = R.dx; out.fin_d[3 * ray + 1] = R.dy; out.fin_d[3 * ray + 2] = R.dz; }
             if (out.nshots) out.nshots[ray] = (int32_t)bounce;

@@ -212,6 +212,8 @@ HD void octw_finish(const PolyRec* __restrict__ polys, const OctPool<SLOTS>& p, 
         ++shots;
         if (out.ev_pid) out.ev_pid[ray * order + bounce] = h ? pid : -1;
         if (out.ev_t) out.ev_t[ray * order + bounce] = h ? closest : 0.0;
+        chain_row_xyz(out, ray, order, bounce, h, bx, by, bz);
+        if (!h) chain_row_uv(out, ray, order, bounce, 0.0, 0.0);               // a hit's u, v were written by the test that found it
         ++bounce;
         bool go_on = false;
         if (h) {
@@ -231,6 +233,7 @@ HD void octw_finish(const PolyRec* __restrict__ polys, const OctPool<SLOTS>& p, 
                 if (out.ev_pid) out.ev_pid[ray * order + q] = -3;
                 if (out.ev_t) out.ev_t[ray * order + q] = 0;
             }
+            chain_rows_clear(out, ray, order, (int)bounce);
             if (out.fin_o) { out.fin_o[3 * ray] = R.x; out.fin_o[3 * ray + 1] = R.y; out.fin_o[3 * ray + 2] = R.z; }
             if (out.fin_d) { out.fin_d[3 * ray] = R.dx; out.fin_d[3 * ray + 1] = R.dy; out.fin_d[3 * ray + 2] = R.dz; }
             if (out.nshots) out.nshots[ray] = (int32_t)bounce;
@@ -488,8 +491,8 @@ HD uint32_t octw_cull(const OctDev& T, const OctPool<SLOTS>& p, int s, CntT<COUN
 }
 
 // ---- T: one exact FP64 test (slow path: u, v) of the lowest surviving entry
-template <bool COUNT, int SLOTS>
-HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const OctPool<SLOTS>& p, int s, const WalkOut& out, CntT<COUNT>& c) {
+template <bool CHAIN, bool COUNT, int SLOTS>
+HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const OctPool<SLOTS>& p, int s, int order, const WalkOut& out, CntT<COUNT>& c) {
     uint32_t masks = p.U(OU_MASKS, s);
     uint32_t bmask = (masks >> 16) & 0xffu;
     const int k = hare_ffs(bmask) - 1;                // lowest survivor first: stored list order
@@ -513,6 +516,7 @@ HD uint32_t octw_test(const OctDev& T, const PolyRec* __restrict__ polys, const 
     if (h && t > 0.0000000001 && t < p.D(OD_CLOSEST, s)) {
         p.D(OD_CLOSEST, s) = t; p.U(OU_PID, s) = pend;
         if (out.uv) { const long long ray = (long long)p.U(OU_RAY, s); out.uv[2 * ray] = u; out.uv[2 * ray + 1] = v; }
+        if (CHAIN && out.ev_uv) chain_row_uv(out, (long long)p.U(OU_RAY, s), order, p.U(OU_FLAGS, s) >> OFL_BOUNCE_SHIFT, u, v);
         fl |= OFL_HIT;
         if (t <= p.D(OD_CA, s)) fl |= FIN_HIT << OFL_FIN_SHIFT;            // early return :233-237 (CA = this leaf's nodeTmin)
         p.U(OU_FLAGS, s) = fl;
@@ -585,7 +589,7 @@ oct_wave_kernel(const OctDev T, const OctFrames F, const PolyRec* __restrict__ p
         // 4. run it
         uint32_t nt = OP_DONE;
         if (ph == OP_T) {
-            if (act) nt = octw_test<COUNT, SLOTS>(T, polys, p, s, out, c);
+            if (act) nt = octw_test<CHAIN, COUNT, SLOTS>(T, polys, p, s, order, out, c);
         } else if (ph == OP_C) {
             if (act) nt = octw_cull<COUNT, SLOTS>(T, p, s, c);
         } else if (ph == OP_G) {

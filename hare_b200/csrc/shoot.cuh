@@ -204,7 +204,24 @@ struct WalkOut {
     int32_t* __restrict__ ev_pid; double* __restrict__ ev_t; double* __restrict__ fin_o; double* __restrict__ fin_d;                   // chain
     int32_t* __restrict__ nshots; unsigned long long* __restrict__ total_shots;
     unsigned long long* __restrict__ counters;
+    double* __restrict__ ev_xyz; double* __restrict__ ev_uv;   // chain: per-bounce X_Point (N x order x 3) and u, v (N x order x 2), optional
 };
+
+// Per-bounce X_Point / (u, v) rows of a chain.  Row `bounce` of chain `ray`; a miss writes zeros like X_Event() does; rows of Shoots
+// that never happen (the chain ended) are zeroed by chain_rows_clear.
+HD void chain_row_xyz(const WalkOut& out, long long ray, int order, uint32_t bounce, bool h, double x, double y, double z) {
+    if (!out.ev_xyz) return;
+    double* q = out.ev_xyz + 3 * (ray * order + (long long)bounce);
+    q[0] = h ? x : 0.0; q[1] = h ? y : 0.0; q[2] = h ? z : 0.0;
+}
+HD void chain_row_uv(const WalkOut& out, long long ray, int order, uint32_t bounce, double u, double v) {
+    if (!out.ev_uv) return;
+    double* q = out.ev_uv + 2 * (ray * order + (long long)bounce);
+    q[0] = u; q[1] = v;
+}
+HD void chain_rows_clear(const WalkOut& out, long long ray, int order, int from) {
+    for (int q = from; q < order; ++q) { chain_row_xyz(out, ray, order, (uint32_t)q, false, 0, 0, 0); chain_row_uv(out, ray, order, (uint32_t)q, 0.0, 0.0); }
+}
 
 #if defined(__CUDACC__)
 // per-warp reduction of the walk counters into counters[0..3] (cells or nodes, entries, tests, hits)

@@ -131,6 +131,8 @@ HD void wave_finish(const PolyRec* __restrict__ polys, const WavePool<SLOTS>& p,
         ++shots;
         if (out.ev_pid) out.ev_pid[ray * order + bounce] = ev_p;
         if (out.ev_t) out.ev_t[ray * order + bounce] = ev_t;
+        chain_row_xyz(out, ray, order, bounce, fin == FIN_HIT, bx, by, bz);
+        chain_row_uv(out, ray, order, bounce, 0.0, 0.0);                       // Voxel_Grid events carry u = v = 0 (Voxel_Grid.cs:487-488)
         ++bounce;
         bool go_on = false;
         if (fin == FIN_HIT) {
@@ -150,6 +152,7 @@ HD void wave_finish(const PolyRec* __restrict__ polys, const WavePool<SLOTS>& p,
                 if (out.ev_pid) out.ev_pid[ray * order + q] = -3;
                 if (out.ev_t) out.ev_t[ray * order + q] = 0;
             }
+            chain_rows_clear(out, ray, order, (int)bounce);
             if (out.fin_o) { out.fin_o[3 * ray] = R.x; out.fin_o[3 * ray + 1] = R.y; out.fin_o[3 * ray + 2] = R.z; }
             if (out.fin_d) { out.fin_d[3 * ray] = R.dx; out.fin_d[3 * ray + 1] = R.dy; out.fin_d[3 * ray + 2] = R.dz; }
             if (out.nshots) out.nshots[ray] = (int32_t)bounce;

@@ -194,17 +194,22 @@ class Spatial_Partition:
             out["counters"] = cnt
         return out
 
-    def Reflect_Chain(self, o, d, order, events=True, counters=False):
-        """Specular chains of `order` Shoots kept on the device (harness op)."""
+    def Reflect_Chain(self, o, d, order, events=True, counters=False, points=False):
+        """Specular chains of `order` Shoots kept on the device (harness op, SURVEY.md 8(d) C2).  events: per-bounce Poly_id and t;
+        points: also per-bounce X_Point (N, order, 3) and u, v (N, order, 2) -- the rest of every bounce's X_Event."""
         o = as_f64(o).reshape(-1, 3); d = as_f64(d).reshape(-1, 3)
         N = o.shape[0]
         evp = np.empty((N, order), np.int32) if events else None
         evt = np.empty((N, order)) if events else None
+        evx = np.empty((N, order, 3)) if points else None
+        evu = np.empty((N, order, 2)) if points else None
         fo = np.empty((N, 3)); fd = np.empty((N, 3)); ns = np.empty(N, np.int32)
         tot = C.c_uint64(); cnt = np.zeros(4, np.uint64) if counters else None
-        check(_lib.lib().hare_reflect_chain(self._h, ptr(o), ptr(d), N, order, ptr(evp), ptr(evt), ptr(fo), ptr(fd), ptr(ns), C.byref(tot), ptr(cnt)),
-              "hare_reflect_chain")
+        check(_lib.lib().hare_reflect_chain_events(self._h, ptr(o), ptr(d), N, order, ptr(evp), ptr(evt), ptr(evx), ptr(evu), ptr(fo), ptr(fd), ptr(ns),
+                                                   C.byref(tot), ptr(cnt)), "hare_reflect_chain_events")
         out = dict(ev_poly_id=evp, ev_t=evt, o=fo, d=fd, nshots=ns, total_shots=tot.value)
+        if points:
+            out["ev_xyz"] = evx; out["ev_uv"] = evu
         if counters:
             out["counters"] = cnt
         return out

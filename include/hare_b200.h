@@ -189,6 +189,16 @@ int hare_reflect_chain(hare_part_t part, const double* o, const double* d, int64
 int hare_reflect_chain_device(hare_part_t part, const double* o, const double* d, int64_t N, int order,
                               int32_t* ev_poly_id, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots,
                               uint64_t* total_shots_device, uint64_t* counters_device, void* cuda_stream);
+/* The same with the rest of every bounce's X_Event as streams: ev_xyz N x order x 3 = X_Point
+ * (Primitives.cs:435-481; the next segment starts there), ev_uv N x order x 2 = u, v (0 for Voxel_Grid, Voxel_Grid.cs:487-488).
+ * Either may be NULL; rows of a miss and of Shoots that never happened are 0.  24 + 16 bytes per Shoot on top of the 12 of
+ * ev_poly_id / ev_t: with host buffers these streams are what the call's time goes into (PCIe). */
+int hare_reflect_chain_events(hare_part_t part, const double* o, const double* d, int64_t N, int order,
+                              int32_t* ev_poly_id, double* ev_t, double* ev_xyz, double* ev_uv, double* fin_o, double* fin_d,
+                              int32_t* nshots, uint64_t* total_shots, uint64_t* counters);
+int hare_reflect_chain_events_device(hare_part_t part, const double* o, const double* d, int64_t N, int order,
+                                     int32_t* ev_poly_id, double* ev_t, double* ev_xyz, double* ev_uv, double* fin_o, double* fin_d,
+                                     int32_t* nshots, uint64_t* total_shots_device, uint64_t* counters_device, void* cuda_stream);
 
 /* ---- host and device buffers for the batched calls --------------------------------- */
 /* Page-locked host memory.  The reference's callers hold managed arrays; C# `fixed` / GCHandle only pins an array for the

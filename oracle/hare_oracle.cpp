@@ -843,7 +843,8 @@ static void shoot_range(const Partition* part, int64_t i0, int64_t i1, double* o
 // Harness-defined specular chain (Hare itself has no reflection):
 //   n = Normal[poly]; k = 2*((dx*nx)+(dy*ny)+(dz*nz)); d' = d - k*n; o' = X_Point; poly_origin1 = poly
 static void chain_range(const Partition* part, int64_t i0, int64_t i1, const double* o, const double* d, int order,
-                        int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nb, Counters& c) {
+                        int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nb, Counters& c,
+                        double* ev_xyz = nullptr, double* ev_uv = nullptr) {
     std::vector<int32_t> mailbox(part->T->P, 0);
     const Topology& T = *part->T;
     for (int64_t i = i0; i < i1; ++i) {
@@ -855,6 +856,8 @@ static void chain_range(const Partition* part, int64_t i0, int64_t i1, const dou
             int st = part->Shoot(R, ev, o1, -1, mailbox.data(), c);
             if (ev_pid) ev_pid[i * order + b] = (st == -2) ? -2 : ev.Poly_id;
             if (ev_t) ev_t[i * order + b] = ev.t;
+            if (ev_xyz) { double* q = ev_xyz + 3 * (i * order + b); q[0] = ev.X.x; q[1] = ev.X.y; q[2] = ev.X.z; }   // X_Point (0 on a miss)
+            if (ev_uv) { double* q = ev_uv + 2 * (i * order + b); q[0] = ev.u; q[1] = ev.v; }
             if (st != 1) { ++b; break; }
             const double* N = T.NV(ev.Poly_id);
             double k = 2 * ((R.dx * N[0]) + (R.dy * N[1]) + (R.dz * N[2]));
@@ -864,6 +867,8 @@ static void chain_range(const Partition* part, int64_t i0, int64_t i1, const dou
         }
         if (ev_pid) for (int q = b; q < order; ++q) ev_pid[i * order + q] = -3;   // not shot
         if (ev_t) for (int q = b; q < order; ++q) ev_t[i * order + q] = 0;
+        if (ev_xyz) for (int q = 3 * b; q < 3 * order; ++q) ev_xyz[3 * i * order + q] = 0;
+        if (ev_uv) for (int q = 2 * b; q < 2 * order; ++q) ev_uv[2 * i * order + q] = 0;
         if (fin_o) { fin_o[3 * i] = R.x; fin_o[3 * i + 1] = R.y; fin_o[3 * i + 2] = R.z; }
         if (fin_d) { fin_d[3 * i] = R.dx; fin_d[3 * i + 1] = R.dy; fin_d[3 * i + 2] = R.dz; }
         if (nb) nb[i] = b;   // number of Shoot calls made for this chain
@@ -982,6 +987,17 @@ void ho_reflect_chain(void* part, int64_t N, const double* o, const double* d, i
     Counters tot;
     par_for(N, nthreads, &tot, [&](int64_t i0, int64_t i1, Counters& c) {
         chain_range((Partition*)part, i0, i1, o, d, order, ev_pid, ev_t, fin_o, fin_d, nbounce, c);
+    });
+    if (counters) { counters[0] = tot.cells; counters[1] = tot.entries; counters[2] = tot.tests; counters[3] = tot.hits; }
+}
+
+// the same with the per-bounce X_Point (N x order x 3) and u, v (N x order x 2) streams
+void ho_reflect_chain_events(void* part, int64_t N, const double* o, const double* d, int order,
+                             int32_t* ev_pid, double* ev_t, double* ev_xyz, double* ev_uv, double* fin_o, double* fin_d, int32_t* nbounce,
+                             uint64_t* counters, int nthreads) {
+    Counters tot;
+    par_for(N, nthreads, &tot, [&](int64_t i0, int64_t i1, Counters& c) {
+        chain_range((Partition*)part, i0, i1, o, d, order, ev_pid, ev_t, fin_o, fin_d, nbounce, c, ev_xyz, ev_uv);
     });
     if (counters) { counters[0] = tot.cells; counters[1] = tot.entries; counters[2] = tot.tests; counters[3] = tot.hits; }
 }

@@ -60,6 +60,7 @@ def lib():
         L.ho_partition_free.argtypes = [vp]
         L.ho_shoot.argtypes = [vp, i64, _d, _d, vp, vp, vp, _d, _d, _i32, vp, vp, i32]
         L.ho_reflect_chain.argtypes = [vp, i64, _d, _d, i32, vp, vp, vp, vp, vp, vp, i32]
+        L.ho_reflect_chain_events.argtypes = [vp, i64, _d, _d, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32]
         L.ho_poly_box_overlap.argtypes = [_d, _d, _d, i32]
         L.ho_round15.restype = dbl
         L.ho_round15.argtypes = [dbl]
@@ -138,13 +139,19 @@ class _Partition:
         lib().ho_shoot(self._h, N, o.reshape(-1), d.reshape(-1), _p(o1), _p(o2), _p(rid), t, xyz.reshape(-1), pid, _p(uv), _p(cnt), nthreads)
         return dict(t=t, xyz=xyz, poly_id=pid, uv=uv, o=o, counters=cnt)
 
-    def reflect_chain(self, o, d, order, events=True, nthreads=1):
+    def reflect_chain(self, o, d, order, events=True, nthreads=1, points=False):
+        """points=True adds the per-bounce X_Point (N, order, 3) and u, v (N, order, 2) streams."""
         o = np.ascontiguousarray(o, np.float64).reshape(-1, 3)
         d = np.ascontiguousarray(d, np.float64).reshape(-1, 3)
         N = o.shape[0]
         ev_pid = np.zeros((N, order), np.int32) if events else None
         ev_t = np.zeros((N, order)) if events else None
         fo = np.zeros((N, 3)); fd = np.zeros((N, 3)); nb = np.zeros(N, np.int32); cnt = np.zeros(4, np.uint64)
+        if points:
+            ev_xyz = np.full((N, order, 3), np.nan); ev_uv = np.full((N, order, 2), np.nan)
+            lib().ho_reflect_chain_events(self._h, N, o.reshape(-1), d.reshape(-1), order, _p(ev_pid), _p(ev_t), _p(ev_xyz), _p(ev_uv), _p(fo), _p(fd),
+                                          _p(nb), _p(cnt), nthreads)
+            return dict(ev_poly_id=ev_pid, ev_t=ev_t, ev_xyz=ev_xyz, ev_uv=ev_uv, o=fo, d=fd, nshots=nb, counters=cnt)
         lib().ho_reflect_chain(self._h, N, o.reshape(-1), d.reshape(-1), order, _p(ev_pid), _p(ev_t), _p(fo), _p(fd), _p(nb), _p(cnt), nthreads)
         return dict(ev_poly_id=ev_pid, ev_t=ev_t, o=fo, d=fd, nshots=nb, counters=cnt)
 

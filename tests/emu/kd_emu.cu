@@ -77,7 +77,8 @@ extern "C" int kd_emu(const double* verts, const double* normals, const int32_t*
                       const double* o, const double* d, const int32_t* o1, const int32_t* o2, const int32_t* rid, int64_t N, int chain, int order,
                       double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
                       int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
-                      int slots, int nmax, int n_warps, int tie_rule_on_tight_boxes, double* stats, unsigned long long* counters) {
+                      int slots, int nmax, int n_warps, int tie_rule_on_tight_boxes, double* stats, unsigned long long* counters,
+                        double* ev_xyz, double* ev_uv /* chain: per-bounce X_Point / u, v rows, optional */) {
     std::vector<PolyRec> recs((size_t)P);
     HostTopo M;
     M.P = P; M.verts.assign(verts, verts + 12 * P); M.vcount.assign(vcount, vcount + P);
@@ -110,7 +111,7 @@ extern "C" int kd_emu(const double* verts, const double* normals, const int32_t*
         for (const KdNode& n : nodes) { const double b[6] = { n.mnx, n.mny, n.mnz, n.mxx, n.mxy, n.mxz }; tightbox.insert(tightbox.end(), b, b + 6); }
         T.ref_box = tightbox.data();
     }
-    WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
+    WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr, ev_xyz, ev_uv };
     Stats st;
 #define RUN(S, M) if (slots == S && nmax == M) { if (chain) run<true, S, M>(T, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, st, counters); \
                                                  else run<false, S, M>(T, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, st, counters); ok = 1; }

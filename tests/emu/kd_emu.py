@@ -44,15 +44,17 @@ def run(topo_arrays, tree_arrays, o, d, origin1=None, origin2=None, ray_id=None,
     if chain:
         ev_pid = np.zeros((N, order), np.int32); ev_t = np.zeros((N, order)); fo = np.zeros((N, 3)); fd = np.zeros((N, 3))
         ns = np.zeros(N, np.int32); tot = np.zeros(1, np.uint64)
+        ev_xyz = np.full((N, order, 3), np.nan); ev_uv = np.full((N, order, 2), np.nan)     # every row must be written
         args = [None] * 5 + [_p(ev_pid), _p(ev_t), _p(fo), _p(fd), _p(ns), _p(tot)]
-        res = dict(ev_poly_id=ev_pid, ev_t=ev_t, o=fo, d=fd, nshots=ns, total=tot)
+        res = dict(ev_poly_id=ev_pid, ev_t=ev_t, ev_xyz=ev_xyz, ev_uv=ev_uv, o=fo, d=fd, nshots=ns, total=tot)
     else:
         t = np.zeros(N); xyz = np.zeros((N, 3)); pid = np.zeros(N, np.int32); uv = np.ones((N, 2)); om = np.zeros((N, 3))
         args = [_p(t), _p(xyz), _p(pid), _p(uv), _p(om)] + [None] * 6
+        ev_xyz = ev_uv = None
         res = dict(t=t, xyz=xyz, poly_id=pid, uv=uv, o=om)
     rc = lib().kd_emu(_p(verts), _p(normals), _p(vcount), C.c_int64(len(vcount)), _p(box), _p(sp), _p(ax), _p(le), _p(lo), _p(lc), _p(pol),
                       C.c_int64(len(le)), C.c_int64(npol), _p(o), _p(d), _p(o1), _p(o2), _p(rid), C.c_int64(N), int(chain), int(order),
-                      *args, int(slots), int(nmax), int(n_warps), int(tie_rule_on_tight_boxes), _p(stats), _p(counters))
+                      *args, int(slots), int(nmax), int(n_warps), int(tie_rule_on_tight_boxes), _p(stats), _p(counters), _p(ev_xyz), _p(ev_uv))
     if rc != 0:
         raise ValueError("kd_emu: unsupported (slots, nmax)")
     res["stats"] = dict(exec=dict(zip(PHASES, stats[0:4])), lanes=dict(zip(PHASES, stats[4:8])), trips=stats[8])

@@ -46,7 +46,7 @@ void run(const OctDev& T, int depth, const PolyRec* polys, const double* o, cons
             if (ray_steps && ph != OP_SF) for (int l = 0; l < cnt; ++l) ++ray_steps[p.U(OU_RAY, sel[l])];   // length of the ray's dependent chain of phase executions
             uint32_t nt[32];
             if (ph == OP_T) {
-                for (int l = 0; l < cnt; ++l) nt[l] = octw_test<true, SLOTS>(T, polys, p, sel[l], out, c);
+                for (int l = 0; l < cnt; ++l) nt[l] = octw_test<CHAIN, true, SLOTS>(T, polys, p, sel[l], order, out, c);
             } else if (ph == OP_C) {
                 for (int l = 0; l < cnt; ++l) nt[l] = octw_cull<true, SLOTS>(T, p, sel[l], c);
             } else if (ph == OP_G) {
@@ -85,7 +85,8 @@ extern "C" int oct_emu(const double* verts, const double* normals, const int32_t
                        const double* o, const double* d, const int32_t* o1, const int32_t* o2, int64_t N, int chain, int order,
                        double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
                        int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
-                       int slots, int nmax, int n_warps, int regular_ok, double* stats, unsigned long long* counters, uint32_t* ray_steps) {
+                       int slots, int nmax, int n_warps, int regular_ok, double* stats, unsigned long long* counters, uint32_t* ray_steps,
+                        double* ev_xyz, double* ev_uv /* chain: per-bounce X_Point / u, v rows, optional */) {
     std::vector<PolyRec> recs((size_t)P);
     std::vector<float> pbox6((size_t)P * 6);
     for (int64_t i = 0; i < P; ++i) {
@@ -113,7 +114,7 @@ extern "C" int oct_emu(const double* verts, const double* normals, const int32_t
     T.cbox = reinterpret_cast<const float4*>(pk.cbox.data()); T.gbox = reinterpret_cast<const float4*>(pk.gbox.data());
     T.pbox = pbox.data(); T.nbox = reinterpret_cast<const float4*>(pk.nbox.data());
     T.depth = depth; T.regular = (pk.regular && regular_ok) ? 1 : 0;
-    WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
+    WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr, ev_xyz, ev_uv };
     Stats st;
 #define RUN(S, M) if (slots == S && nmax == M) { if (chain) run<true, S, M>(T, depth, recs.data(), o, d, o1, o2, N, order, out, n_warps, st, counters, ray_steps); \
                                                  else run<false, S, M>(T, depth, recs.data(), o, d, o1, o2, N, order, out, n_warps, st, counters, ray_steps); ok = 1; }

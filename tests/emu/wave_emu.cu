@@ -107,7 +107,8 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
                         int chain, int order,
                         double* t, double* xyz, int32_t* pid, double* uv, double* omoved,
                         int32_t* ev_pid, double* ev_t, double* fin_o, double* fin_d, int32_t* nshots, unsigned long long* total_shots,
-                        int slots, int wmax, int n_warps, int wexit, double* stats, unsigned long long* counters) {
+                        int slots, int wmax, int n_warps, int wexit, double* stats, unsigned long long* counters,
+                        double* ev_xyz, double* ev_uv /* chain: per-bounce X_Point / u, v rows, optional */) {
     std::vector<PolyRec> recs((size_t)P);
     for (int64_t i = 0; i < P; ++i) {
         for (int k = 0; k < 12; ++k) recs[i].v[k] = verts[12 * i + k];
@@ -151,7 +152,7 @@ extern "C" int wave_emu(const double* verts, const double* normals, const int32_
         lbox[2 * k] = make_float4(lo[0], lo[1], lo[2], hare_u2f((uint32_t)i)); lbox[2 * k + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
     }
     g.lbox = lbox.data();
-    WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr };
+    WalkOut out = { t, xyz, pid, uv, omoved, ev_pid, ev_t, fin_o, fin_d, nshots, total_shots, nullptr, ev_xyz, ev_uv };
     Stats st;
 #define RUN(S, W) if (slots == S && wmax == W) { if (chain) run<true, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, wexit, st, counters); \
                                                  else run<false, S, W>(g, recs.data(), o, d, o1, o2, rid, N, order, out, n_warps, wexit, st, counters); ok = 1; }

@@ -255,6 +255,35 @@ def test_reflect_chain_octree(gpu):
     assert np.array_equal(got["ev_poly_id"], ref["ev_poly_id"]) and np.array_equal(got["ev_t"], ref["ev_t"])
 
 
+@pytest.mark.parametrize("kind,args,level,nchains", [("Voxel_Grid", (24,), "10k", 120_000), ("Octree", (6, 16), "10k", 40_000), ("KDTree", (14, 8), "2k", 8_000)])
+def test_reflect_chain_event_streams_carry_the_whole_x_event(gpu, kind, args, level, nchains):
+    """hare_reflect_chain_events: per-bounce X_Point and u, v rows next to Poly_id and t -- bit-equal to the oracle's chain, rows of
+    misses and of Shoots that never happened zero, and consistent with each other (the next segment starts at X_Point; t is its
+    length along the segment's direction)."""
+    mesh = meshes.hall(level)
+    T, To = _pair(gpu, mesh)
+    order = 12
+    o, d = rays_from_sources(nchains, meshes.sources(4), stream=12)     # Voxel_Grid: two pipelined chunks of 87 381 chains
+    o[::11] += np.array([60.0, -9.0, 2.0])                       # some chains start outside the model
+    part = getattr(gpu, kind)([T], *args)
+    ref = (ho.Voxel_Grid(To, args[0], mode="fast") if kind == "Voxel_Grid" else getattr(ho, kind)(To, *args)).reflect_chain(o, d, order, nthreads=8, points=True)
+    got = part.Reflect_Chain(o, d, order, points=True)
+    for k in ("ev_poly_id", "ev_t", "ev_xyz", "ev_uv", "nshots", "o", "d"):
+        assert np.array_equal(got[k], ref[k]), (kind, k)
+    hit = got["ev_poly_id"] >= 0
+    assert not got["ev_xyz"][~hit].any() and not got["ev_uv"][~hit].any()
+    if kind == "Voxel_Grid":
+        assert not got["ev_uv"].any()                               # Voxel_Grid.cs:487-488
+    else:
+        assert got["ev_uv"][hit].any()
+    # a chain that made all its Shoots ends where its last X_Point is
+    full = hit[:, -1]
+    assert full.any() and np.array_equal(got["o"][full], got["ev_xyz"][full, -1])
+    # only the streams asked for are touched: the plain call returns the same Poly_id / t
+    plain = part.Reflect_Chain(o, d, order)
+    assert np.array_equal(plain["ev_poly_id"], got["ev_poly_id"]) and np.array_equal(plain["ev_t"], got["ev_t"])
+
+
 # ---------------------------------------------------------------- size-independent properties at larger sizes
 def test_large_batch_properties(gpu):
     """2M rays on the 50k hall: closed mesh => (almost) every interior ray hits; the hit point lies on the

@@ -65,9 +65,9 @@ def test_octree_wave_chain_matches_oracle(hall10k):
     T, ta = hall10k
     oc = ho.Octree(T, 6, 16)
     o, d = rays_from_sources(1200, meshes.sources(4), stream=3)
-    ref = oc.reflect_chain(o, d, 10, nthreads=4)
+    ref = oc.reflect_chain(o, d, 10, nthreads=4, points=True)
     got = oct_emu.run(ta, oc.arrays(), o, d, chain=True, order=10, slots=64, nmax=4, n_warps=2)
-    for k in ("ev_poly_id", "ev_t", "o", "d", "nshots"):
+    for k in ("ev_poly_id", "ev_t", "ev_xyz", "ev_uv", "o", "d", "nshots"):     # ev_xyz / ev_uv: per-bounce X_Point and u, v rows
         assert np.array_equal(got[k], ref[k]), k
     assert int(got["total"][0]) == int(ref["nshots"].sum())
 
@@ -131,9 +131,9 @@ def test_kdtree_wave_chain_matches_oracle():
     T = ho.Topology.from_mesh(meshes.hall("2k"))
     kd = ho.KDTree(T, 14, 8)
     o, d = rays_from_sources(600, meshes.sources(4), stream=3)
-    ref = kd.reflect_chain(o, d, 8, nthreads=8)
+    ref = kd.reflect_chain(o, d, 8, nthreads=8, points=True)
     got = kd_emu.run(T.arrays(), kd.arrays(), o, d, chain=True, order=8, n_warps=2)
-    for k in ("ev_poly_id", "ev_t", "o", "d", "nshots"):
+    for k in ("ev_poly_id", "ev_t", "ev_xyz", "ev_uv", "o", "d", "nshots"):     # ev_xyz / ev_uv: per-bounce X_Point and u, v rows
         assert np.array_equal(got[k], ref[k]), k
 
 

@@ -50,9 +50,9 @@ def test_wave_chain_matches_oracle(hall, slots, wmax, warps):
     from tests.emu import wave_emu
     T, g, ta, gi, csr = hall
     o, d = rays_from_sources(1500, meshes.sources(4), stream=3)
-    ref = g.reflect_chain(o, d, 12, nthreads=4)
+    ref = g.reflect_chain(o, d, 12, nthreads=4, points=True)
     got = wave_emu.run(ta, gi, csr, o, d, chain=True, order=12, slots=slots, wmax=wmax, n_warps=warps)
-    for k in ("ev_poly_id", "ev_t", "o", "d", "nshots"):
+    for k in ("ev_poly_id", "ev_t", "ev_xyz", "ev_uv", "o", "d", "nshots"):     # ev_xyz / ev_uv: per-bounce X_Point and u, v rows
         assert np.array_equal(got[k], ref[k]), k
     assert int(got["total"][0]) == int(ref["nshots"].sum())
 
