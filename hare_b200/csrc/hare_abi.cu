@@ -1167,8 +1167,8 @@ struct ShootArgs {
 
 // Ray supply of a traversal launch of `total_warps` warps (RayFeed in vg_wave.cuh): block size and the counter the warps claim their
 // rays from, zeroed in stream order
-static int make_feed(int64_t N, int64_t total_warps, cudaStream_t st, RayFeedArgs* feed) {
-    feed->block = feed_block_for(N, total_warps);
+static int make_feed(int64_t N, int64_t total_warps, cudaStream_t st, RayFeedArgs* feed, int huge = HARE_FEED_BLOCK) {
+    feed->block = feed_block_for(N, total_warps, huge);
     feed->first = total_warps * feed->block;
     feed->ctr = nullptr;
     CK(cudaMallocAsync(reinterpret_cast<void**>(&feed->ctr), sizeof(unsigned long long), st));
@@ -1241,6 +1241,9 @@ static int launch_vg_walk(const VGrid& g, const PartDev& d, const double* o, con
 #ifndef HARE_OCTW_NMAX
 #define HARE_OCTW_NMAX 4
 #endif
+#ifndef HARE_OCTW_FEED_HUGE
+#define HARE_OCTW_FEED_HUGE 128   /* rays per RayFeed block for batches of ~39 M rays and more (100 M rays: 844 vs 829 Mrays/s with 64; 12.5 M: 708 vs 721) */
+#endif
 
 // Octree: per-warp wavefront scheduler over shared-memory ray pools (oct_wave.cuh), one CTA of HARE_OCTW_WARPS warps per SM.
 // The spilled traversal frames live in a scratch area allocated stream-ordered for this launch (24 bytes per slot and level).
@@ -1260,7 +1263,7 @@ static int launch_oct_wave2(const OctDev& t, const PartDev& d, const double* o, 
     CK(cudaMallocAsync(&scratch, nfr * (sizeof(double2) + sizeof(uint2)), st));
     F.ab = reinterpret_cast<double2*>(scratch); F.cq = reinterpret_cast<uint2*>(F.ab + nfr);
     RayFeedArgs feed;
-    int rc = make_feed(N, blocks * HARE_OCTW_WARPS, st, &feed);
+    int rc = make_feed(N, blocks * HARE_OCTW_WARPS, st, &feed, HARE_OCTW_FEED_HUGE);
     if (rc) { cudaFreeAsync(scratch, st); return rc; }
     k<<<(unsigned)blocks, threads, smem, st>>>(t, F, d.polys, o, dd, o1, o2, N, order, perm, feed, w);
     ++g_launches;

@@ -382,8 +382,11 @@ struct RayFeed {                    // warp-uniform, except b1: lane 0's until i
     long long b0, b1;               // ray number of the first ray of the open block / of the block in reserve
     int used;                       // rays taken from the open block (< block)
 };
-// rays per block for a batch of N rays on tw warps: HARE_FEED_BLOCK, 32 when that would leave fewer than eight blocks per warp
-HD int feed_block_for(long long N, long long tw) { return N >= tw * HARE_FEED_BLOCK * 8 ? HARE_FEED_BLOCK : 32; }
+// rays per block for a batch of N rays on tw warps: HARE_FEED_BLOCK; 32 when that would leave fewer than eight blocks per warp;
+// `huge` (a kernel's choice, >= HARE_FEED_BLOCK) when there are 256 or more
+HD int feed_block_for(long long N, long long tw, int huge = HARE_FEED_BLOCK) {
+    return N >= tw * HARE_FEED_BLOCK * 256 ? huge : (N >= tw * HARE_FEED_BLOCK * 8 ? HARE_FEED_BLOCK : 32);
+}
 // claim the next block (one lane per warp)
 HD long long feed_claim(const RayFeedArgs& A) {
 #if defined(__CUDA_ARCH__)

@@ -208,7 +208,8 @@ extern "C" void emu_ray_bin_keys(const double* o, const double* d, int64_t n, co
 // were answered with ray numbers >= N (in the kernels: every slot of its pool has gone to DONE).
 extern "C" long long emu_ray_feed(int64_t N, int64_t tw, uint64_t seed, uint32_t* counts) {
     unsigned long long ctr = 0;
-    const RayFeedArgs feed = { &ctr, tw * feed_block_for(N, tw), feed_block_for(N, tw) };
+    const int fb = feed_block_for(N, tw, 128);   // (the Octree launcher's choice for huge batches)
+    const RayFeedArgs feed = { &ctr, tw * fb, fb };
     std::vector<RayFeed> f((size_t)tw);
     std::vector<int> dry((size_t)tw, 0);
     for (int64_t w = 0; w < tw; ++w) { f[w] = RayFeed{ w * feed.block, 0, 0 }; f[w].b1 = feed_claim(feed); }
