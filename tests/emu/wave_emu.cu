@@ -230,3 +230,11 @@ extern "C" long long emu_ray_feed(int64_t N, int64_t tw, uint64_t seed, uint32_t
     }
     return feed.first + (long long)ctr;
 }
+
+// ---- the chunk schedule of hare_shoot_batch (schedule.hpp) -------------------------------------------------------------------
+#include "../../hare_b200/csrc/schedule.hpp"
+extern "C" int emu_shoot_schedule(int64_t n, int64_t* sizes, int cap) {
+    const std::vector<int64_t> v = shoot_schedule(n);
+    for (size_t k = 0; k < v.size() && (int)k < cap; ++k) sizes[k] = v[k];
+    return (int)v.size();
+}

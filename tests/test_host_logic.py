@@ -227,3 +227,28 @@ def test_sass_has_no_contracted_fp64_multiply_adds():
     assert len(seen) == 2
     for k in ("vg_wave_kernel", "oct_wave_kernel", "kd_wave_kernel"):
         assert any(k in p.split("\n", 1)[0] for p in parts), k
+
+
+def test_ray_order_and_sampling_helpers():
+    """harness/rays.py: the direction of a ray depends on its number only; 'source-major' hands every source one contiguous run of the
+    workload and a shard of it equals the same rays of the whole; sample_blocks / sample_rays pick evenly spaced runs that reach every
+    source and can be generated without the rest of the batch."""
+    from hare_b200.harness import rays_from_sources, sample_blocks, sample_rays, source_index
+    S = meshes.sources(8)
+    n = 100_003
+    oi, di = rays_from_sources(n, S, stream=3)
+    om, dm = rays_from_sources(n, S, stream=3, order="source-major", total=n)
+    assert np.array_equal(di, dm)
+    src = source_index(np.arange(n), 8, "source-major", n)
+    assert np.all(np.diff(src) >= 0) and set(src) == set(range(8)) and np.array_equal(om, S[src])
+    assert np.bincount(src).max() - np.bincount(src).min() <= 1
+    assert np.array_equal(oi, S[np.arange(n) % 8])
+    o2, d2 = rays_from_sources(30_001, S, stream=3, first=45_000, order="source-major", total=n)      # a rank's block
+    assert np.array_equal(o2, om[45_000:75_001]) and np.array_equal(d2, dm[45_000:75_001])
+    with pytest.raises(ValueError):
+        rays_from_sources(10, S, order="source-major")
+    idx = sample_blocks(n, 6_400)
+    assert len(idx) == 6_400 and np.all(np.diff(idx) > 0) and idx[-1] < n and set(src[idx]) == set(range(8))
+    assert np.array_equal(sample_blocks(50, 100), np.arange(50)) and np.array_equal(sample_blocks(1000, 10), np.arange(10))
+    i3, o3, d3 = sample_rays(n, 6_400, S, stream=3, order="source-major")
+    assert np.array_equal(i3, idx) and np.array_equal(o3, om[idx]) and np.array_equal(d3, dm[idx])

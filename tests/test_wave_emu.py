@@ -186,3 +186,25 @@ def test_ray_feed_hands_out_every_ray_exactly_once(n, tw):
         assert covered >= n
         assert np.all(counts[:n] == 1)
         assert covered <= n + tw * 128 * 4
+
+
+def test_shoot_batch_chunk_schedule_covers_the_batch():
+    """schedule.hpp: the chunks of a hare_shoot_batch share add up to the share, are never empty (for a non-empty share) nor larger
+    than the staging cap, start and end small (what is copied in first and out last overlaps with nothing) and are symmetric."""
+    import ctypes as C
+    from tests.emu import wave_emu
+    L = wave_emu.lib()
+    rng = np.random.default_rng(3)
+    sizes = np.zeros(4096, np.int64)
+    for n in [1, 2, 1000, 262_143, 262_144, 524_289, 1_000_000, 4_000_000, 12_500_000, 100_000_000, 4_294_967_295] + \
+             [int(x) for x in rng.integers(1, 600_000_000, 300)]:
+        k = L.emu_shoot_schedule(C.c_int64(n), sizes.ctypes.data_as(C.c_void_p), len(sizes))
+        v = sizes[:k]
+        assert 0 < k <= len(sizes) and int(v.sum()) == n
+        assert v.min() > 0 and v.max() <= (1 << 24)
+        assert v[0] <= max(1 << 20, n) and v[0] == v[-1] or k == 1
+        if n >= (1 << 24):
+            assert v[0] <= (1 << 20) and v[-1] <= (1 << 20)        # the un-overlapped copies stay small
+        h = (k - 1) // 2
+        assert h == 0 or np.abs(v[:h] - v[::-1][:h]).max() <= 1     # (the equal middle chunks differ by a ray)
+    assert L.emu_shoot_schedule(C.c_int64(0), sizes.ctypes.data_as(C.c_void_p), len(sizes)) == 1 and sizes[0] == 0
