@@ -8,10 +8,13 @@
 // of its exhaustive DFS order, which kd_dfs_before() reconstructs from the reference's own (untightened) node boxes, so
 // Poly_id, u and v match as well.
 //
-// The stack of pending far children lives in a per-slot scratch area in global memory (4 bytes per level, L2 resident): a
-// push is a store, a pop one load per finished leaf; the node being descended into stays in the slot.
+// The walk reads 4-wide records (KdWide, shoot.cuh): a node together with its (up to four) grandchildren, FP32 padded boxes, one
+// 128-byte fetch per two levels of the reference's binary tree; the four entries are ordered by entry parameter in registers (a
+// 5-comparator network).  The stack of pending entries lives in a per-slot scratch area in global memory (16-byte entries: node or
+// leaf list, entry parameter; 3 * (depth / 2 + 2) + 4 per slot, L2 resident): a push is a store, an entry a closer hit has overtaken
+// is dropped at pop time from its parameter alone; the record being descended into stays in the slot.
 //
-// Phases:  SF finish / fetch / set-up;  N descend until a reachable leaf with a non-empty list (<= N_MAX nodes per execution);
+// Phases:  SF finish / fetch / set-up;  N descend until a reachable leaf with a non-empty list (<= N_MAX records per execution);
 //          C cull the next (up to) eight leaf entries (poly_origin / duplicate skip, padded-box reject);  T one exact slow-path
 //          (u, v) Moller-Trumbore test, strict t < closestT.
 #pragma once
