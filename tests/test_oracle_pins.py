@@ -194,3 +194,43 @@ def test_more_than_four_sides_is_rejected():
     T = ho.Topology([0, 0, 0], [1, 1, 1])
     with pytest.raises(NotImplementedError):
         T.Add_Polygon(np.zeros((5, 3)))
+
+
+# ---------------------------------------------------------------- harness chains: the C++ oracle against the Python restatement
+@pytest.mark.parametrize("kind,args", [("Voxel_Grid", (6,)), ("Octree", (3, 4)), ("KDTree", (5, 4))])
+def test_chain_event_rows_match_python_restatement(kind, args):
+    """The specular chain is harness-defined: n = Normal[poly], k = 2*((dx*nx)+(dy*ny)+(dz*nz)), d' = d - k*n,
+    o' = X_Point, poly_origin1 = poly.  Run it bounce by bounce on the independent pure-Python Shoots and compare every row the C++
+    oracle's reflect_chain(points=True) reports: Poly_id, t, X_Point, u, v, the final ray and the number of Shoots."""
+    mesh = meshes.hall("tiny")
+    To = ho.Topology.from_mesh(mesh)
+    Tp = _py_topo(mesh)
+    order, n = 6, 60
+    o, d = rays_from_sources(n, meshes.sources(4), stream=21)
+    o[::7] += np.array([40.0, -5.0, 1.0])                         # some chains start outside the model
+    cpp = (ho.Voxel_Grid(To, args[0], mode="flat") if kind == "Voxel_Grid" else getattr(ho, kind)(To, *args)).reflect_chain(o, d, order, points=True)
+    part = getattr(hp, kind)([Tp], *args)
+    hits = 0
+    for i in range(n):
+        R = hp.Ray(*map(float, o[i]), *map(float, d[i]), Ray_ID=1)
+        o1, b = -1, 0
+        while b < order:
+            R.Ray_ID = (i * order + b) % 2147483646 + 1
+            hit, ev = part.Shoot(R, 0, o1)
+            row = (i, b)
+            assert cpp["ev_poly_id"][row] == ev.Poly_id and cpp["ev_t"][row] == ev.t, (kind, row)
+            X = ev.X_Point if hit else (0.0, 0.0, 0.0)
+            assert tuple(cpp["ev_xyz"][row]) == tuple(X) and tuple(cpp["ev_uv"][row]) == (ev.u, ev.v), (kind, row)
+            b += 1
+            if not hit:
+                break
+            hits += 1
+            N = Tp.Polys[ev.Poly_id][1]
+            k = 2 * ((R.dx * N[0]) + (R.dy * N[1]) + (R.dz * N[2]))
+            R.dx, R.dy, R.dz = R.dx - k * N[0], R.dy - k * N[1], R.dz - k * N[2]
+            R.x, R.y, R.z = X
+            o1 = ev.Poly_id
+        assert cpp["nshots"][i] == b
+        assert not cpp["ev_xyz"][i, b:].any() and not cpp["ev_uv"][i, b:].any() and np.all(cpp["ev_poly_id"][i, b:] == -3)
+        assert tuple(cpp["o"][i]) == (R.x, R.y, R.z) and tuple(cpp["d"][i]) == (R.dx, R.dy, R.dz)
+    assert hits > n * 2
