@@ -499,6 +499,26 @@ def test_q4_dda_tie_rule(gpu):
     assert int(got["counters"][0]) == int(ref["counters"][0])      # voxels entered: the same path through every tie
 
 
+def test_q3_epsilon_skirt_of_the_voxels_in_the_gpu_build(gpu):
+    """Voxel_Grid.cs:283-285: a polygon 0.4 mm beyond a voxel's nominal face is on that voxel's list, one 1.6 mm beyond it is not --
+    in the lists the GPU builds, which equal the oracle's."""
+    from tests.test_quirks import q3_mesh
+    mesh, obox, vd, ct = q3_mesh()
+    T, To = _pair(gpu, mesh)
+    ooff, opol = ho.Voxel_Grid(To, 10, mode="flat").csr()
+    iy = int((3.3 - obox[1]) / vd[1]); iz = int((1.5 - obox[2]) / vd[2])
+    for g in (gpu.Voxel_Grid([T], 10),):
+        off, pol = g.csr()
+        assert np.array_equal(off, ooff) and np.array_equal(pol, opol)
+        listed = lambda ix: set(int(p) for p in pol[off[(ix * int(ct[1]) + iy) * int(ct[2]) + iz]:off[(ix * int(ct[1]) + iy) * int(ct[2]) + iz + 1]])
+        assert {6, 7} <= listed(3) and 6 in listed(2) and 7 not in listed(2) and 6 not in listed(1)
+    # a ray through the squares from the x = 2 side meets the nearer one first, and the event is the oracle's
+    o = np.array([[obox[0] + 2.5 * vd[0], 3.3, 1.5]]); d = np.array([[1.0, 0.0, 0.0]])
+    got = gpu.Voxel_Grid([T], 10).Shoot_Batch(o, d); ref = ho.Voxel_Grid(To, 10, mode="flat").Shoot(o, d)
+    assert_events_equal(got, ref, uv=False, what="Q3")
+    assert int(got["poly_id"][0]) == 6
+
+
 def test_q11_octree_early_return_is_not_the_closest_hit(gpu):
     """"Octree - alt.cs":233-237: far-first pops + early return.  The table is closer, the Octree reports the floor; and the hall rays
     contain such cases too (octree.poly_id != the KDTree's global closest hit), all reproduced."""

@@ -147,3 +147,78 @@ def test_q14_kernel_replays():
                      (kd_emu.run(To.arrays(), kd.arrays(), o, d, n_warps=1), kd.Shoot(o, d))):
         for k in ("poly_id", "t", "xyz"):
             assert np.array_equal(got[k], ref[k]), k
+
+
+# ---------------------------------------------------------------- Q2, Q3: the two quirks that only had implicit coverage
+def _shoebox_with(extra_quads):
+    from hare_b200.harness import meshes
+    from hare_b200.harness.meshes import Mesh
+    box = meshes.shoebox()
+    verts = np.concatenate([box.verts, np.asarray(extra_quads, np.float64).reshape(-1, 4, 3)])
+    vcount = np.concatenate([box.vcount, np.full(len(extra_quads), 4, box.vcount.dtype)])
+    return Mesh(verts, vcount, box.minpt, box.maxpt, "shoebox+")
+
+
+def q3_mesh():
+    """The C1 shoebox plus two 20 cm squares parallel to the nominal face between voxels x = 2 and x = 3 of its 10^3 grid, 0.4 mm and
+    1.6 mm beyond it (polygons 6 and 7).  Returns (mesh, obox, voxel dims, counts) of that grid."""
+    from hare_b200.harness import meshes
+    g0 = ho.Voxel_Grid(ho.Topology.from_mesh(meshes.shoebox()), 10, mode="flat")
+    obox, vd, ct, _ = g0.info()
+    face = obox[0] + 3 * vd[0]
+    quads = []
+    for dx in (0.0004, 0.0016):
+        x = face + dx
+        quads.append([[x, 3.2, 1.4], [x, 3.4, 1.4], [x, 3.4, 1.6], [x, 3.2, 1.6]])
+    return _shoebox_with(quads), obox, vd, ct
+
+
+def test_q3_voxels_are_inflated_by_epsilon_on_every_face():
+    """Voxel_Grid.cs:283-285: a voxel's box is [(x*vd - eps) + omin, ((x+1)*vd + eps) + omin] with eps = 0.001 -- a polygon lying 0.4 mm
+    beyond a voxel's nominal face is still on that voxel's list, one lying 1.6 mm beyond it is not.  Checked on the C++ oracle, on the
+    pure-Python restatement and on the product's host-side expectation of the same lists (the GPU build is compared with these lists on
+    the halls by tests/test_gpu_parity.py)."""
+    from oracle import hare_oracle_py as hp
+    mesh, obox, vd, ct = q3_mesh()
+    To = ho.Topology.from_mesh(mesh)
+    g = ho.Voxel_Grid(To, 10, mode="flat")
+    obox2, vd2, ct2, _ = g.info()
+    assert np.array_equal(obox, obox2) and np.array_equal(vd, vd2)    # the squares lie inside the room: same grid
+    off, pol = g.csr()
+    iy = int((3.3 - obox[1]) / vd[1]); iz = int((1.5 - obox[2]) / vd[2])
+
+    def listed(ix):
+        c = (ix * int(ct[1]) + iy) * int(ct[2]) + iz
+        return set(int(p) for p in pol[off[c]:off[c + 1]])
+    near, far = 6, 7                                              # the two added quads (after the shoebox's six)
+    assert near in listed(3) and far in listed(3)                 # both lie in voxel 3
+    assert near in listed(2) and far not in listed(2)             # only the one inside the epsilon skirt is ALSO in voxel 2
+    assert near not in listed(1) and near not in listed(4)
+    # the fast (polygon-major) oracle build and the Python restatement agree
+    off2, pol2 = ho.Voxel_Grid(To, 10, mode="fast").csr()
+    assert np.array_equal(off, off2) and np.array_equal(pol, pol2)
+    Tp = hp.Topology(tuple(mesh.minpt), tuple(mesh.maxpt))
+    for i in range(mesh.P):
+        Tp.Add_Polygon([tuple(map(float, mesh.verts[i, k])) for k in range(mesh.vcount[i])])
+    Tp.Finish_Topology()
+    gp = hp.Voxel_Grid([Tp], 10)
+    for ix in (1, 2, 3, 4):
+        assert set(gp.Voxel_Inv[(ix, iy, iz)]) == listed(ix)
+
+
+def test_q2_mailbox_never_changes_a_result():
+    """Voxel_Grid.cs:478-480 / KDTree.cs:224-229: with unique non-zero Ray_IDs the mailbox only suppresses a second test of a polygon
+    by the SAME ray, which the strict `t < tmin` would reject anyway.  The oracle keeps the reference's mailbox; its results do not
+    depend on which rays went through a mailbox before (1 thread = one mailbox history, 8 threads = eight others, or ids in reverse),
+    and the kernels, which keep no mailbox at all, are compared with it bit for bit everywhere else."""
+    from hare_b200.harness import meshes, rays_from_sources
+    To = ho.Topology.from_mesh(meshes.hall("2k"))
+    o, d = rays_from_sources(6000, meshes.sources(4), stream=17)
+    ids = np.arange(1, len(o) + 1, dtype=np.int32)
+    for part in (ho.Voxel_Grid(To, 12, mode="fast"), ho.KDTree(To, 8, 8)):
+        a = part.Shoot(o, d, ray_id=ids, nthreads=1)
+        b = part.Shoot(o, d, ray_id=ids, nthreads=8)
+        c = part.Shoot(o, d, ray_id=ids[::-1].copy(), nthreads=3)
+        for k in ("poly_id", "t", "xyz", "uv"):
+            assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
+        assert (a["poly_id"] >= 0).mean() > 0.9
