@@ -252,3 +252,17 @@ def test_ray_order_and_sampling_helpers():
     assert np.array_equal(sample_blocks(50, 100), np.arange(50)) and np.array_equal(sample_blocks(1000, 10), np.arange(10))
     i3, o3, d3 = sample_rays(n, 6_400, S, stream=3, order="source-major")
     assert np.array_equal(i3, idx) and np.array_equal(o3, om[idx]) and np.array_equal(d3, dm[idx])
+
+
+def test_q8_q9_a_single_topology_per_partition(host_only):
+    """Q8 / Q9: the reference's Octree and KDTree overwrite `root` per topology and index Model[0] only ("Octree - alt.cs":63-88, 123;
+    KDTree.cs:71-87, 99), and Voxel_Grid's multi-topology bounds are inconsistent (Voxel_Grid.cs:67-72): the boundary takes
+    Model.Length == 1 and says so instead of guessing."""
+    T = hb.Topology.from_mesh(meshes.shoebox())
+    T2 = hb.Topology.from_mesh(meshes.shoebox())
+    for ctor in (lambda M: hb.Octree(M, 3, 2), lambda M: hb.KDTree(M, 4, 1), lambda M: hb.Voxel_Grid(M, 10)):
+        with pytest.raises(NotImplementedError, match="single Topology"):
+            ctor([T, T2])
+        with pytest.raises(NotImplementedError, match="single Topology"):
+            ctor([])
+    assert hb.Octree([T], 3, 2).info()["nodes"] > 1
