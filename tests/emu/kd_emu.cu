@@ -16,26 +16,36 @@ struct Stats { double exec[KP_COUNT] = {}, lanes[KP_COUNT] = {}, trips = 0; };
 template <bool CHAIN, int SLOTS, int N_MAX>
 void run(const KdDev& T, const PolyRec* polys, const double* o, const double* d, const int32_t* o1a, const int32_t* o2a, const int32_t* rid,
          long long N, int order, const WalkOut& out, int tw, Stats& st, unsigned long long* counters) {
-    std::vector<unsigned char> mem(KdPool<SLOTS>::STRIDE + 64);
+    // The simulated warps take turns, one trip each: their pools are in flight together and their claims on the launch's counter
+    // interleave, as on the device (where the order is arbitrary -- results must not depend on it).
+    struct Warp {
+        std::vector<unsigned char> mem; std::vector<uint4> stk;
+        KdPool<SLOTS> p; KdStacks S; RayFeed f; unsigned int shots = 0; bool done = false;
+    };
     const int sdepth = 3 * (T.depth / 2 + 2) + 4;
-    std::vector<uint4> stk((size_t)SLOTS * sdepth);
-    KdStacks S = { stk.data(), sdepth };
     CntT<true> c;
     unsigned long long total = 0;
-    unsigned long long feed_ctr = 0;   // the launch's claim counter: the simulated warps run one after the other, so the first one takes everything but the other warps' first blocks
+    unsigned long long feed_ctr = 0;
     const RayFeedArgs feed = { &feed_ctr, tw * feed_block_for(N, tw), feed_block_for(N, tw) };
+    std::vector<Warp> warps((size_t)tw);
     for (long long gw = 0; gw < tw; ++gw) {
-        KdPool<SLOTS> p;
-        p.bind(mem.data());
-        for (int s = 0; s < SLOTS; ++s) { p.U(KU_FLAGS, s) = KFL_NORAY; p.U(KU_LPOS, s) = 0; p.U(KU_LEND, s) = 0; p.tag[s] = (uint8_t)KP_SF; }
-        RayFeed f = { gw * feed.block, 0, 0 };
-        f.b1 = feed_claim(feed);
-        unsigned int shots = 0;
-        while (true) {
+        Warp& w = warps[(size_t)gw];
+        w.mem.resize(KdPool<SLOTS>::STRIDE + 64); w.stk.resize((size_t)SLOTS * sdepth);
+        w.S = KdStacks{ w.stk.data(), sdepth };
+        w.p.bind(w.mem.data());
+        for (int s = 0; s < SLOTS; ++s) { w.p.U(KU_FLAGS, s) = KFL_NORAY; w.p.U(KU_LPOS, s) = 0; w.p.U(KU_LEND, s) = 0; w.p.tag[s] = (uint8_t)KP_SF; }
+        w.f = RayFeed{ gw * feed.block, 0, 0 };
+        w.f.b1 = feed_claim(feed);
+    }
+    for (long long live = tw; live > 0;) {
+        for (long long gw = 0; gw < tw; ++gw) {
+            Warp& w = warps[(size_t)gw];
+            if (w.done) continue;
+            KdPool<SLOTS>& p = w.p; const KdStacks& S = w.S; RayFeed& f = w.f; unsigned int& shots = w.shots;
             int n[KP_COUNT] = {};
             for (int s = 0; s < SLOTS; ++s) if (p.tag[s] < KP_COUNT) ++n[p.tag[s]];
             const int ph = kd_pick(n);
-            if (ph < 0) break;
+            if (ph < 0) { w.done = true; --live; total += shots; continue; }
             int sel[32], cnt = 0;
             for (int s = 0; s < SLOTS && cnt < 32; ++s) if (p.tag[s] == ph) sel[cnt++] = s;
             st.exec[ph] += 1; st.lanes[ph] += cnt; st.trips += 1;
@@ -63,7 +73,6 @@ void run(const KdDev& T, const PolyRec* polys, const double* o, const double* d,
             }
             for (int l = 0; l < cnt; ++l) p.tag[sel[l]] = (uint8_t)nt[l];
         }
-        total += shots;
     }
     if (CHAIN && out.total_shots) *out.total_shots = total;
     if (counters) { counters[0] = c.cells; counters[1] = c.entries; counters[2] = c.tests; counters[3] = c.hits; }

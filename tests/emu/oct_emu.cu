@@ -2,7 +2,7 @@
 //
 // The per-slot phase functions of oct_wave.cuh (octw_finish / octw_fetch / octw_setup / octw_node / octw_group / octw_cull /
 // octw_test) and its policy (oct_pick, oct_tag) are `__host__ __device__`; this file compiles them for the host and drives
-// them with a sequential copy of the kernel's trip loop (one simulated warp at a time, 32 "lanes" one after the other).
+// them with a sequential copy of the kernel's trip loop (the simulated warps take turns trip by trip, 32 "lanes" one after the other).
 // The device arrays are built by the same pack_octree() the library uses (hare_b200/csrc/pack.hpp).  Nothing here is
 // shipped or measured; it never launches a kernel.
 #include <cmath>
@@ -21,25 +21,35 @@ struct Stats { double exec[OP_COUNT] = {}, lanes[OP_COUNT] = {}, trips = 0, nste
 template <bool CHAIN, int SLOTS, int N_MAX>
 void run(const OctDev& T, int depth, const PolyRec* polys, const double* o, const double* d, const int32_t* o1a, const int32_t* o2a,
          long long N, int order, const WalkOut& out, int tw, Stats& st, unsigned long long* counters, uint32_t* ray_steps) {
-    std::vector<unsigned char> mem(OctPool<SLOTS>::STRIDE + 64);
-    std::vector<double2> fab((size_t)SLOTS * (depth + 1)); std::vector<uint2> fcq((size_t)SLOTS * (depth + 1));
-    OctFrames F = { fab.data(), fcq.data(), depth + 1 };
+    // The simulated warps take turns, one trip each: their pools are in flight together and their claims on the launch's counter
+    // interleave, as on the device (where the order is arbitrary -- results must not depend on it).
+    struct Warp {
+        std::vector<unsigned char> mem; std::vector<double2> fab; std::vector<uint2> fcq;
+        OctPool<SLOTS> p; OctFrames F; RayFeed f; unsigned int shots = 0; bool done = false;
+    };
     CntT<true> c;
     unsigned long long total = 0;
-    unsigned long long feed_ctr = 0;   // the launch's claim counter: the simulated warps run one after the other, so the first one takes everything but the other warps' first blocks
+    unsigned long long feed_ctr = 0;
     const RayFeedArgs feed = { &feed_ctr, tw * feed_block_for(N, tw), feed_block_for(N, tw) };
+    std::vector<Warp> warps((size_t)tw);
     for (long long gw = 0; gw < tw; ++gw) {
-        OctPool<SLOTS> p;
-        p.bind(mem.data());
-        for (int s = 0; s < SLOTS; ++s) { p.U(OU_FLAGS, s) = OFL_NORAY; p.U(OU_LPOS, s) = 0; p.U(OU_LEND, s) = 0; p.U(OU_MASKS, s) = 0; p.tag[s] = (uint8_t)OP_SF; }
-        RayFeed f = { gw * feed.block, 0, 0 };
-        f.b1 = feed_claim(feed);
-        unsigned int shots = 0;
-        while (true) {
+        Warp& w = warps[(size_t)gw];
+        w.mem.resize(OctPool<SLOTS>::STRIDE + 64); w.fab.resize((size_t)SLOTS * (depth + 1)); w.fcq.resize((size_t)SLOTS * (depth + 1));
+        w.F = OctFrames{ w.fab.data(), w.fcq.data(), depth + 1 };
+        w.p.bind(w.mem.data());
+        for (int s = 0; s < SLOTS; ++s) { w.p.U(OU_FLAGS, s) = OFL_NORAY; w.p.U(OU_LPOS, s) = 0; w.p.U(OU_LEND, s) = 0; w.p.U(OU_MASKS, s) = 0; w.p.tag[s] = (uint8_t)OP_SF; }
+        w.f = RayFeed{ gw * feed.block, 0, 0 };
+        w.f.b1 = feed_claim(feed);
+    }
+    for (long long live = tw; live > 0;) {
+        for (long long gw = 0; gw < tw; ++gw) {
+            Warp& w = warps[(size_t)gw];
+            if (w.done) continue;
+            OctPool<SLOTS>& p = w.p; const OctFrames& F = w.F; RayFeed& f = w.f; unsigned int& shots = w.shots;
             int n[OP_COUNT] = {};
             for (int s = 0; s < SLOTS; ++s) if (p.tag[s] < OP_COUNT) ++n[p.tag[s]];
             const int ph = oct_pick(n);
-            if (ph < 0) break;
+            if (ph < 0) { w.done = true; --live; total += shots; continue; }
             int sel[32], cnt = 0;
             for (int s = 0; s < SLOTS && cnt < 32; ++s) if (p.tag[s] == ph) sel[cnt++] = s;
             st.exec[ph] += 1; st.lanes[ph] += cnt; st.trips += 1;
@@ -70,7 +80,6 @@ void run(const OctDev& T, int depth, const PolyRec* polys, const double* o, cons
             }
             for (int l = 0; l < cnt; ++l) p.tag[sel[l]] = (uint8_t)nt[l];
         }
-        total += shots;
     }
     if (CHAIN && out.total_shots) *out.total_shots = total;
     if (counters) { counters[0] = c.cells; counters[1] = c.entries; counters[2] = c.tests; counters[3] = c.hits; }

@@ -2,8 +2,8 @@
 //
 // The per-slot phase functions of vg_wave.cuh (wave_finish / wave_fetch / wave_setup / wave_walk / wave_cull /
 // wave_test) and its policy (wave_pick, wave_tag, the RayFeed) are `__host__ __device__`; this file compiles
-// them for the host and drives them with a sequential copy of the kernel's trip loop (one simulated warp at a
-// time, 32 "lanes" run one after the other).  It lets the CPU test-suite check the state machine against the
+// them for the host and drives them with a sequential copy of the kernel's trip loop (the simulated warps take
+// turns trip by trip, 32 "lanes" run one after the other).  It lets the CPU test-suite check the state machine against the
 // oracle without a GPU, and reports how many lanes each phase execution would keep busy.
 // Nothing here is shipped or measured; it never launches a kernel.
 #include <cmath>
@@ -22,24 +22,35 @@ struct Stats { double exec[4] = { 0, 0, 0, 0 }, lanes[4] = { 0, 0, 0, 0 }, wstep
 template <bool CHAIN, int SLOTS, int W_MAX>
 void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d, const int32_t* o1a, const int32_t* o2a,
          const int32_t* rid, long long N, int order, const WalkOut& out, int tw, int wexit, Stats& st, unsigned long long* counters) {
-    std::vector<unsigned char> mem(WavePool<SLOTS>::STRIDE + 64);
+    // The simulated warps take turns, one trip each: their pools are in flight together and their claims on the launch's counter
+    // interleave, as on the device (where the order is arbitrary -- results must not depend on it).
+    struct Warp {
+        std::vector<unsigned char> mem;
+        WavePool<SLOTS> p; RayFeed f; unsigned int shots = 0; bool done = false;
+    };
     CntT<true> c;
     const WaveGeom wg = wave_geom(g);
     unsigned long long total = 0;
-    unsigned long long feed_ctr = 0;   // the launch's claim counter: the simulated warps run one after the other, so the first one takes everything but the other warps' first blocks
+    unsigned long long feed_ctr = 0;
     const RayFeedArgs feed = { &feed_ctr, tw * feed_block_for(N, tw), feed_block_for(N, tw) };
+    std::vector<Warp> warps((size_t)tw);
     for (long long gw = 0; gw < tw; ++gw) {
-        WavePool<SLOTS> p;
-        p.bind(mem.data());
-        for (int s = 0; s < SLOTS; ++s) { p.U(U_FLAGS, s) = WF_NORAY; p.U(U_LPOS, s) = 0; p.U(U_LEND, s) = 0; p.tag[s] = (uint8_t)PH_SF; }
-        RayFeed f = { gw * feed.block, 0, 0 };
-        f.b1 = feed_claim(feed);
-        unsigned int shots = 0;
-        while (true) {
+        Warp& w = warps[(size_t)gw];
+        w.mem.resize(WavePool<SLOTS>::STRIDE + 64);
+        w.p.bind(w.mem.data());
+        for (int s = 0; s < SLOTS; ++s) { w.p.U(U_FLAGS, s) = WF_NORAY; w.p.U(U_LPOS, s) = 0; w.p.U(U_LEND, s) = 0; w.p.tag[s] = (uint8_t)PH_SF; }
+        w.f = RayFeed{ gw * feed.block, 0, 0 };
+        w.f.b1 = feed_claim(feed);
+    }
+    for (long long live = tw; live > 0;) {
+        for (long long gw = 0; gw < tw; ++gw) {
+            Warp& w = warps[(size_t)gw];
+            if (w.done) continue;
+            WavePool<SLOTS>& p = w.p; RayFeed& f = w.f; unsigned int& shots = w.shots;
             int n[PH_COUNT] = { 0, 0, 0, 0 };
             for (int s = 0; s < SLOTS; ++s) if (p.tag[s] < PH_COUNT) ++n[p.tag[s]];
             const int ph = wave_pick(n);
-            if (ph < 0) break;
+            if (ph < 0) { w.done = true; --live; total += shots; continue; }
             // the kernel ranks group 0 (slots 0..31) before group 1, lane order inside a group = slot order
             int sel[32], cnt = 0;
             for (int s = 0; s < SLOTS && cnt < 32; ++s) if (p.tag[s] == ph) sel[cnt++] = s;
@@ -91,7 +102,6 @@ void run(const VGrid& g, const PolyRec* polys, const double* o, const double* d,
             }
             for (int l = 0; l < cnt; ++l) p.tag[sel[l]] = (uint8_t)nt[l];
         }
-        total += shots;
     }
     if (CHAIN && out.total_shots) *out.total_shots = total;
     if (counters) { counters[0] = c.cells; counters[1] = c.entries; counters[2] = c.tests; counters[3] = c.hits; }
